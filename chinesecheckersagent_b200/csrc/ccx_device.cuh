@@ -1,0 +1,296 @@
+// ccx_device.cuh — device-side building blocks shared by every kernel: bitboard shifts, long-jump
+// flood fill (board.py:139-211), move application (board.py:226-250), win test (board.py:89-111),
+// Philox4x32-10.  sm_100a only.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// Every per-game routine is __host__ __device__ so that tests/hostcheck can instantiate the very same
+// source on the CPU and compare it with the oracle where no GPU exists (test-only; libccx.so has no
+// host compute path).
+#define CCX_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define ccx_popc(x) __popc(x)
+#define ccx_popcll(x) __popcll(x)
+#define ccx_umulhi(a, b) __umulhi((a), (b))
+#define ccx_clz(x) __clz(x)
+#define ccx_ffs(x) __ffs(x)
+#else
+#define ccx_popc(x) __builtin_popcount(x)
+#define ccx_popcll(x) __builtin_popcountll(x)
+#define ccx_umulhi(a, b) ((u32)(((u64)(u32)(a) * (u64)(u32)(b)) >> 32))
+#define ccx_clz(x) ((x) ? __builtin_clz(x) : 32)
+#define ccx_ffs(x) __builtin_ffs(x)
+#endif
+
+// 7x7 board in a 64-bit word with row stride 8: bit = 8*r + c.  Column 7 and row 7 are guard bits.
+#define CCX_VALID 0x007F7F7F7F7F7F7FULL
+// board.py:96-111: player 1 wins on diagonals k=4,5,6 -> (0,4)(1,5)(2,6)(0,5)(1,6)(0,6)
+#define CCX_TARGET_P1 ((1ULL << 4) | (1ULL << 5) | (1ULL << 6) | (1ULL << 13) | (1ULL << 14) | (1ULL << 22))
+// player 2 wins on diagonals -4,-5,-6 -> (4,0)(5,1)(6,2)(5,0)(6,1)(6,0)
+#define CCX_TARGET_P2 ((1ULL << 32) | (1ULL << 40) | (1ULL << 41) | (1ULL << 48) | (1ULL << 49) | (1ULL << 50))
+// Board() start position (board.py:20-26, 42-46)
+#define CCX_START_OCC1 ((1ULL << 48) | (1ULL << 40) | (1ULL << 49) | (1ULL << 32) | (1ULL << 41) | (1ULL << 50))
+#define CCX_START_OCC2 ((1ULL << 6) | (1ULL << 14) | (1ULL << 5) | (1ULL << 22) | (1ULL << 13) | (1ULL << 4))
+#define CCX_START_CELLS1 (48ULL | (40ULL << 8) | (49ULL << 16) | (32ULL << 24) | (41ULL << 32) | (50ULL << 40))
+#define CCX_START_CELLS2 (6ULL | (14ULL << 8) | (5ULL << 16) | (22ULL << 24) | (13ULL << 32) | (4ULL << 40))
+#define CCX_START_META 0x00000000FFFFFFFFULL
+#define CCX_HIST_EMPTY 0xFFFFFFFFFFFFFFFFULL
+
+// board.py:33-40 direction order: N(-1,0) E(0,+1) SE(+1,+1) S(+1,0) W(0,-1) NW(-1,-1)
+template <int D> CCX_HD u64 shd(u64 x)
+{
+    if (D == 0) return x >> 8;
+    if (D == 1) return x << 1;
+    if (D == 2) return x << 9;
+    if (D == 3) return x << 8;
+    if (D == 4) return x >> 1;
+    return x >> 9;
+}
+
+// One flood-fill round in direction D: all landings of mirror jumps (board.py:172-201) from the
+// frontier set F.  `occ` excludes the moving checker (board.py:158), `empty` = ~occ & VALID.
+// A jump over a pivot at distance s needs cells 1..s-1 empty, cell s occupied, cells s+1..2s empty.
+template <int D> CCX_HD u64 jump_dir(u64 F, u64 occ, u64 empty)
+{
+    u64 a1 = shd<D>(F);
+    u64 L = shd<D>(a1 & occ) & empty;                                   // s = 1
+    u64 m1 = a1 & empty;
+    u64 a2 = shd<D>(m1);
+    L |= shd<D>(shd<D>(a2 & occ) & empty) & empty;                      // s = 2
+    u64 m2 = a2 & empty;
+    u64 a3 = shd<D>(m2);
+    L |= shd<D>(shd<D>(shd<D>(a3 & occ) & empty) & empty) & empty;      // s = 3 (edge to edge on 7x7)
+    return L;
+}
+
+CCX_HD u64 jump_round(u64 F, u64 occ, u64 empty)
+{
+    return jump_dir<0>(F, occ, empty) | jump_dir<1>(F, occ, empty) | jump_dir<2>(F, occ, empty) |
+           jump_dir<3>(F, occ, empty) | jump_dir<4>(F, occ, empty) | jump_dir<5>(F, occ, empty);
+}
+
+CCX_HD u64 neighbours(u64 o)
+{
+    return shd<0>(o) | shd<1>(o) | shd<2>(o) | shd<3>(o) | shd<4>(o) | shd<5>(o);
+}
+
+// Board.get_valid_moves for the side owning `cells` (board.py:215-222).  dest[id] = walks | jump closure.
+// Jump parity lemma: jump landings keep (row&1, col&1) of the origin, walk cells do
+// not, so the reference's pre-marking of walk cells (board.py:148,155) never prunes a jump chain and
+// the legal set is exactly walks ∪ transitive closure.
+// The six flood fills run as ONE loop whose body is a single closure round of the thread's current
+// checker; a thread that finishes a checker moves on to its next one inside the same loop, so a warp
+// iterates max_lanes(sum_checkers rounds) times instead of sum_checkers(max_lanes rounds).
+CCX_HD void movegen(u64 occ_all, u64 cells, u64 (&dest)[6])
+{
+#pragma unroll
+    for (int k = 0; k < 6; k++) dest[k] = 0;
+    int id = 0;
+    u64 o = 1ULL << (cells & 0xFF);
+    u64 occ = occ_all & ~o;
+    u64 empty = ~occ & CCX_VALID;
+    u64 walks = neighbours(o) & empty;
+    u64 F = o, reach = 0;
+    for (;;) {
+        u64 nw = jump_round(F, occ, empty) & ~(reach | o);
+        reach |= nw;
+        F = nw;
+        if (F == 0) {
+            u64 d = walks | reach;
+#pragma unroll
+            for (int k = 0; k < 6; k++) if (id == k) dest[k] = d;
+            if (++id == 6) break;
+            o = 1ULL << ((cells >> (8 * id)) & 0xFF);
+            occ = occ_all & ~o;
+            empty = ~occ & CCX_VALID;
+            walks = neighbours(o) & empty;
+            F = o;
+            reach = 0;
+        }
+    }
+}
+
+// k-th (0-based) set bit of m, ascending; requires k < popc(m)
+CCX_HD int select64(u64 m, u32 k)
+{
+    u32 lo = (u32)m, hi = (u32)(m >> 32);
+    u32 c = ccx_popc(lo);
+    u32 w = lo; int base = 0;
+    if (k >= c) { w = hi; base = 32; k -= c; }
+    c = ccx_popc(w & 0xFFFFu); if (k >= c) { w >>= 16; base += 16; k -= c; }
+    c = ccx_popc(w & 0xFFu);   if (k >= c) { w >>= 8;  base += 8;  k -= c; }
+    c = ccx_popc(w & 0xFu);    if (k >= c) { w >>= 4;  base += 4;  k -= c; }
+    c = ccx_popc(w & 0x3u);    if (k >= c) { w >>= 2;  base += 2;  k -= c; }
+    c = w & 1u;              if (k >= c) { base += 1; }
+    return base;
+}
+
+CCX_HD int check_win(u64 occ1, u64 occ2)      // board.py:89-111
+{
+    if ((occ1 & CCX_TARGET_P1) == CCX_TARGET_P1) return 1;
+    if ((occ2 & CCX_TARGET_P2) == CCX_TARGET_P2) return 2;
+    return 0;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); key = seed, counter = (c0, c1, game id lo, game id hi)
+struct Philox4 { u32 x, y, z, w; };
+CCX_HD Philox4 philox4x32_10(u32 k0, u32 k1, u32 c0, u32 c1, u32 c2, u32 c3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        u32 h0 = ccx_umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        u32 h1 = ccx_umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        u32 n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 o = {c0, c1, c2, c3};
+    return o;
+}
+
+// The per-game record the env kernels keep in registers, from the side to move's point of view.
+struct Game {
+    u64 occ_me, occ_op, cells_me, cells_op, meta;
+};
+
+// Board.place for checker `id` of the side to move (board.py:226-250): occupancy swap, id->cell
+// rewrite in place (:235-238), last-two-moves shift (:246-248), ply++, side flip.
+CCX_HD void apply_move(Game &g, int id, int from, int to)
+{
+    g.occ_me ^= (1ULL << from) | (1ULL << to);
+    g.cells_me = (g.cells_me & ~(0xFFULL << (8 * id))) | ((u64)to << (8 * id));
+    u64 meta = g.meta;
+    u64 ply = ((meta >> 32) + 1) & 0xFFFF;
+    g.meta = (meta & 0xFFFF000000000000ULL) ^ (1ULL << 48) | (ply << 32) | ((meta & 0xFFFF) << 16) |
+             (u64)from | ((u64)to << 8);
+    u64 t;
+    t = g.occ_me; g.occ_me = g.occ_op; g.occ_op = t;
+    t = g.cells_me; g.cells_me = g.cells_op; g.cells_op = t;
+}
+
+CCX_HD void push_hist(u64 &lo, u64 &hi, int to)     // board.py:246-248 (destinations only)
+{
+    hi = (hi << 8) | (lo >> 56);
+    lo = (lo << 8) | (u64)to;
+}
+
+CCX_HD int level_of(int cell) { return (cell >> 3) - (cell & 7) + 6; }   // board_utils.py:3-7: human row - 1
+
+CCX_HD int winner_of(const Game &g)     // check_win in absolute player numbering
+{
+    bool p2 = (g.meta >> 48) & 1;
+    return check_win(p2 ? g.occ_op : g.occ_me, p2 ? g.occ_me : g.occ_op);
+}
+
+CCX_HD void reset_start(Game &g)
+{
+    g.occ_me = CCX_START_OCC1; g.occ_op = CCX_START_OCC2;
+    g.cells_me = CCX_START_CELLS1; g.cells_op = CCX_START_CELLS2;
+    g.meta = CCX_START_META;
+}
+
+// selfplay.make_random_move's choice (selfplay.py:93-98) from two 32-bit random words; returns the
+// checker id, fills from/to.  Requires at least one non-empty mask.
+CCX_HD int pick_random(const Game &g, const u64 (&dest)[6], u32 nonempty, u32 r0, u32 r1, int &from, int &to)
+{
+    int j = (int)ccx_umulhi(r0, nonempty);
+    int id = 0, rank = 0; u64 m = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {         // j-th checker (id order) that can move
+        bool ne = dest[k] != 0;
+        if (ne && rank == j) { id = k; m = dest[k]; }
+        rank += ne;
+    }
+    to = select64(m, ccx_umulhi(r1, (u32)ccx_popcll(m)));
+    from = (int)((g.cells_me >> (8 * id)) & 0xFF);
+    return id;
+}
+
+// cells of one diagonal level l = r - c + 6 (human row l + 1)
+CCX_HD u64 diag_mask(int l)
+{
+    const u64 D0 = 0x0040201008040201ULL;            // bits 9r, r = 0..6
+    int k = 6 - l;                                   // c = r + k
+    if (k >= 0) return (D0 << k) & ((1ULL << (8 * (7 - k))) - 1ULL) & CCX_VALID;
+    return (D0 << (8 * (-k))) & CCX_VALID;
+}
+
+// GreedyPlayer.decide_move's filtered_best_moves (player.py:99-118) as per-checker destination masks;
+// returns the number of candidates.  dist = rows advanced (player.py:103-105); best_moves = max dist;
+// last_checker = rearmost start row among them (:113); keep best moves starting on that row (:115).
+CCX_HD int greedy_candidates(const Game &g, const u64 (&dest)[6], u64 (&cand)[6])
+{
+    bool p2 = (g.meta >> 48) & 1;
+    int dist[6], start[6];
+    int max_dist = -100;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        u32 levels = 0;
+#pragma unroll
+        for (int l = 0; l < 13; l++) {
+            const u64 dm = diag_mask(l);          // constant-folded after unrolling
+            levels |= (dest[k] & dm) ? (1u << l) : 0u;
+        }
+        start[k] = level_of((int)((g.cells_me >> (8 * k)) & 0xFF));
+        int best_end = p2 ? (31 - ccx_clz(levels)) : (ccx_ffs(levels) - 1);
+        dist[k] = levels ? (p2 ? best_end - start[k] : start[k] - best_end) : -100;
+        max_dist = dist[k] > max_dist ? dist[k] : max_dist;
+    }
+    int s_star = p2 ? 100 : -100;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (dist[k] == max_dist) s_star = p2 ? (start[k] < s_star ? start[k] : s_star) : (start[k] > s_star ? start[k] : s_star);
+    int total = 0;
+    if (max_dist == -100) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cand[k] = 0;
+        return 0;
+    }
+    u64 end_mask = diag_mask(p2 ? s_star + max_dist : s_star - max_dist);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        cand[k] = (dist[k] == max_dist && start[k] == s_star) ? (dest[k] & end_mask) : 0;
+        total += ccx_popcll(cand[k]);
+    }
+    return total;
+}
+
+// uniform pick among the candidates in canonical order (checker id, then ascending cell) — player.py:121
+CCX_HD int pick_candidate(const Game &g, const u64 (&cand)[6], int total, u32 r0, int &from, int &to)
+{
+    int pick = (int)ccx_umulhi(r0, (u32)total);
+    int id = 0; u64 m = 0; int base = 0; bool found = false;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        int c = ccx_popcll(cand[k]);
+        if (!found && pick < base + c) { id = k; m = cand[k]; pick -= base; found = true; }
+        base += c;
+    }
+    to = select64(m, (u32)pick);
+    from = (int)((g.cells_me >> (8 * id)) & 0xFF);
+    return id;
+}
+
+// game.py:73-82: with 16 stored destinations, the mover's are every second one from the end
+CCX_HD bool repetition_stop(u64 lo, u64 hi)
+{
+    u64 seen = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        seen |= 1ULL << ((lo >> (16 * q)) & 63);
+        seen |= 1ULL << ((hi >> (16 * q)) & 63);
+    }
+    return ccx_popcll(seen) <= 3;                    // config.py:16 UNIQUE_DEST_LIMIT
+}
+
+CCX_HD u64 undo_in_cells(u64 cells, int from, int to)
+{
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (((cells >> (8 * k)) & 0xFF) == (u64)to) cells = (cells & ~(0xFFULL << (8 * k))) | ((u64)from << (8 * k));
+    return cells;
+}

@@ -1,0 +1,534 @@
+// ccx_env.cu — env kernels (movegen / apply / win / random + greedy stepping / plane encoder) and the
+// handle part of the C-ABI declared in include/ccx.h.  Hand-written for sm_100a; one thread per game,
+// SoA words so that a warp's loads and stores are 256-byte contiguous.
+#include <cuda_bf16.h>
+#include <new>
+#include "ccx_device.cuh"
+#include "ccx_internal.h"
+
+#define ENV_THREADS 128
+
+// --------------------------------------------------------------------------------------------------
+// state load / store (side-to-move relative)
+
+__device__ __forceinline__ Game load_game(const u64 *__restrict__ st, int64_t n, int64_t i)
+{
+    u64 occ1 = st[0 * n + i], occ2 = st[1 * n + i], c1 = st[2 * n + i], c2 = st[3 * n + i];
+    Game g;
+    g.meta = st[4 * n + i];
+    bool p2 = (g.meta >> 48) & 1;
+    g.occ_me = p2 ? occ2 : occ1; g.occ_op = p2 ? occ1 : occ2;
+    g.cells_me = p2 ? c2 : c1;   g.cells_op = p2 ? c1 : c2;
+    return g;
+}
+
+__device__ __forceinline__ void store_game(u64 *__restrict__ st, int64_t n, int64_t i, const Game &g)
+{
+    bool p2 = (g.meta >> 48) & 1;
+    st[0 * n + i] = p2 ? g.occ_op : g.occ_me;
+    st[1 * n + i] = p2 ? g.occ_me : g.occ_op;
+    st[2 * n + i] = p2 ? g.cells_op : g.cells_me;
+    st[3 * n + i] = p2 ? g.cells_me : g.cells_op;
+    st[4 * n + i] = g.meta;
+}
+
+// --------------------------------------------------------------------------------------------------
+// K0 reset  (board.py:10-57, 61-85)
+
+__global__ void __launch_bounds__(ENV_THREADS)
+k_reset(u64 *__restrict__ st, int64_t n, int mode, u32 k0, u32 k1, int64_t gid0)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 occ[2] = {CCX_START_OCC1, CCX_START_OCC2}, cells[2] = {CCX_START_CELLS1, CCX_START_CELLS2};
+    if (mode == CCX_RESET_RANDOMISED) {
+        // 12 draws without replacement: the k-th free cell, k = mulhi(rnd, #free)  (board.py:69)
+        u64 gid = (u64)(gid0 + i);
+        u64 taken = 0;
+        occ[0] = occ[1] = cells[0] = cells[1] = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            Philox4 r = philox4x32_10(k0, k1, (u32)q, 2u, (u32)gid, (u32)(gid >> 32));
+            u32 rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int idx = q * 4 + j;
+                u32 k = __umulhi(rr[j], (u32)(49 - idx));
+                int cell = select64(~taken & CCX_VALID, k);
+                taken |= 1ULL << cell;
+                int pl = idx / 6, id = idx % 6;
+                occ[pl] |= 1ULL << cell;
+                cells[pl] |= (u64)cell << (8 * id);
+            }
+        }
+    }
+    st[0 * n + i] = occ[0]; st[1 * n + i] = occ[1];
+    st[2 * n + i] = cells[0]; st[3 * n + i] = cells[1];
+    st[4 * n + i] = CCX_START_META;
+    st[5 * n + i] = CCX_HIST_EMPTY; st[6 * n + i] = CCX_HIST_EMPTY;
+    st[7 * n + i] = 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// K1 movegen  (board.py:139-222)
+
+__global__ void __launch_bounds__(ENV_THREADS)
+k_movegen(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ masks)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Game g = load_game(st, n, i);
+    u64 dest[6];
+    movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+#pragma unroll
+    for (int k = 0; k < 6; k++) masks[k * n + i] = dest[k];
+}
+
+// --------------------------------------------------------------------------------------------------
+// K2/K3 apply + win  (board.py:226-250, 89-111)
+
+__global__ void __launch_bounds__(ENV_THREADS)
+k_apply(u64 *__restrict__ st, int64_t n, const uint8_t *__restrict__ from, const uint8_t *__restrict__ to,
+        uint8_t *__restrict__ winner)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Game g = load_game(st, n, i);
+    int f = from[i], t = to[i];
+    int id = 0;
+#pragma unroll
+    for (int k = 5; k >= 0; k--) if (((g.cells_me >> (8 * k)) & 0xFF) == (u64)f) id = k;   // board.py:235-238
+    apply_move(g, id, f, t);
+    store_game(st, n, i, g);
+    u64 lo = st[5 * n + i], hi = st[6 * n + i];
+    push_hist(lo, hi, t);
+    st[5 * n + i] = lo; st[6 * n + i] = hi;
+    winner[i] = (uint8_t)winner_of(g);
+}
+
+__global__ void __launch_bounds__(ENV_THREADS)
+k_info(const u64 *__restrict__ st, int64_t n, int16_t *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 occ1 = st[0 * n + i], occ2 = st[1 * n + i], c1 = st[2 * n + i], c2 = st[3 * n + i];
+    int d1 = 70, d2 = -14;                                     // config.py:13-14, board.py:270-288
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        d1 -= level_of((int)((c1 >> (8 * k)) & 0xFF)) + 1;
+        d2 += level_of((int)((c2 >> (8 * k)) & 0xFF)) + 1;
+    }
+    out[i * 5 + 0] = (int16_t)check_win(occ1, occ2);
+    out[i * 5 + 1] = (int16_t)__popcll(occ1 & CCX_TARGET_P1);  // board.py:254-266
+    out[i * 5 + 2] = (int16_t)__popcll(occ2 & CCX_TARGET_P2);
+    out[i * 5 + 3] = (int16_t)d1;
+    out[i * 5 + 4] = (int16_t)d2;
+}
+
+// --------------------------------------------------------------------------------------------------
+// fused random-legal env step  (selfplay.py:83-104 + board.py:226-250 + board.py:89-111)
+
+template <bool TRACE>
+__global__ void __launch_bounds__(ENV_THREADS)
+k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies,
+              u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Game g = load_game(st, n, i);
+    u64 gid = (u64)(gid0 + i);
+    u32 w1 = 0, w2 = 0;
+    for (int t = 0; t < plies; t++) {
+        u64 dest[6];
+        movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+        u32 nonempty = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) nonempty += dest[k] != 0;
+        u64 *row = nullptr;
+        if (TRACE && i < trace_games) {
+            row = trace + ((int64_t)t * trace_games + i) * CCX_TRACE_WORDS;
+            bool p2 = (g.meta >> 48) & 1;
+            row[0] = p2 ? g.occ_op : g.occ_me; row[1] = p2 ? g.occ_me : g.occ_op;
+            row[2] = p2 ? g.cells_op : g.cells_me; row[3] = p2 ? g.cells_me : g.cells_op;
+            row[4] = g.meta & 0x00FFFFFFFFFFFFFFULL;
+#pragma unroll
+            for (int k = 0; k < 6; k++) row[5 + k] = dest[k];
+            row[11] = 0xFFULL | (0xFFULL << 8) | (0xFFULL << 24);
+        }
+        if (nonempty == 0) continue;          // cannot happen with 12 checkers on 49 cells; mirrors the oracle
+        Philox4 r = philox4x32_10(k0, k1, step0 + (u32)t, 0u, (u32)gid, (u32)(gid >> 32));
+        int from, to;
+        int id = pick_random(g, dest, nonempty, r.x, r.y, from, to);
+        apply_move(g, id, from, to);
+        int win = winner_of(g);
+        if (TRACE && row) row[11] = (u64)from | ((u64)to << 8) | ((u64)win << 16) | ((u64)id << 24);
+        if (win) {
+            w1 += win == 1; w2 += win == 2;
+            reset_start(g);
+        }
+    }
+    store_game(st, n, i, g);
+    if (w1) atomicAdd(&wins[0], (u64)w1);
+    if (w2) atomicAdd(&wins[1], (u64)w2);
+}
+
+// --------------------------------------------------------------------------------------------------
+// K4 greedy  (player.py:99-121, board_utils.py:3-7)
+
+__global__ void __launch_bounds__(ENV_THREADS)
+k_greedy_candidates(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ masks)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Game g = load_game(st, n, i);
+    u64 dest[6], cand[6];
+    movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+    greedy_candidates(g, dest, cand);
+#pragma unroll
+    for (int k = 0; k < 6; k++) masks[k * n + i] = cand[k];
+}
+
+// Game.start (game.py:58-100) with two GreedyPlayers
+__global__ void __launch_bounds__(ENV_THREADS)
+k_play_greedy(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, int max_plies,
+              u64 *__restrict__ counters)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 played = 0, w1 = 0, w2 = 0, rep = 0;
+    if (i < n) {
+        Game g = load_game(st, n, i);
+        u64 lo = st[5 * n + i], hi = st[6 * n + i];
+        u64 gid = (u64)(gid0 + i);
+        int status = (int)(g.meta >> 56);
+        for (int t = 0; status == CCX_ST_RUNNING && t < max_plies; t++) {
+            u64 dest[6], cand[6];
+            movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+            int total = greedy_candidates(g, dest, cand);
+            if (total == 0) { status = CCX_ST_NO_MOVES; break; }     // reference raises (player.py:113)
+            u32 ply = (u32)((g.meta >> 32) & 0xFFFF);
+            Philox4 r = philox4x32_10(k0, k1, ply, 1u, (u32)gid, (u32)(gid >> 32));
+            int from, to;
+            int id = pick_candidate(g, cand, total, r.x, from, to);   // player.py:121
+            apply_move(g, id, from, to);                              // game.py:65
+            push_hist(lo, hi, to);
+            played++;
+            int win = winner_of(g);
+            if (win) { status = win; w1 += win == 1; w2 += win == 2; break; }     // game.py:70-71
+            if (((g.meta >> 32) & 0xFFFF) >= 16 && repetition_stop(lo, hi)) { status = CCX_ST_REPETITION; rep++; }
+        }
+        g.meta = (g.meta & 0x00FFFFFFFFFFFFFFULL) | ((u64)status << 56);
+        store_game(st, n, i, g);
+        st[5 * n + i] = lo; st[6 * n + i] = hi;
+    }
+    if (counters) {
+        // warp-aggregated counters: one atomic per warp per counter
+        for (int off = 16; off; off >>= 1) {
+            played += __shfl_down_sync(0xFFFFFFFFu, played, off);
+            w1 += __shfl_down_sync(0xFFFFFFFFu, w1, off);
+            w2 += __shfl_down_sync(0xFFFFFFFFu, w2, off);
+            rep += __shfl_down_sync(0xFFFFFFFFu, rep, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (played) atomicAdd(&counters[0], (u64)played);
+            if (w1) atomicAdd(&counters[1], (u64)w1);
+            if (w2) atomicAdd(&counters[2], (u64)w2);
+            if (rep) atomicAdd(&counters[3], (u64)rep);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// K5 plane encoder  (utils.py:101-160): planes (2k, 2k+1) = id-labelled (mover, opponent) position k
+// plies ago, k < min(plies, 2) + 1; plane 6 = 1 iff player 2 is to move.  Each block stages G games'
+// (7,7,7) tensors in shared memory (scatter of 12 labels per history step) and streams them out with
+// 16-byte stores, so HBM sees one contiguous G*343*sizeof(T) write per block.
+
+template <typename T> __device__ __forceinline__ T enc_val(int v);
+template <> __device__ __forceinline__ uint8_t enc_val<uint8_t>(int v) { return (uint8_t)v; }
+template <> __device__ __forceinline__ float enc_val<float>(int v) { return (float)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 enc_val<__nv_bfloat16>(int v) { return __int2bfloat16_rn(v); }
+
+template <typename T, int G>
+__global__ void __launch_bounds__(ENV_THREADS)
+k_encode(const u64 *__restrict__ st, int64_t n, T *__restrict__ out)
+{
+    extern __shared__ uint4 smem_u4[];
+    T *tile = reinterpret_cast<T *>(smem_u4);
+    constexpr int TILE_BYTES = G * 343 * (int)sizeof(T);
+    static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 16-byte vectors");
+    int64_t g0 = (int64_t)blockIdx.x * G;
+    int games = (int)min((int64_t)G, n - g0);
+    for (int v = threadIdx.x; v < TILE_BYTES / 16; v += blockDim.x) smem_u4[v] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int lg = threadIdx.x; lg < games; lg += blockDim.x) {
+        int64_t i = g0 + lg;
+        u64 c1 = st[2 * n + i], c2 = st[3 * n + i], meta = st[4 * n + i];
+        bool p2 = (meta >> 48) & 1;
+        u64 cur = p2 ? c2 : c1, opp = p2 ? c1 : c2;
+        int plies = (int)((meta >> 32) & 0xFFFF);
+        T *t = tile + lg * 343;
+#pragma unroll
+        for (int h = 0; h < 3; h++) {
+            if (h == 1) { if (plies < 1) break; opp = undo_in_cells(opp, (int)(meta & 0xFF), (int)((meta >> 8) & 0xFF)); }
+            if (h == 2) { if (plies < 2) break; cur = undo_in_cells(cur, (int)((meta >> 16) & 0xFF), (int)((meta >> 24) & 0xFF)); }
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                int a = (int)((cur >> (8 * k)) & 0xFF), b = (int)((opp >> (8 * k)) & 0xFF);
+                t[((a >> 3) * 7 + (a & 7)) * 7 + 2 * h] = enc_val<T>(k + 1);
+                t[((b >> 3) * 7 + (b & 7)) * 7 + 2 * h + 1] = enc_val<T>(k + 1);
+            }
+        }
+        if (p2)
+            for (int c = 0; c < 49; c++) t[c * 7 + 6] = enc_val<T>(1);
+    }
+    __syncthreads();
+    char *dst = reinterpret_cast<char *>(out) + g0 * 343 * (int64_t)sizeof(T);
+    int bytes = games * 343 * (int)sizeof(T);
+    int nvec = bytes / 16;       // block base offset is a multiple of 16 bytes because TILE_BYTES is
+    uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) dst4[v] = smem_u4[v];
+    const char *src = reinterpret_cast<const char *>(smem_u4);
+    for (int b = nvec * 16 + threadIdx.x; b < bytes; b += blockDim.x) dst[b] = src[b];
+}
+
+// --------------------------------------------------------------------------------------------------
+// C-ABI
+
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" {
+
+int ccx_abi_version(void) { return CCX_ABI_VERSION; }
+
+const char *ccx_strerror(int code)
+{
+    switch (code) {
+    case CCX_OK: return "ok";
+    case CCX_ERR_ARG: return "invalid argument";
+    case CCX_ERR_CUDA: return "CUDA error (see ccx_last_cuda_error)";
+    case CCX_ERR_NOMEM: return "out of device memory";
+    case CCX_ERR_STATE: return "invalid handle state";
+    case CCX_ERR_UNSUPPORTED: return "unsupported";
+    case CCX_ERR_OVERFLOW: return "node pool overflow";
+    default: return "unknown error";
+    }
+}
+
+const char *ccx_last_cuda_error(const ccx_handle *h) { return h ? h->cuda_err : ""; }
+
+int ccx_create(int device_ordinal, ccx_handle **out)
+{
+    if (!out) return CCX_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device_ordinal < 0 || device_ordinal >= count) return e != cudaSuccess ? CCX_ERR_CUDA : CCX_ERR_ARG;
+    ccx_handle *h = new (std::nothrow) ccx_handle();
+    if (!h) return CCX_ERR_NOMEM;
+    h->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return CCX_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return CCX_OK;
+}
+
+int ccx_destroy(ccx_handle *h)
+{
+    if (!h) return CCX_OK;
+    cudaSetDevice(h->device);
+    ccx_net_free(h);
+    ccx_trees_free(h);
+    ccx_scratch *s[] = {&h->d_state, &h->d_aux0, &h->d_aux1, &h->d_aux2};
+    for (auto *p : s) if (p->ptr) cudaFree(p->ptr);
+    delete h;
+    return CCX_OK;
+}
+
+int ccx_set_stream(ccx_handle *h, void *cuda_stream)
+{
+    if (!h) return CCX_ERR_ARG;
+    h->stream = (cudaStream_t)cuda_stream;
+    return CCX_OK;
+}
+
+int ccx_synchronize(ccx_handle *h)
+{
+    if (!h) return CCX_ERR_ARG;
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CCX_OK;
+}
+
+int64_t ccx_launch_count(const ccx_handle *h) { return h ? h->launches : 0; }
+
+int ccx_reset(ccx_handle *h, int64_t n, uint64_t *state, int mode, uint64_t seed, int64_t game_id0)
+{
+    if (!h || n < 0 || (n && !state) || (mode != CCX_RESET_START && mode != CCX_RESET_RANDOMISED)) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_reset<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((u64 *)state, n, mode, (u32)seed, (u32)(seed >> 32), game_id0);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_movegen(ccx_handle *h, int64_t n, const uint64_t *state, uint64_t *dest_masks)
+{
+    if (!h || n < 0 || (n && (!state || !dest_masks))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_movegen<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((const u64 *)state, n, (u64 *)dest_masks);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_apply(ccx_handle *h, int64_t n, uint64_t *state, const uint8_t *from, const uint8_t *to, uint8_t *winner)
+{
+    if (!h || n < 0 || (n && (!state || !from || !to || !winner))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_apply<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((u64 *)state, n, from, to, winner);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_info(ccx_handle *h, int64_t n, const uint64_t *state, int16_t *out)
+{
+    if (!h || n < 0 || (n && (!state || !out))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_info<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((const u64 *)state, n, out);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0, uint64_t seed, uint32_t step0,
+                    int32_t plies, uint64_t *wins, uint64_t *trace, int64_t trace_games)
+{
+    if (!h || n < 0 || plies < 0 || (n && (!state || !wins)) || (trace_games > 0 && !trace)) return CCX_ERR_ARG;
+    if (n == 0 || plies == 0) return CCX_OK;
+    unsigned grid = blocks_for(n, ENV_THREADS);
+    if (trace && trace_games > 0)
+        k_step_random<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed, (u32)(seed >> 32),
+                                                                  step0, plies, (u64 *)wins, (u64 *)trace, trace_games);
+    else
+        k_step_random<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed, (u32)(seed >> 32),
+                                                                   step0, plies, (u64 *)wins, nullptr, 0);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_greedy_candidates(ccx_handle *h, int64_t n, const uint64_t *state, uint64_t *cand_masks)
+{
+    if (!h || n < 0 || (n && (!state || !cand_masks))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_greedy_candidates<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((const u64 *)state, n, (u64 *)cand_masks);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_play_greedy(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0, uint64_t seed, int32_t max_plies,
+                    uint64_t *counters)
+{
+    if (!h || n < 0 || max_plies < 0 || (n && !state)) return CCX_ERR_ARG;
+    if (n == 0 || max_plies == 0) return CCX_OK;
+    k_play_greedy<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed,
+                                                                              (u32)(seed >> 32), max_plies, (u64 *)counters);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_encode(ccx_handle *h, int64_t n, const uint64_t *state, void *out, int dtype)
+{
+    if (!h || n < 0 || (n && (!state || !out))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    constexpr int SMEM = 128 * 343;      // 43,904 B for every dtype (G = 128 / 64 / 32)
+    switch (dtype) {
+    case CCX_DTYPE_U8:
+        k_encode<uint8_t, 128><<<blocks_for(n, 128), ENV_THREADS, SMEM, h->stream>>>((const u64 *)state, n, (uint8_t *)out);
+        break;
+    case CCX_DTYPE_BF16:
+        k_encode<__nv_bfloat16, 64><<<blocks_for(n, 64), ENV_THREADS, SMEM, h->stream>>>((const u64 *)state, n, (__nv_bfloat16 *)out);
+        break;
+    case CCX_DTYPE_F32:
+        k_encode<float, 32><<<blocks_for(n, 32), ENV_THREADS, SMEM, h->stream>>>((const u64 *)state, n, (float *)out);
+        break;
+    default:
+        return CCX_ERR_ARG;
+    }
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+// ---- host-buffer variants ---------------------------------------------------------------------------
+
+int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host)
+{
+    if (!h || n < 0 || (n && (!state_host || !dest_masks_host))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    size_t sb = (size_t)n * CCX_STATE_WORDS * 8, mb = (size_t)n * 6 * 8;
+    int rc;
+    if ((rc = ccx_reserve(h, h->d_state, sb)) || (rc = ccx_reserve(h, h->d_aux0, mb))) return rc;
+    // only words 0-4 are read by movegen
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_state.ptr, state_host, (size_t)n * 5 * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ccx_movegen(h, n, (const uint64_t *)h->d_state.ptr, (uint64_t *)h->d_aux0.ptr))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(dest_masks_host, h->d_aux0.ptr, mb, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CCX_OK;
+}
+
+int ccx_apply_host(ccx_handle *h, int64_t n, uint64_t *state_host, const uint8_t *from_host, const uint8_t *to_host,
+                   uint8_t *winner_host)
+{
+    if (!h || n < 0 || (n && (!state_host || !from_host || !to_host || !winner_host))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    size_t sb = (size_t)n * CCX_STATE_WORDS * 8;
+    int rc;
+    if ((rc = ccx_reserve(h, h->d_state, sb)) || (rc = ccx_reserve(h, h->d_aux0, (size_t)n)) ||
+        (rc = ccx_reserve(h, h->d_aux1, (size_t)n)) || (rc = ccx_reserve(h, h->d_aux2, (size_t)n))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_state.ptr, state_host, sb, cudaMemcpyHostToDevice, h->stream));
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_aux0.ptr, from_host, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_aux1.ptr, to_host, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ccx_apply(h, n, (uint64_t *)h->d_state.ptr, (const uint8_t *)h->d_aux0.ptr, (const uint8_t *)h->d_aux1.ptr,
+                        (uint8_t *)h->d_aux2.ptr))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(state_host, h->d_state.ptr, sb, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaMemcpyAsync(winner_host, h->d_aux2.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CCX_OK;
+}
+
+int ccx_step_random_host(ccx_handle *h, int64_t n, uint64_t *state_host, int64_t game_id0, uint64_t seed, uint32_t step0,
+                         int32_t plies, uint64_t *wins_host)
+{
+    if (!h || n < 0 || plies < 0 || (n && (!state_host || !wins_host))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    size_t sb = (size_t)n * CCX_STATE_WORDS * 8, hot = (size_t)n * 5 * 8;
+    int rc;
+    if ((rc = ccx_reserve(h, h->d_state, sb)) || (rc = ccx_reserve(h, h->d_aux0, 16))) return rc;
+    // the step touches words 0-4 only: 40 B per game each way
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_state.ptr, state_host, hot, cudaMemcpyHostToDevice, h->stream));
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_aux0.ptr, wins_host, 16, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ccx_step_random(h, n, (uint64_t *)h->d_state.ptr, game_id0, seed, step0, plies, (uint64_t *)h->d_aux0.ptr,
+                              nullptr, 0))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(state_host, h->d_state.ptr, hot, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaMemcpyAsync(wins_host, h->d_aux0.ptr, 16, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CCX_OK;
+}
+
+int ccx_encode_host(ccx_handle *h, int64_t n, const uint64_t *state_host, void *out_host, int dtype)
+{
+    if (!h || n < 0 || (n && (!state_host || !out_host))) return CCX_ERR_ARG;
+    if (dtype < CCX_DTYPE_U8 || dtype > CCX_DTYPE_F32) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    size_t esz = dtype == CCX_DTYPE_U8 ? 1 : dtype == CCX_DTYPE_BF16 ? 2 : 4;
+    size_t sb = (size_t)n * CCX_STATE_WORDS * 8, ob = (size_t)n * 343 * esz;
+    int rc;
+    if ((rc = ccx_reserve(h, h->d_state, sb)) || (rc = ccx_reserve(h, h->d_aux0, ob))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_state.ptr, state_host, (size_t)n * 5 * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ccx_encode(h, n, (const uint64_t *)h->d_state.ptr, h->d_aux0.ptr, dtype))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(out_host, h->d_aux0.ptr, ob, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CCX_OK;
+}
+
+}  // extern "C"
+
+// weak defaults so that libccx.so links before the MCTS / net translation units exist
+__attribute__((weak)) void ccx_net_free(ccx_handle *) {}
+__attribute__((weak)) void ccx_trees_free(ccx_handle *) {}

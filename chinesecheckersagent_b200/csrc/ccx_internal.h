@@ -1,0 +1,61 @@
+// ccx_internal.h — the opaque handle behind include/ccx.h and the launch helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/ccx.h"
+
+struct ccx_scratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct ccx_net;     // ccx_net.cu
+struct ccx_trees;   // ccx_mcts.cu
+
+struct ccx_handle {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    char cuda_err[256] = {0};
+    // device scratch for the *_host entry points (grown on demand, freed in ccx_destroy)
+    ccx_scratch d_state, d_aux0, d_aux1, d_aux2;
+    ccx_net *net = nullptr;
+    ccx_trees *trees = nullptr;
+};
+
+static inline int ccx_fail(ccx_handle *h, cudaError_t e)
+{
+    if (h) snprintf(h->cuda_err, sizeof(h->cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? CCX_ERR_NOMEM : CCX_ERR_CUDA;
+}
+
+#define CCX_CUDA(h, call)                                   \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return ccx_fail((h), e__);  \
+    } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define CCX_LAUNCHED(h)                                     \
+    do {                                                    \
+        (h)->launches++;                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return ccx_fail((h), e__);  \
+    } while (0)
+
+static inline int ccx_reserve(ccx_handle *h, ccx_scratch &s, size_t bytes)
+{
+    if (s.bytes >= bytes) return CCX_OK;
+    if (s.ptr) { CCX_CUDA(h, cudaFree(s.ptr)); s.ptr = nullptr; s.bytes = 0; }
+    size_t want = bytes + bytes / 4;
+    CCX_CUDA(h, cudaMalloc(&s.ptr, want));
+    s.bytes = want;
+    return CCX_OK;
+}
+
+// sub-module teardown hooks (defined where the sub-module lives)
+void ccx_net_free(ccx_handle *h);
+void ccx_trees_free(ccx_handle *h);

@@ -1,0 +1,126 @@
+/*
+ * ccx.h — C-ABI of the B200-native batched Chinese Checkers engine (libccx.so).
+ *
+ * The reference (kenziyuliu/ChineseCheckersAgent) is pure Python and has no FFI layer; its boundary is
+ * the Python object surface.  Each entry point below replaces one reference function
+ * for a BATCH of independent games and cites the reference file:line it stands in for.  The Python
+ * mirror of the reference interface (chinesecheckersagent_b200/{board,utils,MCTS,player,game,selfplay}.py)
+ * is a thin ctypes layer over these symbols; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the function name contains `_host`
+ *   - every call is enqueued on the handle's stream (ccx_set_stream) and is asynchronous with
+ *     respect to the host, except the `_host` variants, which return after their results are in the
+ *     caller's host buffers
+ *   - return value: 0 = CCX_OK, negative = error (ccx_strerror); never throws, never aborts
+ *   - no global mutable state; one handle per (device, stream) user; handles are thread-compatible
+ *
+ * State layout ("SoA words"): uint64 state[CCX_STATE_WORDS][n], plane-major (word k of game i at
+ * state[k*n + i]) so that consecutive threads read consecutive 8-byte words (coalesced).
+ *   cell index  = 8*row + col   (row, col in 0..6 — the reference's numpy indices, board.py:20-26);
+ *                 row stride 8 leaves guard bits so that direction shifts never wrap.
+ *   word 0  OCC1   bitboard of player 1's checkers            (board.py:19-26 plane 0 == 1)
+ *   word 1  OCC2   bitboard of player 2's checkers            (plane 0 == 2)
+ *   word 2  CELLS1 byte id (0..5) = cell of player 1's checker `id`   (board.py:42-44 checkers_pos[1])
+ *   word 3  CELLS2 same for player 2                                   (board.py:45-46)
+ *   word 4  META   byte0 last move from, byte1 last move to, byte2/3 the move before (0xFF = none)
+ *                  (board.py:246-248 hist_moves[-1], [-2]); bytes 4-5 plies played (uint16);
+ *                  byte 6 side to move (0 = PLAYER_ONE, 1 = PLAYER_TWO); byte 7 status (CCX_ST_*)
+ *   word 5  HIST_LO destinations of the last 8 plies, byte 0 most recent, 0xFF = none
+ *   word 6  HIST_HI destinations of plies 9..16 ago      (board.py:54 hist_moves / game.py:60,73-75)
+ *   word 7  AUX    self-play bookkeeping (selfplay.py:19-23): bytes 0-1 num_useless_moves,
+ *                  byte 2/3 player_progresses[0/1], bytes 4-5 recorded plies
+ * The env step reads and writes words 0-4 (40 B each way = the 80 B/step algorithmic traffic).
+ */
+#ifndef CCX_H
+#define CCX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCX_ABI_VERSION 1
+#define CCX_STATE_WORDS 8
+#define CCX_NUM_CHECKERS 6          /* config.py:8  */
+#define CCX_BOARD_W 7               /* config.py:10 */
+#define CCX_NUM_ACTIONS 294         /* utils.py:164-171: id*49 + r*7 + c */
+#define CCX_TRACE_WORDS 12
+
+enum { CCX_OK = 0, CCX_ERR_ARG = -1, CCX_ERR_CUDA = -2, CCX_ERR_NOMEM = -3, CCX_ERR_STATE = -4,
+       CCX_ERR_UNSUPPORTED = -5, CCX_ERR_OVERFLOW = -6 };
+/* status byte of META */
+enum { CCX_ST_RUNNING = 0, CCX_ST_WON_P1 = 1, CCX_ST_WON_P2 = 2, CCX_ST_REPETITION = 3,
+       CCX_ST_MOVE_LIMIT = 4, CCX_ST_NO_MOVES = 5 };
+enum { CCX_RESET_START = 0, CCX_RESET_RANDOMISED = 1 };
+enum { CCX_DTYPE_U8 = 0, CCX_DTYPE_BF16 = 1, CCX_DTYPE_F32 = 2 };
+
+typedef struct ccx_handle ccx_handle;
+
+int         ccx_abi_version(void);
+const char *ccx_strerror(int code);
+/* last CUDA error string seen by this handle (empty if none) */
+const char *ccx_last_cuda_error(const ccx_handle *h);
+
+int ccx_create(int device_ordinal, ccx_handle **out);
+int ccx_destroy(ccx_handle *h);
+/* cuda_stream is a cudaStream_t passed as void*; NULL = the legacy default stream */
+int ccx_set_stream(ccx_handle *h, void *cuda_stream);
+int ccx_synchronize(ccx_handle *h);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t ccx_launch_count(const ccx_handle *h);
+
+/* Board() / Board(randomised=True)  — board.py:10-57, 61-85.  RANDOMISED draws 12 distinct cells with
+ * Philox4x32-10 keyed by (seed, game_id0 + i); the first six go to player 1 ids 0..5. */
+int ccx_reset(ccx_handle *h, int64_t n, uint64_t *state, int mode, uint64_t seed, int64_t game_id0);
+
+/* Board.get_valid_moves(side to move) — board.py:139-222.  dest_masks[id*n + i] = bitboard of the
+ * legal destinations of checker `id` (canonical order = ascending bit = ascending r*7+c). */
+int ccx_movegen(ccx_handle *h, int64_t n, const uint64_t *state, uint64_t *dest_masks);
+
+/* Board.place(side to move, from, to) -> check_win() — board.py:226-250, 89-111.  No legality check
+ * (the reference has none either); `to` must be empty.  winner[i] in {0,1,2}. */
+int ccx_apply(ccx_handle *h, int64_t n, uint64_t *state, const uint8_t *from, const uint8_t *to,
+              uint8_t *winner);
+
+/* out[i*5 + {0..4}] = check_win, player_progress(1), player_progress(2), player_forward_distance(1),
+ * player_forward_distance(2) — board.py:89-111, 254-266, 270-288 */
+int ccx_info(ccx_handle *h, int64_t n, const uint64_t *state, int16_t *out);
+
+/* `plies` fused env steps per game: movegen -> selfplay.make_random_move's choice (selfplay.py:93-98:
+ * uniform over checkers that can move, then uniform over its destinations) -> place -> check_win; a won
+ * game is counted in wins[winner-1] and restarted from Board().  RNG: Philox4x32-10, key = seed,
+ * counter = (step0 + t, 0, game id lo, game id hi).  trace (may be NULL): for the first trace_games
+ * games and every ply, CCX_TRACE_WORDS words = state words 0-4 before the move, the six destination
+ * masks, then from | to<<8 | winner<<16 | checker id<<24; trace[(t*trace_games + g)*12 + k]. */
+int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0, uint64_t seed,
+                    uint32_t step0, int32_t plies, uint64_t *wins, uint64_t *trace, int64_t trace_games);
+
+/* GreedyPlayer.decide_move(training=True) — player.py:99-118.  cand_masks[id*n + i] = destinations of
+ * checker `id` that are in filtered_best_moves. */
+int ccx_greedy_candidates(ccx_handle *h, int64_t n, const uint64_t *state, uint64_t *cand_masks);
+
+/* Game('greedy','greedy').start() — game.py:58-100 — for every game whose status is RUNNING, until it
+ * ends (win / repetition stop) or max_plies more plies were played.  Uniform pick among
+ * filtered_best_moves (player.py:121) in canonical order with Philox counter (ply, 1, game id).
+ * counters (may be NULL): uint64[4] += {plies played, P1 wins, P2 wins, repetition stops}. */
+int ccx_play_greedy(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0, uint64_t seed,
+                    int32_t max_plies, uint64_t *counters);
+
+/* utils.to_model_input(board, side to move) — utils.py:101-160 — written channels-last (n,7,7,7)
+ * straight into the network's input tensor; dtype CCX_DTYPE_*. */
+int ccx_encode(ccx_handle *h, int64_t n, const uint64_t *state, void *out_nhwc, int dtype);
+
+/* ---- host-buffer variants: the reference-facing path with H2D/D2H inside the call -------------- */
+int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host);
+int ccx_apply_host(ccx_handle *h, int64_t n, uint64_t *state_host, const uint8_t *from_host,
+                   const uint8_t *to_host, uint8_t *winner_host);
+int ccx_step_random_host(ccx_handle *h, int64_t n, uint64_t *state_host, int64_t game_id0, uint64_t seed,
+                         uint32_t step0, int32_t plies, uint64_t *wins_host);
+int ccx_encode_host(ccx_handle *h, int64_t n, const uint64_t *state_host, void *out_host, int dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCX_H */
