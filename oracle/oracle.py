@@ -48,10 +48,10 @@ def lib():
         L.orc_apply_batch.argtypes = [vp, i64, vp, vp, vp]
         L.orc_info_batch.argtypes = [vp, i64, vp]
         L.orc_greedy_list_batch.argtypes = [vp, i64, vp, vp]
-        if hasattr(L, "orc_mcts_stub_batch"):
-            L.orc_mcts_stub_batch.argtypes = [vp, i64, i32, dbl, dbl, i32, vp, vp, vp, i32]
-        if hasattr(L, "orc_mcts_table_batch"):
-            L.orc_mcts_table_batch.argtypes = [vp, i64, i32, dbl, dbl, i32, vp, vp, vp, vp, vp, i32]
+        L.orc_mcts_stub_batch.argtypes = [vp, i64, i32, dbl, dbl, i32, vp, vp, vp, i32]
+        L.orc_mcts_batch.argtypes = [vp, i64, i32, dbl, dbl, i32, i32, vp, i32, vp, vp, vp, vp, i32]
+        L.orc_mcts_stub_batch.restype = None
+        L.orc_mcts_batch.restype = None
         for name in ("orc_movegen_batch", "orc_encode_batch", "orc_greedy_batch", "orc_step_random",
                      "orc_play_greedy", "orc_philox"):
             getattr(L, name).restype = None
@@ -213,12 +213,23 @@ def philox(k0, k1, c0, c1, c2, c3):
     return out
 
 
-def mcts_stub(st, num_itr=175, cpuct=3.5, tau=1.0, pre_expand=0, nthreads=1):
+EVAL_UNIFORM, EVAL_HASH = 0, 1
+
+
+def mcts(st, num_itr=175, cpuct=3.5, tau=1.0, pre_expand=0, evaluator=EVAL_UNIFORM, noise=None, nthreads=1):
+    """MCTS.search on every root (canonical edge order, first-maximum tie-break).
+    Returns (visits[n,294] u32, pi[n,294] f64, root Q[n,294] f64, node count[n])."""
     st = np.ascontiguousarray(st, dtype=np.uint64)
     n = st.shape[1]
     visits = np.zeros((n, NACT), dtype=np.uint32)
     pi = np.zeros((n, NACT), dtype=np.float64)
+    q = np.zeros((n, NACT), dtype=np.float64)
     nodes = np.zeros(n, dtype=np.int32)
-    lib().orc_mcts_stub_batch(_ptr(st), n, num_itr, cpuct, tau, pre_expand, _ptr(visits), _ptr(pi),
-                              _ptr(nodes), nthreads)
-    return visits, pi, nodes
+    stride = 0
+    if noise is not None:
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        stride = noise.shape[1]
+    lib().orc_mcts_batch(_ptr(st), n, num_itr, cpuct, tau, pre_expand, evaluator,
+                         _ptr(noise) if noise is not None else None, stride, _ptr(visits), _ptr(pi), _ptr(nodes),
+                         _ptr(q), nthreads)
+    return visits, pi, q, nodes
