@@ -27,6 +27,12 @@ SIGNATURES = {
     "ccx_greedy_candidates": (i32, [vp, i64, vp, vp]),
     "ccx_play_greedy": (i32, [vp, i64, vp, i64, u64, i32, vp]),
     "ccx_encode": (i32, [vp, i64, vp, vp, i32]),
+    "ccx_mcts_search": (i32, [vp, i64, vp, i32, i32, f64, f64, i32, vp, i32, i32, vp, vp, vp, vp]),
+    "ccx_mcts_begin": (i32, [vp, i64, vp, i32, i32]),
+    "ccx_mcts_select": (i32, [vp, i64, f64, vp]),
+    "ccx_mcts_expand_backup": (i32, [vp, i64, vp, vp, vp, i32]),
+    "ccx_mcts_finalize": (i32, [vp, i64, f64, vp, vp, vp, vp]),
+    "ccx_mcts_pool_bytes": (i64, [vp]),
     "ccx_movegen_host": (i32, [vp, i64, vp, vp]),
     "ccx_apply_host": (i32, [vp, i64, vp, vp, vp, vp]),
     "ccx_step_random_host": (i32, [vp, i64, vp, i64, u64, u32, i32, vp]),

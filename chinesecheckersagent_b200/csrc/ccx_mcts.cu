@@ -1,0 +1,529 @@
+// ccx_mcts.cu — batched MCTS (MCTS.py:13-153) as per-tree device node pools, one warp per tree.
+//
+// Reference semantics kept bit for bit: one simulation at a time per tree, PUCT in
+// IEEE float64 evaluated left to right without FMA contraction (MCTS.py:62-63), strict-'>' running
+// maximum so the first maximal edge wins (MCTS.py:65-69 with the first-choice tie-break), un-normalised
+// priors (MCTS.py:108), terminal leaves never expanded (MCTS.py:81-90), no virtual loss, no tree reuse.
+// What changes is the machinery: instead of deep-copying a Board into one Node object per legal move
+// (MCTS.py:104-107) a tree is a bump-allocated edge pool (SoA: N, W, P, child, move) plus a pool of the
+// nodes that were actually visited; a child's 40-byte state is materialised lazily on its first visit.
+//
+// Edge order = checker id ascending, then destination cell ascending ("canonical", BASELINE.json).
+#include "ccx_device.cuh"
+#include "ccx_internal.h"
+#include <new>
+
+#define FULL 0xFFFFFFFFu
+#define MCTS_WARPS_PER_BLOCK 4
+#define NODE_WORDS 6            // 5 state words + info word
+
+// info word of a node: edge_begin (32) | n_edges (16) | winner (8) | expanded (8)
+__device__ __forceinline__ u64 make_info(u32 eb, u32 ne, u32 winner, u32 expanded)
+{
+    return (u64)eb | ((u64)ne << 32) | ((u64)winner << 48) | ((u64)expanded << 56);
+}
+
+struct ccx_trees {
+    int64_t cap_trees = 0;
+    int32_t nodes_per_tree = 0, edges_per_tree = 0, path_max = 0;
+    u64 *node = nullptr;        // [T][NPT][NODE_WORDS]
+    u32 *eN = nullptr;          // [T][EPT]
+    double *eW = nullptr, *eP = nullptr;
+    int32_t *eChild = nullptr;  // node index inside the tree or -1
+    uint16_t *eMove = nullptr;  // checker id << 8 | destination cell
+    int32_t *path = nullptr;    // [T][PATH_MAX] edge indices of the current simulation
+    int32_t *tree_meta = nullptr;   // [T][8]: n_nodes, n_edges, overflow, path_len, leaf_node, leaf_kind, sims_done, spare
+    size_t bytes = 0;
+};
+
+struct TreeView {
+    u64 *node; u32 *eN; double *eW; double *eP; int32_t *eChild; uint16_t *eMove; int32_t *path; int32_t *meta;
+    int32_t npt, ept, path_max;
+};
+
+__device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
+{
+    TreeView v;
+    v.node = t.node + tree * t.nodes_per_tree * NODE_WORDS;
+    v.eN = t.eN + tree * t.edges_per_tree;
+    v.eW = t.eW + tree * t.edges_per_tree;
+    v.eP = t.eP + tree * t.edges_per_tree;
+    v.eChild = t.eChild + tree * t.edges_per_tree;
+    v.eMove = t.eMove + tree * t.edges_per_tree;
+    v.path = t.path + tree * t.path_max;
+    v.meta = t.tree_meta + tree * 8;
+    v.npt = t.nodes_per_tree; v.ept = t.edges_per_tree; v.path_max = t.path_max;
+    return v;
+}
+
+enum { META_NNODES = 0, META_NEDGES = 1, META_OVERFLOW = 2, META_PATHLEN = 3, META_LEAF = 4, META_LEAFKIND = 5 };
+enum { LEAF_EVAL = 0, LEAF_TERMINAL = 1, LEAF_DEAD = 2 };
+enum { EVAL_UNIFORM = 0, EVAL_HASH = 1, EVAL_NET = 2 };
+
+__device__ __forceinline__ u64 shfl64(u64 v, int src)
+{
+    u32 lo = __shfl_sync(FULL, (u32)v, src), hi = __shfl_sync(FULL, (u32)(v >> 32), src);
+    return (u64)lo | ((u64)hi << 32);
+}
+
+__device__ __forceinline__ Game game_of_words(u64 occ1, u64 occ2, u64 c1, u64 c2, u64 meta)
+{
+    Game g;
+    g.meta = meta;
+    bool p2 = (meta >> 48) & 1;
+    g.occ_me = p2 ? occ2 : occ1; g.occ_op = p2 ? occ1 : occ2;
+    g.cells_me = p2 ? c2 : c1;   g.cells_op = p2 ? c1 : c2;
+    return g;
+}
+
+__device__ __forceinline__ Game load_node_game(const TreeView &tv, int node)
+{
+    const u64 *w = tv.node + (int64_t)node * NODE_WORDS;
+    return game_of_words(w[0], w[1], w[2], w[3], w[4]);
+}
+
+__device__ __forceinline__ void store_node(const TreeView &tv, int node, const Game &g, u64 info)
+{
+    u64 *w = tv.node + (int64_t)node * NODE_WORDS;
+    bool p2 = (g.meta >> 48) & 1;
+    w[0] = p2 ? g.occ_op : g.occ_me; w[1] = p2 ? g.occ_me : g.occ_op;
+    w[2] = p2 ? g.cells_op : g.cells_me; w[3] = p2 ? g.cells_me : g.cells_op;
+    w[4] = g.meta; w[5] = info;
+}
+
+// ---- test evaluators (specification shared with the CPU checker; not reference code) ---------------
+__host__ __device__ constexpr u64 splitmix64_c(u64 z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ constexpr u64 plane6_sum()
+{
+    u64 s = 0;
+    for (int c = 0; c < 49; c++) s += splitmix64_c((u64)(c * 7 + 6) + 1);
+    return s;
+}
+
+// hash of utils.to_model_input(state, side to move): sum over non-zero plane entries of
+// splitmix64(k+1) * value, k = (r*7+c)*7 + channel.  Warp-cooperative: 36 labelled entries + plane 6.
+__device__ __forceinline__ u64 warp_sum_u64(u64 v)
+{
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += shfl64(v, (threadIdx.x & 31) ^ off);
+    return v;
+}
+
+__device__ __forceinline__ u64 leaf_hash(const Game &g, int lane)
+{
+    int plies = (int)((g.meta >> 32) & 0xFFFF);
+    u64 cur0 = g.cells_me, opp0 = g.cells_op;
+    u64 opp1 = undo_in_cells(opp0, (int)(g.meta & 0xFF), (int)((g.meta >> 8) & 0xFF));
+    u64 cur2 = undo_in_cells(cur0, (int)((g.meta >> 16) & 0xFF), (int)((g.meta >> 24) & 0xFF));
+    u64 h = 0;
+    for (int e = lane; e < 36; e += 32) {
+        int hs = e / 12, side = (e / 6) & 1, id = e % 6;
+        if (hs > plies) continue;
+        u64 cells = side ? (hs >= 1 ? opp1 : opp0) : (hs >= 2 ? cur2 : cur0);
+        int cell = (int)((cells >> (8 * id)) & 0xFF);
+        int k = ((cell >> 3) * 7 + (cell & 7)) * 7 + 2 * hs + side;
+        h += splitmix64_c((u64)k + 1) * (u64)(id + 1);
+    }
+    h = warp_sum_u64(h);
+    if ((g.meta >> 48) & 1) h += plane6_sum();                   // utils.py:157-158
+    return h;
+}
+
+// ---- select (MCTS.moveToLeaf, MCTS.py:49-76) ---------------------------------------------------------
+// Returns the leaf node index (materialising it if this is its first visit) and leaves the path in
+// tv.path / path_len.  leaf_kind: LEAF_EVAL (needs evaluation + expansion), LEAF_TERMINAL (winner != 0).
+__device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double cpuct, int &path_len, int &leaf_kind)
+{
+    int node = 0, depth = 0;
+    for (;;) {
+        u64 info = tv.node[(int64_t)node * NODE_WORDS + 5];
+        int winner = (int)((info >> 48) & 0xFF);
+        int ne = (int)((info >> 32) & 0xFFFF);
+        if (winner) { leaf_kind = LEAF_TERMINAL; break; }
+        if (ne == 0) { leaf_kind = LEAF_EVAL; break; }           // Node.isLeaf()
+        int eb = (int)(u32)info;
+        // N_sum (MCTS.py:58-59)
+        u32 nsum = 0;
+        for (int j = lane; j < ne; j += 32) nsum += tv.eN[eb + j];
+        nsum = __reduce_add_sync(FULL, nsum);
+        double sq = sqrt((double)nsum);                          // np.sqrt(N_sum)
+        double best = -INFINITY; int besti = 0x7FFFFFFF;
+        for (int j = lane; j < ne; j += 32) {
+            u32 N = tv.eN[eb + j];
+            double W = tv.eW[eb + j], P = tv.eP[eb + j];
+            double Q = N ? __ddiv_rn(W, (double)N) : 0.0;                                   // MCTS.py:89,118
+            double U = __ddiv_rn(__dmul_rn(__dmul_rn(cpuct, P), sq), __dadd_rn(1.0, (double)N));   // :62
+            double QU = __dadd_rn(Q, U);                                                    // :63
+            if (QU > best) { best = QU; besti = j; }                                        // :65-67
+        }
+        // warp arg-max, ties to the smallest edge index (= first maximal edge in list order)
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            double ob = __shfl_xor_sync(FULL, best, off);
+            int oi = __shfl_xor_sync(FULL, besti, off);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        int e = eb + besti;
+        if (lane == 0 && depth < tv.path_max) tv.path[depth] = e;
+        depth++;
+        int child = tv.eChild[e];
+        if (child < 0) {
+            // first visit: materialise the child state = Board.place on a copy (MCTS.py:104-105)
+            int nn = tv.meta[META_NNODES];
+            if (nn >= tv.npt) { if (lane == 0) tv.meta[META_OVERFLOW] = 1; leaf_kind = LEAF_DEAD; node = 0; break; }
+            Game g = load_node_game(tv, node);
+            u32 mv = tv.eMove[e];
+            int id = (int)(mv >> 8), to = (int)(mv & 0xFF);
+            int from = (int)((g.cells_me >> (8 * id)) & 0xFF);
+            apply_move(g, id, from, to);
+            int w = winner_of(g);
+            __syncwarp();
+            if (lane == 0) {
+                store_node(tv, nn, g, make_info(0, 0, (u32)w, 0));
+                tv.eChild[e] = nn;
+                tv.meta[META_NNODES] = nn + 1;
+            }
+            __syncwarp();
+            node = nn;
+            leaf_kind = w ? LEAF_TERMINAL : LEAF_EVAL;
+            break;
+        }
+        node = child;
+    }
+    path_len = depth;
+    return node;
+}
+
+// ---- backup (MCTS.py:83-90 terminal, 112-118 value) ---------------------------------------------------
+__device__ __forceinline__ void backup(const TreeView &tv, int lane, int path_len, double v, bool terminal)
+{
+    for (int d = lane; d < path_len; d += 32) {
+        int e = tv.path[d];
+        bool same = ((path_len - d) & 1) == 0;                   // edge.currPlayer == leafNode.currPlayer
+        double delta = terminal ? (same ? -1.0 : 1.0)            // REWARD['win'] * direction
+                                : __dmul_rn(v, same ? 1.0 : -1.0);
+        tv.eN[e] += 1;
+        tv.eW[e] = __dadd_rn(tv.eW[e], delta);
+    }
+}
+
+// ---- expand (MCTS.py:95-109) ---------------------------------------------------------------------------
+// Lanes 0..5 run one checker's flood fill each; the six masks are then broadcast and every lane writes a
+// strided share of the edge list.  prior(idx) is supplied by the evaluator functor.
+template <typename PriorFn>
+__device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int node, const Game &g, PriorFn prior)
+{
+    u64 mine = 0;
+    if (lane < 6) {
+        u64 occ_all = g.occ_me | g.occ_op;
+        u64 o = 1ULL << ((g.cells_me >> (8 * lane)) & 0xFF);
+        u64 occ = occ_all & ~o, empty = ~occ & CCX_VALID;
+        u64 F = o, reach = 0;
+        while (F) { u64 nw = jump_round(F, occ, empty) & ~(reach | o); reach |= nw; F = nw; }
+        mine = (neighbours(o) & empty) | reach;
+    }
+    u64 dest[6]; int pre[7]; pre[0] = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { dest[k] = shfl64(mine, k); pre[k + 1] = pre[k] + __popcll(dest[k]); }
+    int total = pre[6];
+    int eb = tv.meta[META_NEDGES];
+    if (eb + total > tv.ept) { if (lane == 0) tv.meta[META_OVERFLOW] = 1; return false; }
+    for (int j = lane; j < total; j += 32) {
+        int k = 0;
+#pragma unroll
+        for (int q = 1; q < 6; q++) k += (j >= pre[q]);
+        u64 m = 0; int base = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) if (k == q) { m = dest[q]; base = pre[q]; }
+        int to = select64(m, (u32)(j - base));
+        int idx = k * 49 + (to >> 3) * 7 + (to & 7);             // utils.encode_checker_index
+        tv.eN[eb + j] = 0; tv.eW[eb + j] = 0.0; tv.eP[eb + j] = prior(idx);     // MCTS.py:32-37,108
+        tv.eChild[eb + j] = -1;
+        tv.eMove[eb + j] = (uint16_t)((k << 8) | to);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        tv.meta[META_NEDGES] = eb + total;
+        u64 *info = tv.node + (int64_t)node * NODE_WORDS + 5;
+        *info = make_info((u32)eb, (u32)total, 0, 1);
+    }
+    __syncwarp();
+    return true;
+}
+
+struct UniformPrior { __device__ double operator()(int) const { return 1.0 / 294.0; } };
+struct HashPrior {
+    u32 k0, k1;
+    __device__ double operator()(int idx) const { return (double)philox4x32_10(k0, k1, (u32)idx, 7u, 0u, 0u).x / 4294967296.0; }
+};
+struct TablePrior {      // priors from an evaluator's output row p[294] (float64)
+    const double *p;
+    __device__ double operator()(int idx) const { return p[idx]; }
+};
+
+// evaluate + expand + backup of one leaf with an in-kernel evaluator
+template <int EVAL>
+__device__ __forceinline__ void eval_expand_backup(const TreeView &tv, int lane, int leaf, int path_len)
+{
+    Game g = load_node_game(tv, leaf);
+    double v = 0.0;
+    bool ok;
+    if (EVAL == EVAL_HASH) {
+        u64 h = leaf_hash(g, lane);
+        HashPrior pr = {(u32)h, (u32)(h >> 32)};
+        v = (double)philox4x32_10(pr.k0, pr.k1, 294u, 7u, 0u, 0u).x / 2147483648.0 - 1.0;
+        ok = expand_node(tv, lane, leaf, g, pr);
+    } else {
+        ok = expand_node(tv, lane, leaf, g, UniformPrior());
+    }
+    if (ok) backup(tv, lane, path_len, v, false);
+}
+
+// selfplay.py:121-124 — root priors mixed with caller-supplied Dirichlet noise (one value per root edge)
+__device__ __forceinline__ void mix_root_noise(const TreeView &tv, int lane, const double *noise)
+{
+    u64 info = tv.node[5];
+    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    for (int j = lane; j < ne; j += 32) {
+        double p = __dmul_rn(tv.eP[eb + j], 1. - 0.25);
+        tv.eP[eb + j] = __dadd_rn(p, __dmul_rn(0.25, noise[j]));
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u64 *roots, int64_t n, int64_t tree)
+{
+    if (lane == 0) {
+        Game g = game_of_words(roots[0 * n + tree], roots[1 * n + tree], roots[2 * n + tree], roots[3 * n + tree],
+                               roots[4 * n + tree] & 0x00FFFFFFFFFFFFFFULL);
+        store_node(tv, 0, g, make_info(0, 0, (u32)winner_of(g), 0));
+        tv.meta[META_NNODES] = 1; tv.meta[META_NEDGES] = 0; tv.meta[META_OVERFLOW] = 0; tv.meta[META_PATHLEN] = 0;
+    }
+    __syncwarp();
+}
+
+// Persistent search with an in-kernel evaluator: every warp runs all simulations of its tree.
+template <int EVAL>
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num_itr, double cpuct, int pre_expand,
+              const double *__restrict__ noise, int noise_stride)
+{
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    init_tree(tv, lane, roots, n, tree);
+    if (pre_expand && ((tv.node[5] >> 48) & 0xFF) == 0) {                    // selfplay.py:117
+        eval_expand_backup<EVAL>(tv, lane, 0, 0);
+        if (noise) mix_root_noise(tv, lane, noise + tree * noise_stride);
+    }
+    for (int it = 0; it < num_itr; it++) {                                   // MCTS.py:123-125
+        int path_len, kind;
+        int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
+        __syncwarp();
+        if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
+        else if (kind == LEAF_EVAL) eval_expand_backup<EVAL>(tv, lane, leaf, path_len);
+        __syncwarp();
+        if (tv.meta[META_OVERFLOW]) break;
+    }
+}
+
+// ---- round-based pieces for an external evaluator (the policy/value net) ----------------------------
+// phase A: select one leaf per tree; terminal leaves are backed up at once; for the others the leaf's
+// state words are written to leaf_state[5][n] (input of ccx_encode / the net)
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_select(ccx_trees trees, int64_t n, double cpuct, u64 *__restrict__ leaf_state)
+{
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    if (tv.meta[META_OVERFLOW]) { if (lane == 0) tv.meta[META_LEAFKIND] = LEAF_DEAD; return; }
+    int path_len, kind;
+    int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
+    __syncwarp();
+    if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
+    if (lane < 5) leaf_state[lane * n + tree] = tv.node[(int64_t)leaf * NODE_WORDS + lane];
+    if (lane == 0) { tv.meta[META_PATHLEN] = path_len; tv.meta[META_LEAF] = leaf; tv.meta[META_LEAFKIND] = kind; }
+}
+
+// phase B: expand the selected leaf with priors p[n][294] (float64, already soft-maxed: model.py:21-24)
+// and back up v[n]; root_only_noise != NULL mixes Dirichlet noise into the root priors (first call).
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, const double *__restrict__ v,
+                     const double *__restrict__ noise, int noise_stride)
+{
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    if (tv.meta[META_LEAFKIND] != LEAF_EVAL) return;
+    int leaf = tv.meta[META_LEAF], path_len = tv.meta[META_PATHLEN];
+    Game g = load_node_game(tv, leaf);
+    TablePrior pr = {p + tree * CCX_NUM_ACTIONS};
+    if (expand_node(tv, lane, leaf, g, pr)) backup(tv, lane, path_len, v[tree], false);
+    if (noise && leaf == 0) mix_root_noise(tv, lane, noise + tree * noise_stride);
+}
+
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_init(ccx_trees trees, const u64 *__restrict__ roots, int64_t n)
+{
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    init_tree(tv, threadIdx.x & 31, roots, n, tree);
+}
+
+// ---- finalize (MCTS.py:131-137): visit counts, pi = N^(1/tau) / sum, root Q ---------------------------
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_finalize(ccx_trees trees, int64_t n, double inv_tau, u32 *__restrict__ visits, double *__restrict__ pi,
+                double *__restrict__ q, int32_t *__restrict__ n_nodes)
+{
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    for (int a = lane; a < CCX_NUM_ACTIONS; a += 32) {
+        visits[tree * CCX_NUM_ACTIONS + a] = 0;
+        if (pi) pi[tree * CCX_NUM_ACTIONS + a] = 0.0;
+        if (q) q[tree * CCX_NUM_ACTIONS + a] = 0.0;
+    }
+    __syncwarp();
+    u64 info = tv.node[5];
+    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    double sum = 0.0;
+    for (int j = lane; j < ne; j += 32) {
+        u32 N = tv.eN[eb + j];
+        double pw = inv_tau == 1.0 ? (double)N : pow((double)N, inv_tau);       // MCTS.py:132
+        sum += pw;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(FULL, sum, off);   // exact for tau = 1 (integers)
+    for (int j = lane; j < ne; j += 32) {
+        u32 N = tv.eN[eb + j];
+        u32 mv = tv.eMove[eb + j];
+        int to = (int)(mv & 0xFF);
+        int idx = (int)(mv >> 8) * 49 + (to >> 3) * 7 + (to & 7);
+        visits[tree * CCX_NUM_ACTIONS + idx] = N;
+        if (pi) {
+            double pw = inv_tau == 1.0 ? (double)N : pow((double)N, inv_tau);
+            pi[tree * CCX_NUM_ACTIONS + idx] = sum > 0.0 ? __ddiv_rn(pw, sum) : 0.0;       // MCTS.py:137
+        }
+        if (q) q[tree * CCX_NUM_ACTIONS + idx] = N ? __ddiv_rn(tv.eW[eb + j], (double)N) : 0.0;
+    }
+    if (n_nodes && lane == 0)
+        n_nodes[tree] = tv.meta[META_OVERFLOW] ? -1 : tv.meta[META_NEDGES] + 1;   // reference node count: root + one per edge
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+
+void ccx_trees_free(ccx_handle *h)
+{
+    ccx_trees *t = h->trees;
+    if (!t) return;
+    void *ptrs[] = {t->node, t->eN, t->eW, t->eP, t->eChild, t->eMove, t->path, t->tree_meta};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete t;
+    h->trees = nullptr;
+}
+
+static int trees_reserve(ccx_handle *h, int64_t n, int32_t num_itr, int32_t edges_per_tree)
+{
+    int32_t npt = num_itr + 2;
+    int32_t ept = edges_per_tree > 0 ? edges_per_tree : 64 * (num_itr + 1);
+    int32_t pm = num_itr + 2;
+    ccx_trees *t = h->trees;
+    if (t && t->cap_trees >= n && t->nodes_per_tree >= npt && t->edges_per_tree == ept && t->path_max >= pm) return CCX_OK;
+    ccx_trees_free(h);
+    t = new (std::nothrow) ccx_trees();
+    if (!t) return CCX_ERR_NOMEM;
+    h->trees = t;
+    t->cap_trees = n; t->nodes_per_tree = npt; t->edges_per_tree = ept; t->path_max = pm;
+    size_t T = (size_t)n;
+    CCX_CUDA(h, cudaMalloc(&t->node, T * npt * NODE_WORDS * 8));
+    CCX_CUDA(h, cudaMalloc(&t->eN, T * ept * 4));
+    CCX_CUDA(h, cudaMalloc(&t->eW, T * ept * 8));
+    CCX_CUDA(h, cudaMalloc(&t->eP, T * ept * 8));
+    CCX_CUDA(h, cudaMalloc(&t->eChild, T * ept * 4));
+    CCX_CUDA(h, cudaMalloc(&t->eMove, T * ept * 2));
+    CCX_CUDA(h, cudaMalloc(&t->path, T * pm * 4));
+    CCX_CUDA(h, cudaMalloc(&t->tree_meta, T * 8 * 4));
+    t->bytes = T * ((size_t)npt * NODE_WORDS * 8 + (size_t)ept * 26 + (size_t)pm * 4 + 32);
+    return CCX_OK;
+}
+
+static inline unsigned tree_blocks(int64_t n) { return (unsigned)((n + MCTS_WARPS_PER_BLOCK - 1) / MCTS_WARPS_PER_BLOCK); }
+
+extern "C" {
+
+int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t evaluator, int32_t num_itr, double cpuct,
+                    double tau, int32_t pre_expand, const double *root_noise, int32_t noise_stride,
+                    int32_t edges_per_tree, uint32_t *visits, double *pi, double *q, int32_t *n_nodes)
+{
+    if (!h || n < 0 || num_itr < 0 || !(tau > 0.0) || (n && (!roots || !visits))) return CCX_ERR_ARG;
+    if (evaluator != EVAL_UNIFORM && evaluator != EVAL_HASH) return CCX_ERR_UNSUPPORTED;   // the net runs round-based
+    if (root_noise && noise_stride < 1) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    int rc = trees_reserve(h, n, num_itr, edges_per_tree);
+    if (rc) return rc;
+    unsigned grid = tree_blocks(n);
+    if (evaluator == EVAL_UNIFORM)
+        k_mcts_search<EVAL_UNIFORM><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, num_itr,
+                                                                                      cpuct, pre_expand, root_noise, noise_stride);
+    else
+        k_mcts_search<EVAL_HASH><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, num_itr,
+                                                                                   cpuct, pre_expand, root_noise, noise_stride);
+    CCX_LAUNCHED(h);
+    k_mcts_finalize<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, 1.0 / tau, visits, pi, q, n_nodes);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree)
+{
+    if (!h || n < 0 || num_itr < 0 || (n && !roots)) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    int rc = trees_reserve(h, n, num_itr, edges_per_tree);
+    if (rc) return rc;
+    k_mcts_init<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state)
+{
+    if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || (n && !leaf_state)) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_mcts_select<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, (u64 *)leaf_state);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const double *v, const double *root_noise,
+                           int32_t noise_stride)
+{
+    if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || (n && (!p || !v))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_mcts_expand_backup<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, p, v, root_noise, noise_stride);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_mcts_finalize(ccx_handle *h, int64_t n, double tau, uint32_t *visits, double *pi, double *q, int32_t *n_nodes)
+{
+    if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || !(tau > 0.0) || (n && !visits)) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_mcts_finalize<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, 1.0 / tau, visits, pi, q, n_nodes);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int64_t ccx_mcts_pool_bytes(const ccx_handle *h) { return (h && h->trees) ? (int64_t)h->trees->bytes : 0; }
+
+}  // extern "C"

@@ -172,3 +172,48 @@ class HostEnv:
         out = np.empty((n, 7, 7, 7), dtype=npdt)
         self.eng.call("ccx_encode_host", n, self._np(st), self._np(out), dtype)
         return out
+
+
+EVAL_UNIFORM, EVAL_HASH = 0, 1
+
+
+class BatchedMCTS:
+    """Batched counterpart of MCTS.MCTS (MCTS.py:40-153): one tree per root state, all trees advanced one
+    simulation at a time; returns visit-count policies."""
+
+    def __init__(self, engine, cpuct=3.5, num_itr=175, tree_tau=1.0, edges_per_tree=0):
+        self.eng = engine
+        self.cpuct, self.num_itr, self.tree_tau, self.edges_per_tree = float(cpuct), int(num_itr), float(tree_tau), int(edges_per_tree)
+
+    def _outputs(self, n, want_q=True):
+        e = self.eng
+        return (e.empty((n, 294), torch.int32), e.empty((n, 294), torch.float64),
+                e.empty((n, 294), torch.float64) if want_q else None, e.empty((n,), torch.int32))
+
+    def search(self, roots, evaluator=EVAL_UNIFORM, pre_expand=False, root_noise=None):
+        """In-kernel evaluator (uniform stub / hash test evaluator).  roots: (8, n) int64 device tensor.
+        Returns dict(visits, pi, q, n_nodes)."""
+        n = roots.shape[1]
+        visits, pi, q, nodes = self._outputs(n)
+        stride = 0 if root_noise is None else root_noise.shape[1]
+        self.eng.call("ccx_mcts_search", n, _p(roots), int(evaluator), self.num_itr, self.cpuct, self.tree_tau,
+                      int(bool(pre_expand)), _p(root_noise), stride, self.edges_per_tree, _p(visits), _p(pi), _p(q), _p(nodes))
+        return dict(visits=visits, pi=pi, q=q, n_nodes=nodes)
+
+    def search_with(self, roots, evaluate, pre_expand=False, root_noise=None):
+        """External evaluator: evaluate(leaf_state (5, n) int64) -> (p (n, 294) float64, v (n,) float64).
+        One select / evaluate / expand+backup round per simulation for all trees."""
+        n = roots.shape[1]
+        e = self.eng
+        leaf = e.empty((5, n), torch.int64)
+        stride = 0 if root_noise is None else root_noise.shape[1]
+        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree)
+        rounds = self.num_itr + (1 if pre_expand else 0)
+        for r in range(rounds):
+            e.call("ccx_mcts_select", n, self.cpuct, _p(leaf))
+            p, v = evaluate(leaf)
+            noise = root_noise if (pre_expand and r == 0) else None
+            e.call("ccx_mcts_expand_backup", n, _p(p), _p(v), _p(noise), stride if noise is not None else 0)
+        visits, pi, q, nodes = self._outputs(n)
+        e.call("ccx_mcts_finalize", n, self.tree_tau, _p(visits), _p(pi), _p(q), _p(nodes))
+        return dict(visits=visits, pi=pi, q=q, n_nodes=nodes)

@@ -112,6 +112,38 @@ int ccx_play_greedy(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
  * straight into the network's input tensor; dtype CCX_DTYPE_*. */
 int ccx_encode(ccx_handle *h, int64_t n, const uint64_t *state, void *out_nhwc, int dtype);
 
+/* ---- MCTS (MCTS.py:13-153) --------------------------------------------------------------------
+ * One tree per root, one simulation at a time per tree (bit-exact visit counts need the reference's
+ * strictly sequential order, MCTS.py:121-125).  Selection = PUCT in float64, first maximal edge
+ * (MCTS.py:56-69 with the first-choice tie-break); expansion creates every legal edge in canonical
+ * order (checker id, then destination cell) with the evaluator's un-normalised prior (MCTS.py:95-109);
+ * terminal leaves back up +-1 (MCTS.py:81-90).
+ *
+ * ccx_mcts_search runs MCTS.search's loop (MCTS.py:121-137) with an in-kernel evaluator:
+ *   evaluator 0 = uniform prior 1/294, v = 0.0 (BASELINE configs[3]);
+ *   evaluator 1 = deterministic pseudo-random (p, v) keyed by a hash of the to_model_input planes
+ *                 (parity-test evaluator, exercises Q-dependent selection and terminal backups).
+ * pre_expand = 0: AiPlayer.decide_move (player.py:157-158, unexpanded root, sum N = num_itr - 1);
+ * pre_expand = 1: selfplay.make_move (selfplay.py:114-127): root expanded first, then root_noise (may be
+ *   NULL; [n][noise_stride] float64, one value per root edge in edge order) is mixed in with weight 0.25.
+ * Outputs: visits[n][294] (uint32 N per policy index), pi[n][294] (N^(1/tau) normalised; may be NULL),
+ * q[n][294] (root Q; may be NULL), n_nodes[n] (reference node count = edges + 1, or -1 if this tree's
+ * edge pool overflowed; may be NULL).  edges_per_tree <= 0 selects 64 * (num_itr + 1). */
+int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t evaluator, int32_t num_itr, double cpuct,
+                    double tau, int32_t pre_expand, const double *root_noise, int32_t noise_stride,
+                    int32_t edges_per_tree, uint32_t *visits, double *pi, double *q, int32_t *n_nodes);
+
+/* Round-based search for an external evaluator (the policy/value net, model.py:21-24): begin, then per
+ * simulation  select -> [ccx_encode + net on leaf_state] -> expand_backup,  finally finalize.
+ * leaf_state is uint64[5][n] (state words 0-4 of every tree's leaf; garbage-free for terminal leaves too);
+ * p is float64[n][294] soft-maxed policy, v float64[n]; trees whose leaf was terminal ignore them. */
+int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree);
+int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state);
+int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const double *v, const double *root_noise,
+                           int32_t noise_stride);
+int ccx_mcts_finalize(ccx_handle *h, int64_t n, double tau, uint32_t *visits, double *pi, double *q, int32_t *n_nodes);
+int64_t ccx_mcts_pool_bytes(const ccx_handle *h);
+
 /* ---- host-buffer variants: the reference-facing path with H2D/D2H inside the call -------------- */
 int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host);
 int ccx_apply_host(ccx_handle *h, int64_t n, uint64_t *state_host, const uint8_t *from_host,
