@@ -114,7 +114,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ccx", choices=["ccx", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -197,7 +197,7 @@ def main():
     if not args.no_extra:
         try:
             from chinesecheckersagent_b200 import bench_extra
-            extra = bench_extra.run(eng, rank, world, barrier)
+            extra = bench_extra.run(eng, rank, world, barrier, peak_gbs=measured_peak_gbs()[0])
         except ImportError:
             pass
 

@@ -33,6 +33,11 @@ SIGNATURES = {
     "ccx_mcts_expand_backup": (i32, [vp, i64, vp, vp, vp, i32]),
     "ccx_mcts_finalize": (i32, [vp, i64, f64, vp, vp, vp, vp]),
     "ccx_mcts_pool_bytes": (i64, [vp]),
+    "ccx_net_num_weights": (i32, []),
+    "ccx_net_load": (i32, [vp, vp, i64]),
+    "ccx_net_forward": (i32, [vp, i64, vp, i32, vp, vp]),
+    "ccx_softmax_f64": (i32, [vp, i64, vp, vp, vp, vp]),
+    "ccx_net_eval": (i32, [vp, i64, vp, vp, vp]),
     "ccx_movegen_host": (i32, [vp, i64, vp, vp]),
     "ccx_apply_host": (i32, [vp, i64, vp, vp, vp, vp]),
     "ccx_step_random_host": (i32, [vp, i64, vp, i64, u64, u32, i32, vp]),

@@ -1,0 +1,82 @@
+"""Secondary measurements reported under "extra" in bench.py's JSON line: the other BASELINE configs
+(cfg 3 greedy self-play, cfg 4 stub MCTS, plane encoder).  Device-timed with CUDA events on the
+launching stream, max over ranks."""
+import json
+import os
+
+import torch
+
+from .config import DEFAULT_SEED, DTYPE_BF16
+from .engine import BatchedEnv, BatchedMCTS
+
+MCTS_TREES = 4096            # BASELINE configs[3]
+MCTS_SIMS = 175              # config.py:35
+MCTS_BYTES_PER_SIM = 1400    # ~0.9 KB read + 0.5 KB written per simulation
+GREEDY_GAMES = 131072        # BASELINE configs[2]: 1M games / 8 GPUs
+
+
+def _timed(fn, reps, world):
+    evs = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run(eng, rank, world, barrier, peak_gbs=None):
+    out = {}
+    # ---- cfg 4: MCTS, uniform-prior stub evaluator, 4,096 concurrent trees per GPU --------------------
+    env = BatchedEnv(MCTS_TREES, engine=eng, seed=DEFAULT_SEED, game_id0=rank * MCTS_TREES)
+    env.step_random(6)                                   # roots = start advanced by 6 random plies
+    mcts = BatchedMCTS(eng, num_itr=MCTS_SIMS)
+    res = mcts.search(env.state)                         # warm-up + pool allocation
+    barrier()
+    l0 = eng.launches
+    reps = 5
+    t = _timed(lambda: mcts.search(env.state), reps, world)
+    sims = world * MCTS_TREES * MCTS_SIMS * reps
+    out["mcts_stub"] = {"metric": "mcts_sims_per_sec", "value": sims / t, "unit": "sims/s", "trees_per_gpu": MCTS_TREES,
+                        "sims_per_move": MCTS_SIMS, "ms_per_search": t / reps * 1e3, "evaluator": "uniform prior 1/294, v=0",
+                        "gpu_launches": eng.launches - l0,
+                        "overflowed_trees": int((res["n_nodes"] < 0).sum().item()),
+                        "mean_nodes_per_tree": float(res["n_nodes"].float().mean().item())}
+    if peak_gbs:
+        ach = MCTS_BYTES_PER_SIM * MCTS_TREES * MCTS_SIMS / (t / reps) / 1e9
+        out["mcts_stub"]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                                        "kernel": "k_mcts_search<uniform>"}
+    # ---- cfg 3: greedy-vs-greedy self-play to the end (game.py:58-100) ----------------------------------
+    genv = BatchedEnv(GREEDY_GAMES, engine=eng, seed=DEFAULT_SEED, game_id0=rank * GREEDY_GAMES)
+    genv.play_greedy()
+    barrier()
+    counters = eng.zeros((4,), torch.int64)
+
+    def greedy_once():
+        genv.reset()
+        genv.play_greedy(counters=counters)
+    reps = 3
+    t = _timed(greedy_once, reps, world)
+    c = counters.cpu().tolist()
+    out["greedy_selfplay"] = {"metric": "env_steps_per_sec", "value": world * c[0] / t, "unit": "plies/s",
+                              "games_per_sec": world * GREEDY_GAMES * reps / t, "games_per_gpu": GREEDY_GAMES,
+                              "mean_plies_per_game": c[0] / (GREEDY_GAMES * reps), "p1_win_frac": c[1] / (GREEDY_GAMES * reps),
+                              "p2_win_frac": c[2] / (GREEDY_GAMES * reps), "repetition_stop_frac": c[3] / (GREEDY_GAMES * reps)}
+    # ---- plane encoder (utils.to_model_input) straight into a bf16 NHWC tensor ----------------------------
+    eenv = BatchedEnv(1 << 20, engine=eng, seed=DEFAULT_SEED)
+    eenv.step_random(8)
+    planes = eng.empty((1 << 20, 7, 7, 7), torch.bfloat16)
+    eenv.encode(DTYPE_BF16, out=planes)
+    barrier()
+    reps = 10
+    t = _timed(lambda: eenv.encode(DTYPE_BF16, out=planes), reps, world)
+    n = (1 << 20) * reps * world
+    out["encode_bf16"] = {"metric": "positions_per_sec", "value": n / t, "unit": "positions/s",
+                          "bytes_per_position": 40 + 686, "achieved_gbs": (40 + 686) * (1 << 20) * reps / t / 1e9}
+    if peak_gbs:
+        out["encode_bf16"]["frac_of_hbm_peak"] = out["encode_bf16"]["achieved_gbs"] / peak_gbs
+    return out

@@ -144,6 +144,22 @@ int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const doub
 int ccx_mcts_finalize(ccx_handle *h, int64_t n, double tau, uint32_t *visits, double *pi, double *q, int32_t *n_nodes);
 int64_t ccx_mcts_pool_bytes(const ccx_handle *h);
 
+/* ---- policy/value net (model.py:15-145) -----------------------------------------------------------
+ * ccx_net_load takes the BN-folded fp32 weights packed by chinesecheckersagent_b200/model.py (layout in
+ * csrc/ccx_net.cu; ccx_net_num_weights() floats, HOST pointer — the one non-_host function that reads
+ * host memory, like Model.load_weights reading a file, model.py:45-47).
+ * ccx_net_forward: Keras predict on a batch: planes (n,7,7,7) channels-last of dtype CCX_DTYPE_* ->
+ *   logits float32[n][294] (linear policy head, model.py:112-116) and value float32[n] (tanh, :98-103).
+ * ccx_softmax_f64: utils.softmax in float64 over all 294 logits (model.py:23, utils.py:187-192);
+ *   v (may be NULL) receives value widened to float64.
+ * ccx_net_eval = utils.to_model_input + Model.predict for packed leaf states (uint64[5][n]): the
+ *   evaluator of the round-based MCTS (MCTS.py:93). */
+int ccx_net_num_weights(void);
+int ccx_net_load(ccx_handle *h, const float *packed_host, int64_t count);
+int ccx_net_forward(ccx_handle *h, int64_t n, const void *planes, int dtype, float *logits, float *value);
+int ccx_softmax_f64(ccx_handle *h, int64_t n, const float *logits, const float *value, double *p, double *v);
+int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p, double *v);
+
 /* ---- host-buffer variants: the reference-facing path with H2D/D2H inside the call -------------- */
 int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host);
 int ccx_apply_host(ccx_handle *h, int64_t n, uint64_t *state_host, const uint8_t *from_host,
