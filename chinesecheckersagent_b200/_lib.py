@@ -28,9 +28,9 @@ SIGNATURES = {
     "ccx_play_greedy": (i32, [vp, i64, vp, i64, u64, i32, vp]),
     "ccx_encode": (i32, [vp, i64, vp, vp, i32]),
     "ccx_mcts_search": (i32, [vp, i64, vp, i32, i32, f64, f64, i32, vp, i32, i32, vp, vp, vp, vp]),
-    "ccx_mcts_begin": (i32, [vp, i64, vp, i32, i32]),
+    "ccx_mcts_begin": (i32, [vp, i64, vp, i32, i32, i32]),
     "ccx_mcts_select": (i32, [vp, i64, f64, vp]),
-    "ccx_mcts_expand_backup": (i32, [vp, i64, vp, vp, vp, i32]),
+    "ccx_mcts_expand_backup": (i32, [vp, i64, vp, vp, vp, i32, i32]),
     "ccx_mcts_finalize": (i32, [vp, i64, f64, vp, vp, vp, vp]),
     "ccx_mcts_pool_bytes": (i64, [vp]),
     "ccx_net_num_weights": (i32, []),
@@ -38,6 +38,10 @@ SIGNATURES = {
     "ccx_net_forward": (i32, [vp, i64, vp, i32, vp, vp]),
     "ccx_softmax_f64": (i32, [vp, i64, vp, vp, vp, vp]),
     "ccx_net_eval": (i32, [vp, i64, vp, vp, vp]),
+    "ccx_gamma_noise": (i32, [vp, i64, i32, f64, u64, u32, i64, vp]),
+    "ccx_selfplay_advance": (i32, [vp, i64, vp, vp, vp, u64, i32, i64, vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "ccx_selfplay_finish": (i32, [vp, i64, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
+    "ccx_traj_pack": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
     "ccx_movegen_host": (i32, [vp, i64, vp, vp]),
     "ccx_apply_host": (i32, [vp, i64, vp, vp, vp, vp]),
     "ccx_step_random_host": (i32, [vp, i64, vp, i64, u64, u32, i32, vp]),

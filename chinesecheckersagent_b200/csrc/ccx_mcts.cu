@@ -286,24 +286,37 @@ __device__ __forceinline__ void eval_expand_backup(const TreeView &tv, int lane,
 }
 
 // selfplay.py:121-124 — root priors mixed with caller-supplied Dirichlet noise (one value per root edge)
-__device__ __forceinline__ void mix_root_noise(const TreeView &tv, int lane, const double *noise)
+__device__ __forceinline__ void mix_root_noise(const TreeView &tv, int lane, const double *noise, bool normalize = false)
 {
     u64 info = tv.node[5];
     int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    double scale = 1.0;
+    if (normalize) {                      // raw gamma draws -> Dirichlet sample over the ne root edges
+        double sum = 0.0;
+        for (int j = lane; j < ne; j += 32) sum += noise[j];
+#pragma unroll
+        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(FULL, sum, off);
+        scale = sum > 0.0 ? 1.0 / sum : 0.0;
+    }
     for (int j = lane; j < ne; j += 32) {
         double p = __dmul_rn(tv.eP[eb + j], 1. - 0.25);
-        tv.eP[eb + j] = __dadd_rn(p, __dmul_rn(0.25, noise[j]));
+        double nz = normalize ? noise[j] * scale : noise[j];
+        tv.eP[eb + j] = __dadd_rn(p, __dmul_rn(0.25, nz));
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u64 *roots, int64_t n, int64_t tree)
+// A root whose status is not RUNNING or whose ply count is below min_ply gets an inactive tree
+// (META_OVERFLOW = 2): every later phase skips it (self-play: opening random plies, finished games).
+__device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u64 *roots, int64_t n, int64_t tree, int min_ply = 0)
 {
     if (lane == 0) {
+        u64 m = roots[4 * n + tree];
+        bool inactive = min_ply >= 0 && ((m >> 56) != 0 || (int)((m >> 32) & 0xFFFF) < min_ply);
         Game g = game_of_words(roots[0 * n + tree], roots[1 * n + tree], roots[2 * n + tree], roots[3 * n + tree],
                                roots[4 * n + tree] & 0x00FFFFFFFFFFFFFFULL);
         store_node(tv, 0, g, make_info(0, 0, (u32)winner_of(g), 0));
-        tv.meta[META_NNODES] = 1; tv.meta[META_NEDGES] = 0; tv.meta[META_OVERFLOW] = 0; tv.meta[META_PATHLEN] = 0;
+        tv.meta[META_NNODES] = 1; tv.meta[META_NEDGES] = 0; tv.meta[META_OVERFLOW] = inactive ? 2 : 0; tv.meta[META_PATHLEN] = 0;
     }
     __syncwarp();
 }
@@ -318,7 +331,7 @@ k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num
     int lane = threadIdx.x & 31;
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
-    init_tree(tv, lane, roots, n, tree);
+    init_tree(tv, lane, roots, n, tree, -1);
     if (pre_expand && ((tv.node[5] >> 48) & 0xFF) == 0) {                    // selfplay.py:117
         eval_expand_backup<EVAL>(tv, lane, 0, 0);
         if (noise) mix_root_noise(tv, lane, noise + tree * noise_stride);
@@ -357,7 +370,7 @@ k_mcts_select(ccx_trees trees, int64_t n, double cpuct, u64 *__restrict__ leaf_s
 // and back up v[n]; root_only_noise != NULL mixes Dirichlet noise into the root priors (first call).
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, const double *__restrict__ v,
-                     const double *__restrict__ noise, int noise_stride)
+                     const double *__restrict__ noise, int noise_stride, int noise_normalize)
 {
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -368,16 +381,16 @@ k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, c
     Game g = load_node_game(tv, leaf);
     TablePrior pr = {p + tree * CCX_NUM_ACTIONS};
     if (expand_node(tv, lane, leaf, g, pr)) backup(tv, lane, path_len, v[tree], false);
-    if (noise && leaf == 0) mix_root_noise(tv, lane, noise + tree * noise_stride);
+    if (noise && leaf == 0) mix_root_noise(tv, lane, noise + tree * noise_stride, noise_normalize != 0);
 }
 
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
-k_mcts_init(ccx_trees trees, const u64 *__restrict__ roots, int64_t n)
+k_mcts_init(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int min_ply)
 {
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
-    init_tree(tv, threadIdx.x & 31, roots, n, tree);
+    init_tree(tv, threadIdx.x & 31, roots, n, tree, min_ply);
 }
 
 // ---- finalize (MCTS.py:131-137): visit counts, pi = N^(1/tau) / sum, root Q ---------------------------
@@ -418,7 +431,7 @@ k_mcts_finalize(ccx_trees trees, int64_t n, double inv_tau, u32 *__restrict__ vi
         if (q) q[tree * CCX_NUM_ACTIONS + idx] = N ? __ddiv_rn(tv.eW[eb + j], (double)N) : 0.0;
     }
     if (n_nodes && lane == 0)
-        n_nodes[tree] = tv.meta[META_OVERFLOW] ? -1 : tv.meta[META_NEDGES] + 1;   // reference node count: root + one per edge
+        n_nodes[tree] = tv.meta[META_OVERFLOW] ? -tv.meta[META_OVERFLOW] : tv.meta[META_NEDGES] + 1;   // reference node count: root + one per edge
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -485,13 +498,13 @@ int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t eva
     return CCX_OK;
 }
 
-int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree)
+int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree, int32_t min_ply)
 {
     if (!h || n < 0 || num_itr < 0 || (n && !roots)) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
     int rc = trees_reserve(h, n, num_itr, edges_per_tree);
     if (rc) return rc;
-    k_mcts_init<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n);
+    k_mcts_init<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, min_ply);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -506,11 +519,11 @@ int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state
 }
 
 int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const double *v, const double *root_noise,
-                           int32_t noise_stride)
+                           int32_t noise_stride, int32_t noise_normalize)
 {
     if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || (n && (!p || !v))) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
-    k_mcts_expand_backup<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, p, v, root_noise, noise_stride);
+    k_mcts_expand_backup<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, p, v, root_noise, noise_stride, noise_normalize);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

@@ -207,13 +207,13 @@ class BatchedMCTS:
         e = self.eng
         leaf = e.empty((5, n), torch.int64)
         stride = 0 if root_noise is None else root_noise.shape[1]
-        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree)
+        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree, -1)
         rounds = self.num_itr + (1 if pre_expand else 0)
         for r in range(rounds):
             e.call("ccx_mcts_select", n, self.cpuct, _p(leaf))
             p, v = evaluate(leaf)
             noise = root_noise if (pre_expand and r == 0) else None
-            e.call("ccx_mcts_expand_backup", n, _p(p), _p(v), _p(noise), stride if noise is not None else 0)
+            e.call("ccx_mcts_expand_backup", n, _p(p), _p(v), _p(noise), stride if noise is not None else 0, 0)
         visits, pi, q, nodes = self._outputs(n)
         e.call("ccx_mcts_finalize", n, self.tree_tau, _p(visits), _p(pi), _p(q), _p(nodes))
         return dict(visits=visits, pi=pi, q=q, n_nodes=nodes)

@@ -137,10 +137,16 @@ int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t eva
  * simulation  select -> [ccx_encode + net on leaf_state] -> expand_backup,  finally finalize.
  * leaf_state is uint64[5][n] (state words 0-4 of every tree's leaf; garbage-free for terminal leaves too);
  * p is float64[n][294] soft-maxed policy, v float64[n]; trees whose leaf was terminal ignore them. */
-int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree);
+/* min_ply: roots that are not RUNNING or have fewer plies get an inactive tree that every phase skips
+ * (self-play opening, selfplay.py:32; finished games); pass -1 to search every root.  n_nodes reports
+ * -1 for an overflowed pool and -2 for an inactive tree. */
+int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree,
+                   int32_t min_ply);
 int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state);
+/* root_noise is applied to trees whose expanded leaf is the root; noise_normalize != 0 divides each
+ * tree's first n_edges values by their sum first (raw gamma draws -> Dirichlet, selfplay.py:121). */
 int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const double *v, const double *root_noise,
-                           int32_t noise_stride);
+                           int32_t noise_stride, int32_t noise_normalize);
 int ccx_mcts_finalize(ccx_handle *h, int64_t n, double tau, uint32_t *visits, double *pi, double *q, int32_t *n_nodes);
 int64_t ccx_mcts_pool_bytes(const ccx_handle *h);
 
@@ -159,6 +165,35 @@ int ccx_net_load(ccx_handle *h, const float *packed_host, int64_t count);
 int ccx_net_forward(ccx_handle *h, int64_t n, const void *planes, int dtype, float *logits, float *value);
 int ccx_softmax_f64(ccx_handle *h, int64_t n, const float *logits, const float *value, double *p, double *v);
 int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p, double *v);
+
+/* ---- self-play (selfplay.py:11-133) and trajectory packing (utils.py:60-73) -------------------------
+ * One game slot per tree, all slots advanced one ply per iteration; see chinesecheckersagent_b200/selfplay.py
+ * for the driver loop.  Records live in caller-owned device buffers indexed rec = iter*n + slot:
+ *   rec_state uint64[rec_iters*n][5], rec_visits uint16[rec_iters*n][294], rec_flag uint8[rec_iters*n]
+ *   (low nibble: 0 none, 1 pending, 2 mover won, 3 mover lost, 4 dropped; 0x10 = pi uses DET_TREE_TAU).
+ * counters uint64[8] += {plies, P1 wins, P2 wins, repetition discards, progress-limit discards,
+ *   pool-overflow discards, records kept, games kept}.
+ * ccx_gamma_noise: raw Gamma(alpha) draws [n][stride] for the root Dirichlet noise (selfplay.py:121).
+ * ccx_selfplay_advance: opening plies (ply < random_plies) take selfplay.make_random_move's choice
+ *   (selfplay.py:83-104); later plies sample np.random.choice(294, p=pi) from this iteration's visit counts
+ *   (MCTS.py:131-140, tau = 0.01 once recorded + random_plies > tau_switch, selfplay.py:62-65), record
+ *   (state, visits) (selfplay.py:128), then apply the move and the repetition / progress / win / useless-move
+ *   rules in the reference's order (selfplay.py:40-74).  Game uid = serial*total_slots + uid0 + slot keys Philox.
+ * ccx_selfplay_finish: labels the records of games that ended (reward from the mover's point of view,
+ *   utils.py:65-71) or drops them for discarded games (selfplay.py:47,74); restart != 0 resets the slot.
+ * ccx_traj_pack: gathers kept records rows[m] into out_state uint64[5][m] (feed to ccx_encode for board_x),
+ *   pi_y float32[m][294] and v_y int8[m]. */
+int ccx_gamma_noise(ccx_handle *h, int64_t n, int32_t stride, double alpha, uint64_t seed, uint32_t iter, int64_t uid0,
+                    double *out);
+int ccx_selfplay_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32_t *visits, const int32_t *tree_nodes,
+                         uint64_t seed, int32_t iter, int64_t uid0, const int64_t *serial, int64_t total_slots,
+                         int32_t random_plies, int32_t tau_switch, int32_t move_limit, uint64_t *rec_state,
+                         uint16_t *rec_visits, uint8_t *rec_flag, int32_t rec_iters, uint64_t *counters,
+                         uint32_t *move_log /* may be NULL: [rec_iters*n] from | to<<8 | status<<16 | 1<<24 | mcts<<25 */);
+int ccx_selfplay_finish(ccx_handle *h, int64_t n, uint64_t *state, int32_t iter, int32_t *start_iter, int64_t *serial,
+                        const uint64_t *rec_state, uint8_t *rec_flag, int32_t rec_iters, int32_t restart, uint64_t *counters);
+int ccx_traj_pack(ccx_handle *h, int64_t m, const int64_t *rows, const uint64_t *rec_state, const uint16_t *rec_visits,
+                  const uint8_t *rec_flag, uint64_t *out_state, float *pi_y, int8_t *v_y);
 
 /* ---- host-buffer variants: the reference-facing path with H2D/D2H inside the call -------------- */
 int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host);
