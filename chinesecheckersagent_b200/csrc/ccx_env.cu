@@ -275,8 +275,9 @@ k_encode(const u64 *__restrict__ st, int64_t n, T *__restrict__ out)
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 int a = (int)((cur >> (8 * k)) & 0xFF), b = (int)((opp >> (8 * k)) & 0xFF);
-                t[((a >> 3) * 7 + (a & 7)) * 7 + 2 * h] = enc_val<T>(k + 1);
-                t[((b >> 3) * 7 + (b & 7)) * 7 + 2 * h + 1] = enc_val<T>(k + 1);
+                // cells of a well-formed state are < 55 with column < 7; anything else is ignored, never written
+                if (a < 55 && (a & 7) < 7) t[((a >> 3) * 7 + (a & 7)) * 7 + 2 * h] = enc_val<T>(k + 1);
+                if (b < 55 && (b & 7) < 7) t[((b >> 3) * 7 + (b & 7)) * 7 + 2 * h + 1] = enc_val<T>(k + 1);
             }
         }
         if (p2)

@@ -357,7 +357,16 @@ k_mcts_select(ccx_trees trees, int64_t n, double cpuct, u64 *__restrict__ leaf_s
     int lane = threadIdx.x & 31;
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
-    if (tv.meta[META_OVERFLOW]) { if (lane == 0) tv.meta[META_LEAFKIND] = LEAF_DEAD; return; }
+    if (tv.meta[META_OVERFLOW]) {
+        // inactive / overflowed tree: hand the evaluator a well-formed dummy position (its output is ignored)
+        if (lane == 0) {
+            tv.meta[META_LEAFKIND] = LEAF_DEAD;
+            leaf_state[0 * n + tree] = CCX_START_OCC1; leaf_state[1 * n + tree] = CCX_START_OCC2;
+            leaf_state[2 * n + tree] = CCX_START_CELLS1; leaf_state[3 * n + tree] = CCX_START_CELLS2;
+            leaf_state[4 * n + tree] = CCX_START_META;
+        }
+        return;
+    }
     int path_len, kind;
     int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
     __syncwarp();

@@ -41,8 +41,8 @@ class BatchedSelfPlay:
         self.serial = e.zeros((n,), torch.int64)
         self.start_iter = e.zeros((n,), torch.int32)
         self.counters = e.zeros((8,), torch.int64)
-        self.rec_state = e.empty((self.max_iters * n, 5), torch.int64)
-        self.rec_visits = e.empty((self.max_iters * n, 294), torch.int16)
+        self.rec_state = e.zeros((self.max_iters * n, 5), torch.int64)
+        self.rec_visits = e.zeros((self.max_iters * n, 294), torch.int16)
         self.rec_flag = e.zeros((self.max_iters * n,), torch.uint8)
         self.move_log = e.zeros((self.max_iters * n,), torch.int32) if log_moves else None
         self.iter = 0

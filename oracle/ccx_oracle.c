@@ -285,7 +285,10 @@ void orc_unpack(const uint64_t w[8], orc_board *b, int *to_move, int *status)
         uint8_t dest = (uint8_t)(w[5 + (k >> 3)] >> (8 * (k & 7)));
         uint8_t *h = b->hist[nh - 1 - k];
         h[0] = h[1] = 0xFF; h[2] = (uint8_t)CR(dest); h[3] = (uint8_t)CC(dest);
-        if (k < 2) { uint8_t from = (uint8_t)(meta >> (16 * k)); h[0] = (uint8_t)CR(from); h[1] = (uint8_t)CC(from); }
+        if (k < 2) {   /* the last two moves are authoritative in META (states may come without HIST words) */
+            uint8_t from = (uint8_t)(meta >> (16 * k)), to = (uint8_t)(meta >> (16 * k + 8));
+            h[0] = (uint8_t)CR(from); h[1] = (uint8_t)CC(from); h[2] = (uint8_t)CR(to); h[3] = (uint8_t)CC(to);
+        }
     }
 }
 

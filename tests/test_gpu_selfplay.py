@@ -71,18 +71,27 @@ def test_bookkeeping_matches_reference_rules(eng):
 
 
 def test_trajectory_format_and_contents(eng):
-    sp = run_selfplay(eng, n=512, iters=200, sims=8, seed=5)
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    model = ResidualCNN(engine=eng).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+    sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=256, num_itr=24, max_iters=130, seed=5)
+    sp.run(iters=130)
     traj = sp.collect()
     bx, pi, vy = traj["board_x"].cpu().numpy(), traj["pi_y"].cpu().numpy(), traj["v_y"].cpu().numpy()
     state = traj["state"].cpu().numpy().view(np.uint64)
     m = bx.shape[0]
     assert m == sp.stats()["records"]
-    if m == 0:
-        pytest.skip("no finished game in this short run")
+    st = sp.stats()
+    assert st["p1_wins"] + st["p2_wins"] > 0 and m > 0, st     # the net finishes games
     assert bx.shape == (m, 7, 7, 7) and pi.shape == (m, 294) and set(np.unique(vy)) <= {-1, 1}
     full = np.zeros((8, m), dtype=np.uint64); full[:5] = state
     assert np.array_equal(bx, orc.encode(full))                                  # utils.to_model_input of the root state
     assert np.allclose(pi.sum(1), 1.0, atol=1e-5)
+    # the reward alternates along a game and the first recorded ply is ply 6 with player 1 to move
+    plies = ((state[4] >> np.uint64(32)) & np.uint64(0xFFFF)).astype(int)
+    to_move = ((state[4] >> np.uint64(48)) & np.uint64(1)).astype(int)
+    assert plies.min() == 6 and np.all(to_move == (plies & 1))
+    assert np.all(to_move[plies == 6] == 0)
     masks = orc.movegen(full)                                                    # pi is supported on legal moves only
     for i in range(0, m, max(1, m // 200)):
         for a in np.nonzero(pi[i])[0]:
@@ -109,8 +118,10 @@ def test_gamma_noise_is_dirichlet_like(eng):
     assert abs(g.mean() - 0.03) < 0.003 and abs(g.var() - 0.03) < 0.006
     d = g / g.sum(1, keepdims=True)
     assert abs(d.mean() - 1 / stride) < 1e-6
-    # Dirichlet(0.03 * 1_32) is extremely sparse: the largest coordinate dominates
-    assert np.median(d.max(1)) > 0.8
+    # Dirichlet(0.03 * 1_32) against numpy's sampler (20k draws): median of the largest coordinate 0.630,
+    # mean number of coordinates above 0.01 is 4.23
+    assert 0.60 < np.median(d.max(1)) < 0.66
+    assert 3.9 < (d > 0.01).sum(1).mean() < 4.6
 
 
 def test_selfplay_with_real_net_smoke(eng):
