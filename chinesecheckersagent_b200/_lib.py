@@ -32,6 +32,8 @@ SIGNATURES = {
     "ccx_mcts_select": (i32, [vp, i64, f64, vp]),
     "ccx_mcts_expand_backup": (i32, [vp, i64, vp, vp, vp, i32, i32]),
     "ccx_mcts_finalize": (i32, [vp, i64, f64, vp, vp, vp, vp]),
+    "ccx_mcts_get_root": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),
+    "ccx_mcts_set_root_priors": (i32, [vp, i64, i32, vp]),
     "ccx_mcts_pool_bytes": (i64, [vp]),
     "ccx_net_num_weights": (i32, []),
     "ccx_net_load": (i32, [vp, vp, i64]),

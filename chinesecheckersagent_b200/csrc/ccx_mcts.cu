@@ -443,6 +443,39 @@ k_mcts_finalize(ccx_trees trees, int64_t n, double inv_tau, u32 *__restrict__ vi
         n_nodes[tree] = tv.meta[META_OVERFLOW] ? -tv.meta[META_OVERFLOW] : tv.meta[META_NEDGES] + 1;   // reference node count: root + one per edge
 }
 
+
+// ---- root edge access for the Python Node/Edge mirror (MCTS.py:24-37; selfplay.py:121-124 mutates P) ----
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_get_root(ccx_trees trees, int64_t n, int stride, int32_t *__restrict__ n_edges, uint16_t *__restrict__ moves,
+                u32 *__restrict__ N, double *__restrict__ W, double *__restrict__ P)
+{
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    u64 info = tv.node[5];
+    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    if (lane == 0) n_edges[tree] = ne;
+    for (int j = lane; j < ne && j < stride; j += 32) {
+        moves[tree * stride + j] = tv.eMove[eb + j];
+        N[tree * stride + j] = tv.eN[eb + j];
+        W[tree * stride + j] = tv.eW[eb + j];
+        P[tree * stride + j] = tv.eP[eb + j];
+    }
+}
+
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_set_root_priors(ccx_trees trees, int64_t n, int stride, const double *__restrict__ P)
+{
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    u64 info = tv.node[5];
+    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    for (int j = lane; j < ne && j < stride; j += 32) tv.eP[eb + j] = P[tree * stride + j];
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 
 void ccx_trees_free(ccx_handle *h)
@@ -542,6 +575,26 @@ int ccx_mcts_finalize(ccx_handle *h, int64_t n, double tau, uint32_t *visits, do
     if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || !(tau > 0.0) || (n && !visits)) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
     k_mcts_finalize<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, 1.0 / tau, visits, pi, q, n_nodes);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_mcts_get_root(ccx_handle *h, int64_t n, int32_t stride, int32_t *n_edges, uint16_t *moves, uint32_t *N, double *W,
+                      double *P)
+{
+    if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || stride < 1 || (n && (!n_edges || !moves || !N || !W || !P)))
+        return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_mcts_get_root<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, stride, n_edges, moves, N, W, P);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_mcts_set_root_priors(ccx_handle *h, int64_t n, int32_t stride, const double *P)
+{
+    if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || stride < 1 || (n && !P)) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_mcts_set_root_priors<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, stride, P);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

@@ -1,0 +1,53 @@
+"""Mirror of the reference's player.py: GreedyPlayer (player.py:67-129) and AiPlayer (player.py:133-166).
+HumanPlayer (interactive stdin) is out of scope."""
+import random
+
+import numpy as np
+
+from . import board_utils
+from . import engine as _engine
+from .config import DET_TREE_TAU, PLAYER_ONE, TOTAL_MOVES_TILL_TAU0
+from .MCTS import MCTS, Node
+
+
+class GreedyPlayer:
+    def __init__(self, player_num, stochastic=False):
+        if stochastic:
+            raise NotImplementedError("the stochastic greedy branch (player.py:77-97) is not on the hot path")
+        self.player_num, self.stochastic = player_num, stochastic
+
+    def decide_move(self, board, verbose=False, training=False, total_moves=None):
+        env = _engine.BatchedEnv(1, engine=board._eng, state=board._pack(self.player_num - 1))
+        masks = env.greedy_candidates().cpu().numpy().view(np.uint64)[:, 0]
+        moves = []
+        for cid in range(6):
+            m = int(masks[cid])
+            for b in range(55):
+                if (m >> b) & 1:
+                    moves.append((board.checkers_pos[self.player_num][cid], (b >> 3, b & 7)))
+        if not moves:
+            raise ValueError("max() arg is an empty sequence")              # what player.py:113 raises
+        if training:                                                        # player.py:117-118 (human coordinates)
+            return [(board_utils.np_index_to_human_coord(s), board_utils.np_index_to_human_coord(e)) for s, e in moves]
+        pick_start, pick_end = random.choice(moves)                         # player.py:121
+        if verbose:
+            board.visualise(cur_player=self.player_num)
+            print('GreedyPlayer moved from {} to {}\n'.format(board_utils.np_index_to_human_coord(pick_start),
+                                                              board_utils.np_index_to_human_coord(pick_end)))
+        return pick_start, pick_end
+
+
+class AiPlayer:
+    def __init__(self, player_num, model, tree_tau):
+        self.player_num, self.model, self.tree_tau = player_num, model, tree_tau
+
+    def decide_move(self, board, verbose=False, total_moves=None):
+        if verbose:
+            board.visualise(cur_player=self.player_num)
+            print('Facing the board above, Ai Version {} is thinking.'.format(self.model.version))
+        node = Node(board, self.player_num)
+        if total_moves is not None and total_moves > TOTAL_MOVES_TILL_TAU0:      # player.py:152-155
+            self.tree_tau = DET_TREE_TAU
+        tree = MCTS(node, self.model, tree_tau=self.tree_tau)
+        pi, sampled_edge = tree.search()                                         # player.py:157-158
+        return sampled_edge.fromPos, sampled_edge.toPos

@@ -127,3 +127,60 @@ def all_gather_trajectories(traj, group=None):
         dist.all_gather_into_tensor(full, pad, group=group)
         out[key] = torch.cat([full[r * mx:r * mx + counts[r]] for r in range(world)], dim=0)
     return out
+
+
+# ---- selfplay.selfplay(model1, model2=None, randomised=False), one game, same contract as selfplay.py:11-80 ----
+def selfplay(model1, model2=None, randomised=False, num_itr=MCTS_SIMULATIONS):
+    """Returns (play_history [(Board, pi)], reward for player 1) or (None, None) for a discarded game; what
+    train.py:62 calls.  For throughput use BatchedSelfPlay; this mirror exists for drop-in compatibility."""
+    import copy
+    import random
+
+    import numpy as np
+
+    from . import utils
+    from .board import Board
+    from .config import (BOARD_HIST_MOVES, DET_TREE_TAU, DIR_NOISE_FACTOR, NUM_CHECKERS, PLAYER_ONE, PLAYER_TWO,
+                         TOTAL_HIST_MOVES, TREE_TAU, UNIQUE_DEST_LIMIT)
+    from .MCTS import MCTS, Node
+    model2 = model2 or model1
+    player_progresses, player_turn, num_useless_moves, play_history, tree_tau = [0, 0], 0, 0, [], TREE_TAU
+    root = Node(Board(randomised=randomised), PLAYER_ONE)
+    use_model1 = True
+    while True:
+        model = model1 if use_model1 else model2
+        if len(root.state.hist_moves) < INITIAL_RANDOM_MOVES:                       # selfplay.py:32-33, 83-104
+            valid = root.state.get_valid_moves(root.currPlayer)
+            start = random.choice([k for k in valid if valid[k]])
+            nxt = copy.deepcopy(root.state)
+            nxt.place(root.currPlayer, start, random.choice(valid[start]))
+            root = Node(nxt, PLAYER_ONE + PLAYER_TWO - root.currPlayer)
+        else:                                                                       # selfplay.py:107-133
+            tree = MCTS(root, model, num_itr=num_itr, tree_tau=tree_tau)
+            tree.expandAndBackUp(tree.root, breadcrumbs=[])
+            noise = np.random.dirichlet(np.ones(len(tree.root.edges)) * DIRICHLET_ALPHA)
+            for i, e in enumerate(tree.root.edges):
+                e.stats['P'] *= (1. - DIR_NOISE_FACTOR)
+                e.stats['P'] += DIR_NOISE_FACTOR * noise[i]
+            pi, edge = tree.search()
+            play_history.append((tree.root.state, pi))
+            root = Node(copy.deepcopy(edge.outNode.state), edge.outNode.currPlayer)
+        hm = root.state.hist_moves
+        mine = [hm[i] for i in range(len(hm) - 1, -1, -2)]
+        if len(mine) * 2 >= TOTAL_HIST_MOVES and len(set(m[1] for m in mine)) <= UNIQUE_DEST_LIMIT:
+            return None, None                                                       # selfplay.py:45-47
+        progress = root.state.player_progress(player_turn + 1)
+        if progress > player_progresses[player_turn]:
+            num_useless_moves = int(num_useless_moves * (NUM_CHECKERS - 1) / NUM_CHECKERS)
+            player_progresses[player_turn] = progress
+        else:
+            num_useless_moves += 1
+        player_turn, use_model1 = 1 - player_turn, not use_model1
+        if len(play_history) + INITIAL_RANDOM_MOVES > TOTAL_MOVES_TILL_TAU0:
+            tree_tau = DET_TREE_TAU
+        if root.state.check_win():
+            break
+        if num_useless_moves >= PROGRESS_MOVE_LIMIT:
+            return None, None
+    reward = utils.get_p1_winloss_reward(root.state)
+    return (play_history[BOARD_HIST_MOVES:] if randomised else play_history), reward

@@ -1,0 +1,52 @@
+"""Mirror of the hot-path part of the reference's utils.py: to_model_input (utils.py:101-160, on the GPU),
+encode/decode_checker_index (utils.py:164-183), softmax (utils.py:187-192), get_p1_winloss_reward
+(utils.py:34-44) and convert_to_train_data (utils.py:60-73)."""
+import numpy as np
+
+from . import engine as _engine
+from .config import BOARD_HEIGHT, BOARD_WIDTH, DTYPE_U8, PLAYER_ONE, PLAYER_TWO, REWARD
+
+
+def to_model_input(board, cur_player):
+    """(7,7,7) float64 channels-last, like the reference; computed by the fused encoder kernel."""
+    env = _engine.BatchedEnv(1, engine=board._eng, state=board._pack(cur_player - 1))
+    return env.encode(DTYPE_U8)[0].cpu().numpy().astype(np.float64)
+
+
+def encode_checker_index(checker_id, coord):
+    return checker_id * BOARD_WIDTH * BOARD_HEIGHT + coord[0] * BOARD_WIDTH + coord[1]
+
+
+def decode_checker_index(model_output_index):
+    checker_id = model_output_index // (BOARD_WIDTH * BOARD_HEIGHT)
+    offset = model_output_index % (BOARD_WIDTH * BOARD_HEIGHT)
+    return checker_id, (offset // BOARD_WIDTH, offset % BOARD_WIDTH)
+
+
+def softmax(input):
+    input = np.copy(input).astype('float64')
+    input -= np.max(input, axis=-1, keepdims=True)
+    exps = np.exp(input)
+    return exps / np.sum(exps, axis=-1, keepdims=True)
+
+
+def get_p1_winloss_reward(board, winner=None):
+    winner = winner or board.check_win()
+    if winner == PLAYER_ONE:
+        return REWARD['win']
+    if winner == PLAYER_TWO:
+        return REWARD['lose']
+    return REWARD['draw']
+
+
+def convert_to_train_data(self_play_games):
+    board_x, pi_y, v_y = [], [], []
+    for history, reward in self_play_games:
+        curr_player = PLAYER_ONE
+        for board, pi in history:
+            board_x.append(to_model_input(board, curr_player))
+            pi_y.append(pi)
+            v_y.append(reward)
+            reward = -reward
+            curr_player = PLAYER_ONE + PLAYER_TWO - curr_player
+    return board_x, pi_y, v_y

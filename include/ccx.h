@@ -148,6 +148,12 @@ int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state
 int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const double *v, const double *root_noise,
                            int32_t noise_stride, int32_t noise_normalize);
 int ccx_mcts_finalize(ccx_handle *h, int64_t n, double tau, uint32_t *visits, double *pi, double *q, int32_t *n_nodes);
+/* Root edge list of every tree in edge order (Edge.stats of root.edges, MCTS.py:24-37): n_edges[n], and per
+ * edge j < min(n_edges, stride): moves = checker id << 8 | destination cell, N, W, P ([n][stride] each).
+ * ccx_mcts_set_root_priors overwrites P (callers mix Dirichlet noise into it, selfplay.py:121-124). */
+int ccx_mcts_get_root(ccx_handle *h, int64_t n, int32_t stride, int32_t *n_edges, uint16_t *moves, uint32_t *N, double *W,
+                      double *P);
+int ccx_mcts_set_root_priors(ccx_handle *h, int64_t n, int32_t stride, const double *P);
 int64_t ccx_mcts_pool_bytes(const ccx_handle *h);
 
 /* ---- policy/value net (model.py:15-145) -----------------------------------------------------------
