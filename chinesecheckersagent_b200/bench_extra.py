@@ -79,4 +79,38 @@ def run(eng, rank, world, barrier, peak_gbs=None):
                           "bytes_per_position": 40 + 686, "achieved_gbs": (40 + 686) * (1 << 20) * reps / t / 1e9}
     if peak_gbs:
         out["encode_bf16"]["frac_of_hbm_peak"] = out["encode_bf16"]["achieved_gbs"] / peak_gbs
+    # ---- cfg 5: full self-play, MCTS + good_model policy/value net, 4,096 concurrent trees per GPU ---------------
+    weights = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "good_model_weights.npz")
+    if os.path.exists(weights):
+        from .model import ResidualCNN
+        from .selfplay import BatchedSelfPlay, all_gather_trajectories
+        model = ResidualCNN(engine=eng).load_weights(weights)
+        sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=MCTS_TREES, seed=DEFAULT_SEED, rank=rank, world=world,
+                             num_itr=MCTS_SIMS, max_iters=16)
+        for _ in range(7):                                # 6 opening plies + 1 searched ply as warm-up
+            sp.step()
+        barrier()
+        l0 = eng.launches
+        reps = 2
+        t = _timed(sp.step, reps, world)
+        sims = world * MCTS_TREES * MCTS_SIMS * reps
+        evals = world * MCTS_TREES * (MCTS_SIMS + 1) * reps
+        out["selfplay_net"] = {"metric": "mcts_sims_per_sec", "value": sims / t, "unit": "sims/s", "net_evals_per_sec": evals / t,
+                               "trees_per_gpu": MCTS_TREES, "sims_per_move": MCTS_SIMS, "ms_per_ply_iteration": t / reps * 1e3,
+                               "net": "good_model.h5 (fixture copy), fused fp32 SIMT kernel", "gpu_launches": eng.launches - l0}
+        # net forward alone on a big batch
+        planes = torch.randint(0, 7, (65536, 7, 7, 7), dtype=torch.uint8, device=eng.device)
+        model.forward(planes)
+        barrier()
+        reps = 5
+        t = _timed(lambda: model.forward(planes), reps, world)
+        out["net_forward"] = {"metric": "positions_per_sec", "value": world * 65536 * reps / t, "unit": "positions/s",
+                              "tflops": 6.483264e6 * 65536 * reps / t / 1e12, "batch": 65536}
+        # trajectory all-gather (the only collective): time it when there is more than one rank
+        traj = sp.collect()
+        if world > 1:
+            all_gather_trajectories(traj)
+            barrier()
+            t = _timed(lambda: all_gather_trajectories(traj), 3, world)
+            out["trajectory_all_gather"] = {"ms": t / 3 * 1e3, "records_this_rank": int(traj["board_x"].shape[0])}
     return out
