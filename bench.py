@@ -35,6 +35,14 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def measured_peak_tflops():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"])
+    except Exception:
+        return 1590.0
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -197,7 +205,7 @@ def main():
     if not args.no_extra:
         try:
             from chinesecheckersagent_b200 import bench_extra
-            extra = bench_extra.run(eng, rank, world, barrier, peak_gbs=measured_peak_gbs()[0])
+            extra = bench_extra.run(eng, rank, world, barrier, peak_gbs=measured_peak_gbs()[0], peak_tflops=measured_peak_tflops())
         except ImportError:
             pass
 

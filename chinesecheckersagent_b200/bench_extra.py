@@ -29,7 +29,7 @@ def _timed(fn, reps, world):
     return float(t.item())
 
 
-def run(eng, rank, world, barrier, peak_gbs=None):
+def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
     out = {}
     # ---- cfg 4: MCTS, uniform-prior stub evaluator, 4,096 concurrent trees per GPU --------------------
     env = BatchedEnv(MCTS_TREES, engine=eng, seed=DEFAULT_SEED, game_id0=rank * MCTS_TREES)
@@ -97,15 +97,23 @@ def run(eng, rank, world, barrier, peak_gbs=None):
         evals = world * MCTS_TREES * (MCTS_SIMS + 1) * reps
         out["selfplay_net"] = {"metric": "mcts_sims_per_sec", "value": sims / t, "unit": "sims/s", "net_evals_per_sec": evals / t,
                                "trees_per_gpu": MCTS_TREES, "sims_per_move": MCTS_SIMS, "ms_per_ply_iteration": t / reps * 1e3,
-                               "net": "good_model.h5 (fixture copy), fused fp32 SIMT kernel", "gpu_launches": eng.launches - l0}
+                               "net": "good_model.h5 (fixture copy), tcgen05 kernels, fp16 operands / fp32 accumulate",
+                               "gpu_launches": eng.launches - l0}
         # net forward alone on a big batch
         planes = torch.randint(0, 7, (65536, 7, 7, 7), dtype=torch.uint8, device=eng.device)
-        model.forward(planes)
-        barrier()
-        reps = 5
-        t = _timed(lambda: model.forward(planes), reps, world)
-        out["net_forward"] = {"metric": "positions_per_sec", "value": world * 65536 * reps / t, "unit": "positions/s",
-                              "tflops": 6.483264e6 * 65536 * reps / t / 1e12, "batch": 65536}
+        for kern in ("tc", "simt"):
+            model.set_kernel(kern)
+            model.forward(planes)
+            barrier()
+            reps = 5
+            t = _timed(lambda: model.forward(planes), reps, world)
+            tf = 6.483264e6 * 65536 * reps / t / 1e12 * world
+            out["net_forward_" + kern] = {"metric": "positions_per_sec", "value": world * 65536 * reps / t, "unit": "positions/s",
+                                          "tflops": tf, "batch": 65536}
+            if kern == "tc" and peak_tflops:
+                out["net_forward_tc"]["roofline"] = {"bound": "tensor", "achieved": tf / world, "peak": peak_tflops, "unit": "TFLOP/s",
+                                                     "frac": tf / world / peak_tflops, "kernel": "k_net_trunk_tc + k_policy_dense_tc"}
+        model.set_kernel("tc")
         # trajectory all-gather (the only collective): time it when there is more than one rank
         traj = sp.collect()
         if world > 1:

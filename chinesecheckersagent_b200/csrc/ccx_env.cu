@@ -340,6 +340,7 @@ int ccx_destroy(ccx_handle *h)
     if (!h) return CCX_OK;
     cudaSetDevice(h->device);
     ccx_net_free(h);
+    ccx_net_tc_free(h);
     ccx_trees_free(h);
     ccx_scratch *s[] = {&h->d_state, &h->d_aux0, &h->d_aux1, &h->d_aux2};
     for (auto *p : s) if (p->ptr) cudaFree(p->ptr);
@@ -534,3 +535,4 @@ int ccx_encode_host(ccx_handle *h, int64_t n, const uint64_t *state_host, void *
 // weak defaults so that libccx.so links before the MCTS / net translation units exist
 __attribute__((weak)) void ccx_net_free(ccx_handle *) {}
 __attribute__((weak)) void ccx_trees_free(ccx_handle *) {}
+__attribute__((weak)) void ccx_net_tc_free(ccx_handle *) {}

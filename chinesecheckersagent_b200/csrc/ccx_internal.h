@@ -13,6 +13,7 @@ struct ccx_scratch {
 
 struct ccx_net;     // ccx_net.cu
 struct ccx_trees;   // ccx_mcts.cu
+struct ccx_net_tc;  // ccx_net_tc.cu
 
 struct ccx_handle {
     int device = 0;
@@ -24,6 +25,8 @@ struct ccx_handle {
     ccx_scratch d_state, d_aux0, d_aux1, d_aux2;
     ccx_net *net = nullptr;
     ccx_trees *trees = nullptr;
+    ccx_net_tc *net_tc = nullptr;
+    int net_mode = 0;           // 0 = fp32 SIMT kernel, 1 = bf16 tcgen05 kernels (ccx_net_set_mode)
 };
 
 static inline int ccx_fail(ccx_handle *h, cudaError_t e)
@@ -59,3 +62,4 @@ static inline int ccx_reserve(ccx_handle *h, ccx_scratch &s, size_t bytes)
 // sub-module teardown hooks (defined where the sub-module lives)
 void ccx_net_free(ccx_handle *h);
 void ccx_trees_free(ccx_handle *h);
+void ccx_net_tc_free(ccx_handle *h);

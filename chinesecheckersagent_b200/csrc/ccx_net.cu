@@ -315,6 +315,14 @@ int ccx_softmax_f64(ccx_handle *h, int64_t n, const float *logits, const float *
     return CCX_OK;
 }
 
+int ccx_net_set_mode(ccx_handle *h, int32_t mode)
+{
+    if (!h || (mode != 0 && mode != 1)) return CCX_ERR_ARG;
+    if (mode == 1 && !h->net_tc) return CCX_ERR_STATE;
+    h->net_mode = mode;
+    return CCX_OK;
+}
+
 // Model.predict for a batch of packed states (leaf_state = words 0-4, plane-major [5][n]):
 // to_model_input -> net -> float64 softmax.  The MCTS round loop's evaluator.
 int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p, double *v)
@@ -334,7 +342,9 @@ int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p
     }
     int rc;
     if ((rc = ccx_encode(h, n, leaf_state, nt->planes, CCX_DTYPE_U8))) return rc;
-    if ((rc = ccx_net_forward(h, n, nt->planes, CCX_DTYPE_U8, nt->logits, nt->value))) return rc;
+    if (h->net_mode == 1) rc = ccx_net_forward_tc(h, n, nt->planes, nt->logits, nt->value);
+    else rc = ccx_net_forward(h, n, nt->planes, CCX_DTYPE_U8, nt->logits, nt->value);
+    if (rc) return rc;
     return ccx_softmax_f64(h, n, nt->logits, nt->value, p, v);
 }
 

@@ -1,0 +1,474 @@
+// ccx_net_tc.cu — bf16 tensor-core (tcgen05 + TMEM) path of the policy/value net (model.py:58-145).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "ccx_device.cuh"
+#include "ccx_internal.h"
+#include "ccx_umma.cuh"
+#include <new>
+
+// ---- self-test of the UMMA plumbing: D[128 x N] = A[128 x K] * Bt[N x K]^T -------------------------------
+__global__ void __launch_bounds__(128)
+k_umma_selftest(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ Bt, int K, int N, float *__restrict__ D)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t *sa = smem, *sb = smem + umma::op_bytes(128, K);
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < 128 * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16 *>(sa + umma::op_offset(r, k, K)) = A[i];
+    }
+    for (int i = t; i < N * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16 *>(sb + umma::op_offset(r, k, K)) = Bt[i];
+    }
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 64);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (t == 0) {
+        umma::gemm_issue(tmem, umma::smem_u32(sa), K, 0, umma::smem_u32(sb), K, 0, K, N, false);
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    for (int c = 0; c < N; c += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (c + j < N) D[t * N + c + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 64);
+}
+
+extern "C" {
+
+int ccx_debug_umma_gemm(ccx_handle *h, const void *A, const void *Bt, int32_t K, int32_t N, float *D)
+{
+    if (!h || !A || !Bt || !D || K % 16 || K < 16 || K > 512 || N % 16 || N < 16 || N > 64) return CCX_ERR_ARG;
+    size_t smem = umma::op_bytes(128, K) + umma::op_bytes(N, K);
+    CCX_CUDA(h, cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest<<<1, 128, smem, h->stream>>>((const __nv_bfloat16 *)A, (const __nv_bfloat16 *)Bt, K, N, D);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// bf16 tensor-core forward pass.
+//
+// Kernel 1 (k_net_trunk_tc): persistent CTAs, 128 threads, one 128-row tile = 5 positions x 25 cells
+// (+3 idle rows) at a time.  Thread t owns row t for the whole network: it keeps the residual stream of
+// its cell in fp32 registers, reads each layer's accumulator row from TMEM (tcgen05.ld), applies bias /
+// ReLU / skip, and writes the bf16 operand row of the next layer straight into shared memory in the UMMA
+// core-matrix layout — for the 3x3 conv as an im2col scatter into the rows of its 8 neighbours.  One elected
+// thread issues the MMAs; completion is tracked with one mbarrier.  Activations never leave the SM.
+// Residual-block weights (26 KB bf16 per block, pre-arranged on the host in the operand layout) stream from
+// L2 through a double buffer with cp.async, one block ahead of the math.
+// Kernel 2 (k_policy_dense_tc): logits = flat(policy conv)[B x 400] * W[400 x 294] as 128-position tiles.
+//
+// Weight blobs (built by model.py pack_weights_tc):
+//   bf16 blob, byte offsets: CONV1 (N64,K64) | HEADS (N32,K64: 16 policy-conv cols, value-conv col, zeros) |
+//     9 x [A (N32,K64) | B (N32,K288) | C (N64,K32)] | policy dense: 2 N-halves x [K 0..207 (N160,K208) | K 208..399 (N160,K192)]
+//   fp32 blob: conv1_b[64] heads_b[32] 9 x (a_b[32] b_b[32] c_b[64]) pold_b[320] d1_w[25][32] d1_b[32] vh_w[32] vh_b[1]
+namespace tcl {
+constexpr int W_CONV1 = 0, W_HEADS = 8192, W_BLOCK0 = 12288, W_BLOCK = 26624, W_BA = 0, W_BB = 4096, W_BC = 4096 + 18432;
+constexpr int W_POLD = W_BLOCK0 + 9 * W_BLOCK;                 // 251,904
+constexpr int POLD_C0 = 160 * 208 * 2, POLD_C1 = 160 * 192 * 2, POLD_HALF = POLD_C0 + POLD_C1;
+constexpr int W_TOTAL = W_POLD + 2 * POLD_HALF;                // 507,904 bytes
+constexpr int F_CONV1 = 0, F_HEADS = 64, F_BLOCK0 = 96, F_BLOCK = 128, F_POLD = F_BLOCK0 + 9 * F_BLOCK;
+constexpr int F_D1W = F_POLD + 320, F_D1B = F_D1W + 800, F_VHW = F_D1B + 32, F_VHB = F_VHW + 32, F_TOTAL = F_VHB + 1;
+// shared memory map of the trunk kernel (bytes)
+constexpr int S_XA = 0, S_IM = S_XA + 128 * 64 * 2, S_M2 = S_IM + 128 * 288 * 2, S_WRES = S_M2 + 128 * 32 * 2;
+constexpr int S_WBUF = S_WRES + 12288, S_PLANES = S_WBUF + 2 * W_BLOCK, S_VALC = S_PLANES + 5 * 343 + 13;
+constexpr int S_TOTAL = S_VALC + 128 * 4;
+}  // namespace tcl
+
+struct ccx_net_tc {
+    uint8_t *wb = nullptr;      // bf16 operand blob
+    float *fb = nullptr;        // fp32 biases + value-head dense
+    __nv_bfloat16 *polc = nullptr;   // [cap][400] policy-conv activations between the two kernels (16-bit)
+    int64_t cap = 0;
+    int fp16 = 0;               // 0 = bf16 operands, 1 = IEEE half operands (same kernels, other instruction descriptor)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// two fp32 -> one 32-bit word of 16-bit operands: bf16 (FP16 = false) or IEEE half (FP16 = true)
+template <bool FP16> __device__ __forceinline__ uint32_t pack2(float a, float b)
+{
+    if (FP16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t *>(&h); }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(128, 1)
+k_net_trunk_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
+               __nv_bfloat16 *__restrict__ polc, float *__restrict__ value)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t sbase = umma::smem_u32(smem);
+    const int64_t n_tiles = (n + 4) / 5;
+
+    // one-time setup: zero the im2col operand (padding taps stay zero for ever), resident weights, TMEM
+    for (int i = t; i < (tcl::S_WRES - tcl::S_XA) / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = t; i < 12288 / 16; i += 128) cp_async16(sbase + tcl::S_WRES + i * 16, wb + i * 16);     // CONV1 + HEADS
+    cp_async_commit();
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+    // prefetch block 0's weights for the first tile
+    for (int i = t; i < tcl::W_BLOCK / 16; i += 128) cp_async16(sbase + tcl::S_WBUF + i * 16, wb + tcl::W_BLOCK0 + i * 16);
+    cp_async_commit();
+    cp_async_wait<1>();                     // resident weights have landed (block 0 may still be in flight)
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 TMEM lanes
+    uint32_t phase = 0;
+    int wslot = 0;                          // which half of the double buffer holds the block about to run
+
+    const int p_local = t / 25, cell = t % 25, cy = cell / 5, cx = cell % 5;
+    const bool row_live = t < 125;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t pos0 = tile * 5;
+        const int n_pos = (int)min((int64_t)5, n - pos0);
+        // ---- stage the input planes (uint8, values 0..6) ------------------------------------------------
+        for (int i = t; i < n_pos * 343; i += 128) smem[tcl::S_PLANES + i] = planes[pos0 * 343 + i];
+        __syncthreads();
+        // ---- conv1 operand: im2col of the 3x3 'valid' window, K = 63 (+1 zero) (model.py:62) ---------------
+        {
+            const bool ok = row_live && p_local < n_pos;
+            const uint8_t *pl = smem + tcl::S_PLANES + p_local * 343;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; c8++) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int kk = c8 * 8 + q;
+                    const int tap = kk / 7, ch = kk % 7, dy = tap / 3, dx = tap % 3;
+                    v[q] = (ok && kk < 63) ? (float)pl[((cy + dy) * 7 + (cx + dx)) * 7 + ch] : 0.f;
+                }
+                uint4 o = make_uint4(pack2<FP16>(v[0], v[1]), pack2<FP16>(v[2], v[3]), pack2<FP16>(v[4], v[5]), pack2<FP16>(v[6], v[7]));
+                *reinterpret_cast<uint4 *>(smem + tcl::S_XA + umma::op_offset(t, c8 * 8, 64)) = o;
+            }
+        }
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+        float x[64];                        // residual stream of this row, fp32
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, sbase + tcl::S_WRES + tcl::W_CONV1, 64, 0, 64, 64, false, FP16);
+            umma::commit(&bar);
+        }
+        umma::mbar_wait(&bar, phase); phase ^= 1;
+        umma::fence_after_sync();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float v[32];
+            umma::tmem_ld32(trow + 32 * h, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[32 * h + j] = fmaxf(v[j] + __ldg(fb + tcl::F_CONV1 + 32 * h + j), 0.f);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 8; c8++)
+            *reinterpret_cast<uint4 *>(smem + tcl::S_XA + umma::op_offset(t, c8 * 8, 64)) =
+                make_uint4(pack2<FP16>(x[c8 * 8], x[c8 * 8 + 1]), pack2<FP16>(x[c8 * 8 + 2], x[c8 * 8 + 3]),
+                           pack2<FP16>(x[c8 * 8 + 4], x[c8 * 8 + 5]), pack2<FP16>(x[c8 * 8 + 6], x[c8 * 8 + 7]));
+
+        // ---- 9 bottleneck residual blocks (model.py:120-145) --------------------------------------------------
+        for (int b = 0; b < 9; b++) {
+            // prefetch the next block's weights (cyclic: block 0 of the next tile after block 8) into the other slot
+            {
+                const uint8_t *src = wb + tcl::W_BLOCK0 + ((b + 1) % 9) * tcl::W_BLOCK;
+                const uint32_t dst = sbase + tcl::S_WBUF + (wslot ^ 1) * tcl::W_BLOCK;
+                for (int i = t; i < tcl::W_BLOCK / 16; i += 128) cp_async16(dst + i * 16, src + i * 16);
+                cp_async_commit();
+            }
+            cp_async_wait<1>();             // this block's weights (committed one block ago) have landed
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            const uint32_t wcur = sbase + tcl::S_WBUF + wslot * tcl::W_BLOCK;
+            const float *bias = fb + tcl::F_BLOCK0 + b * tcl::F_BLOCK;
+            // A: 1x1 conv 64 -> 32, ReLU
+            if (t == 0) {
+                umma::fence_after_sync();
+                umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, wcur + tcl::W_BA, 64, 0, 64, 32, false, FP16);
+                umma::commit(&bar);
+            }
+            umma::mbar_wait(&bar, phase); phase ^= 1;
+            umma::fence_after_sync();
+            {
+                float v[32];
+                umma::tmem_ld32(trow, v);
+                uint4 o[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float r[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) r[q] = fmaxf(v[c * 8 + q] + __ldg(bias + c * 8 + q), 0.f);
+                    o[c] = make_uint4(pack2<FP16>(r[0], r[1]), pack2<FP16>(r[2], r[3]), pack2<FP16>(r[4], r[5]), pack2<FP16>(r[6], r[7]));
+                }
+                // im2col scatter for the 3x3 'same' conv: this cell is input tap (dy,dx) of output cell (cy-dy, cx-dx)
+                if (row_live) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) {
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        const int oy = cy - dy, ox = cx - dx;
+                        if (oy < 0 || oy > 4 || ox < 0 || ox > 4) continue;
+                        const int orow = p_local * 25 + oy * 5 + ox;
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            *reinterpret_cast<uint4 *>(smem + tcl::S_IM + umma::op_offset(orow, tap * 32 + c * 8, 288)) = o[c];
+                    }
+                }
+            }
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            // B: 3x3 conv 32 -> 32 as one K = 288 GEMM, ReLU
+            if (t == 0) {
+                umma::fence_after_sync();
+                umma::gemm_issue(tmem + 32, sbase + tcl::S_IM, 288, 0, wcur + tcl::W_BB, 288, 0, 288, 32, false, FP16);
+                umma::commit(&bar);
+            }
+            umma::mbar_wait(&bar, phase); phase ^= 1;
+            umma::fence_after_sync();
+            {
+                float v[32];
+                umma::tmem_ld32(trow + 32, v);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float r[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) r[q] = fmaxf(v[c * 8 + q] + __ldg(bias + 32 + c * 8 + q), 0.f);
+                    *reinterpret_cast<uint4 *>(smem + tcl::S_M2 + umma::op_offset(t, c * 8, 32)) =
+                        make_uint4(pack2<FP16>(r[0], r[1]), pack2<FP16>(r[2], r[3]), pack2<FP16>(r[4], r[5]), pack2<FP16>(r[6], r[7]));
+                }
+            }
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            // C: 1x1 conv 32 -> 64, + skip, ReLU (model.py:137-144)
+            if (t == 0) {
+                umma::fence_after_sync();
+                umma::gemm_issue(tmem + 64, sbase + tcl::S_M2, 32, 0, wcur + tcl::W_BC, 32, 0, 32, 64, false, FP16);
+                umma::commit(&bar);
+            }
+            umma::mbar_wait(&bar, phase); phase ^= 1;
+            umma::fence_after_sync();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float v[32];
+                umma::tmem_ld32(trow + 64 + 32 * h, v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) x[32 * h + j] = fmaxf(v[j] + __ldg(bias + 64 + 32 * h + j) + x[32 * h + j], 0.f);
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 8; c8++)
+                *reinterpret_cast<uint4 *>(smem + tcl::S_XA + umma::op_offset(t, c8 * 8, 64)) =
+                    make_uint4(pack2<FP16>(x[c8 * 8], x[c8 * 8 + 1]), pack2<FP16>(x[c8 * 8 + 2], x[c8 * 8 + 3]),
+                               pack2<FP16>(x[c8 * 8 + 4], x[c8 * 8 + 5]), pack2<FP16>(x[c8 * 8 + 6], x[c8 * 8 + 7]));
+            wslot ^= 1;
+        }
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- heads: policy conv 64 -> 16 and value conv 64 -> 1 in one N = 32 GEMM (model.py:91, 108) ------------
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, sbase + tcl::S_WRES + tcl::W_HEADS, 64, 0, 64, 32, false, FP16);
+            umma::commit(&bar);
+        }
+        umma::mbar_wait(&bar, phase); phase ^= 1;
+        umma::fence_after_sync();
+        {
+            float v[32];
+            umma::tmem_ld32(trow, v);
+            float *valc = reinterpret_cast<float *>(smem + tcl::S_VALC);
+            valc[t] = fmaxf(v[16] + __ldg(fb + tcl::F_HEADS + 16), 0.f);
+            if (row_live && p_local < n_pos) {
+                uint4 o[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    float r[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) r[q] = fmaxf(v[c * 8 + q] + __ldg(fb + tcl::F_HEADS + c * 8 + q), 0.f);
+                    o[c] = make_uint4(pack2<FP16>(r[0], r[1]), pack2<FP16>(r[2], r[3]), pack2<FP16>(r[4], r[5]), pack2<FP16>(r[6], r[7]));
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(polc + (pos0 + p_local) * 400 + cell * 16);      // Flatten in (y, x, c) order
+                dst[0] = o[0]; dst[1] = o[1];
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- value head: dense_1 25 -> 32 ReLU, value_head 32 -> 1 tanh (model.py:95-103), fp32 ---------------------
+        for (int p = warp; p < n_pos; p += 4) {
+            const float *valc = reinterpret_cast<const float *>(smem + tcl::S_VALC) + p * 25;
+            float acc = __ldg(fb + tcl::F_D1B + lane);
+            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], __ldg(fb + tcl::F_D1W + k * 32 + lane), acc);
+            float s = fmaxf(acc, 0.f) * __ldg(fb + tcl::F_VHW + lane);
+#pragma unroll
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+            if (lane == 0) value[pos0 + p] = tanhf(s + __ldg(fb + tcl::F_VHB));
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 128);
+}
+
+// logits[B x 294] = polc[B x 400] (bf16) * W (bf16) + b  —  128 positions x 160 outputs per CTA, K in two chunks
+template <bool FP16>
+__global__ void __launch_bounds__(128, 1)
+k_policy_dense_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const __nv_bfloat16 *__restrict__ polc, int64_t n,
+                  float *__restrict__ logits)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    const int half = blockIdx.y;
+    const int64_t row0 = (int64_t)blockIdx.x * 128;
+    const uint32_t sbase = umma::smem_u32(smem);
+    constexpr int SA = 0, SB = 128 * 208 * 2;
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    uint32_t phase = 0;
+    for (int chunk = 0; chunk < 2; chunk++) {
+        const int k0 = chunk ? 208 : 0, Kc = chunk ? 192 : 208;
+        // A chunk: rows row0..row0+127, columns k0..k0+Kc of polc (16-byte pieces into the operand layout)
+        const int pieces = Kc / 8;
+        for (int i = t; i < 128 * pieces; i += 128) {
+            const int r = i / pieces, k8 = i % pieces;
+            const int64_t row = row0 + r;
+            const uint32_t dst = sbase + SA + umma::op_offset(r, k8 * 8, Kc);
+            if (row < n) cp_async16(dst, polc + row * 400 + k0 + k8 * 8);
+            else *reinterpret_cast<uint4 *>(smem + SA + umma::op_offset(r, k8 * 8, Kc)) = make_uint4(0, 0, 0, 0);
+        }
+        const uint8_t *wsrc = wb + tcl::W_POLD + half * tcl::POLD_HALF + (chunk ? tcl::POLD_C0 : 0);
+        const int wbytes = chunk ? tcl::POLD_C1 : tcl::POLD_C0;
+        for (int i = t; i < wbytes / 16; i += 128) cp_async16(sbase + SB + i * 16, wsrc + i * 16);
+        cp_async_commit();
+        cp_async_wait<0>();
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+            umma::fence_after_sync();
+            umma::gemm_issue(tmem, sbase + SA, Kc, 0, sbase + SB, Kc, 0, Kc, 160, chunk > 0, FP16);
+            umma::commit(&bar);
+        }
+        umma::mbar_wait(&bar, phase); phase ^= 1;       // operands are free to be overwritten once the MMAs are done
+        umma::fence_after_sync();
+    }
+    const int64_t row = row0 + t;
+    for (int c = 0; c < 160; c += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        if (row < n) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int col = half * 160 + c + j;
+                if (col < CCX_NUM_ACTIONS) logits[row * CCX_NUM_ACTIONS + col] = v[j] + __ldg(fb + tcl::F_POLD + col);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 256);
+}
+
+static ccx_net_tc *tc_of(ccx_handle *h, bool create)
+{
+    if (!h->net_tc && create) h->net_tc = new (std::nothrow) ccx_net_tc();
+    return h->net_tc;
+}
+
+void ccx_net_tc_free(ccx_handle *h)
+{
+    ccx_net_tc *tc = h->net_tc;
+    if (!tc) return;
+    cudaFree(tc->wb); cudaFree(tc->fb); cudaFree(tc->polc);
+    delete tc;
+    h->net_tc = nullptr;
+}
+
+extern "C" {
+
+int ccx_net_tc_blob_bytes(void) { return tcl::W_TOTAL; }
+int ccx_net_tc_num_floats(void) { return tcl::F_TOTAL; }
+
+int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_bytes, const float *f32_host, int64_t n_floats,
+                    int32_t fp16)
+{
+    if (!h || !bf16_blob_host || !f32_host || blob_bytes != tcl::W_TOTAL || n_floats != tcl::F_TOTAL || (fp16 != 0 && fp16 != 1))
+        return CCX_ERR_ARG;
+    ccx_net_tc *tc = tc_of(h, true);
+    if (!tc) return CCX_ERR_NOMEM;
+    if (!tc->wb) CCX_CUDA(h, cudaMalloc(&tc->wb, tcl::W_TOTAL));
+    if (!tc->fb) CCX_CUDA(h, cudaMalloc(&tc->fb, sizeof(float) * tcl::F_TOTAL));
+    CCX_CUDA(h, cudaMemcpyAsync(tc->wb, bf16_blob_host, tcl::W_TOTAL, cudaMemcpyHostToDevice, h->stream));
+    CCX_CUDA(h, cudaMemcpyAsync(tc->fb, f32_host, sizeof(float) * tcl::F_TOTAL, cudaMemcpyHostToDevice, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    tc->fp16 = fp16;
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 208 * 2 + 160 * 208 * 2));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 208 * 2 + 160 * 208 * 2));
+    return CCX_OK;
+}
+
+// planes: uint8 (n,7,7,7) on the device -> logits float32[n][294], value float32[n]
+int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value)
+{
+    if (!h || n < 0 || (n && (!planes || !logits || !value))) return CCX_ERR_ARG;
+    ccx_net_tc *tc = tc_of(h, false);
+    if (!tc || !tc->wb) return CCX_ERR_STATE;
+    if (n == 0) return CCX_OK;
+    if (tc->cap < n) {
+        if (tc->polc) CCX_CUDA(h, cudaFree(tc->polc));
+        tc->polc = nullptr; tc->cap = 0;
+        CCX_CUDA(h, cudaMalloc(&tc->polc, sizeof(__nv_bfloat16) * 400 * (size_t)n));
+        tc->cap = n;
+    }
+    int64_t tiles = (n + 4) / 5;
+    unsigned grid = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    if (tc->fp16) k_net_trunk_tc<true><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+    else k_net_trunk_tc<false><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+    CCX_LAUNCHED(h);
+    dim3 g2((unsigned)((n + 127) / 128), 2);
+    constexpr int SM2 = 128 * 208 * 2 + 160 * 208 * 2;
+    if (tc->fp16) k_policy_dense_tc<true><<<g2, 128, SM2, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+    else k_policy_dense_tc<false><<<g2, 128, SM2, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+}  // extern "C"

@@ -52,6 +52,50 @@ def pack_weights(w):
     return np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64) for p in parts]).astype(np.float32))
 
 
+def _op_layout(Wt, fp16=False):
+    """[N][K] float matrix -> bf16 bytes in the UMMA K-major core-matrix operand layout (csrc/ccx_umma.cuh):
+    byte offset of (n, k) = (n//8)*(K//8)*128 + (k//8)*128 + (n%8)*16 + (k%8)*2."""
+    N, K = Wt.shape
+    assert N % 8 == 0 and K % 8 == 0
+    bits = torch.from_numpy(np.ascontiguousarray(Wt, dtype=np.float32)).to(torch.float16 if fp16 else torch.bfloat16).view(torch.int16).numpy()
+    out = np.zeros(N * K, dtype=np.int16)
+    n, k = np.meshgrid(np.arange(N), np.arange(K), indexing="ij")
+    off = (n // 8) * (K // 8) * 64 + (k // 8) * 64 + (n % 8) * 8 + (k % 8)        # in 2-byte elements
+    out[off.ravel()] = bits.ravel()
+    return out
+
+
+def pack_weights_tc(w, fp16=False):
+    """Keras tensors -> (bf16 operand blob as int16 array, fp32 bias blob) for ccx_net_load_tc
+    (layout: csrc/ccx_net_tc.cu header).  Every weight matrix is stored transposed ([N][K]) and BN-folded."""
+    ops, fl = [], []
+
+    def folded(i):
+        m, b = _fold(w, i)                       # (K, N), (N,)
+        return m, b
+    m, b = folded(1)                             # conv1: K 63 -> 64
+    ops.append(_op_layout(np.pad(m, ((0, 1), (0, 0))).T, fp16)); fl.append(b)
+    mp, bp = folded(29)                          # policy conv (64,16)
+    mv, bv = folded(30)                          # value conv (64,1)
+    heads = np.zeros((64, 32)); heads[:, :16] = mp; heads[:, 16] = mv[:, 0]
+    hb = np.zeros(32); hb[:16] = bp; hb[16] = bv[0]
+    ops.append(_op_layout(heads.T, fp16)); fl.append(hb)
+    for blk in range(9):
+        for i in (2 + 3 * blk, 3 + 3 * blk, 4 + 3 * blk):
+            m, b = folded(i)
+            ops.append(_op_layout(m.T, fp16)); fl.append(b)
+    Wd = np.zeros((400, 320)); Wd[:, :294] = w["policy_head/kernel"]
+    bd = np.zeros(320); bd[:294] = w["policy_head/bias"]
+    for half in range(2):
+        Wh = Wd[:, half * 160:(half + 1) * 160]
+        ops.append(_op_layout(Wh[:208].T, fp16)); ops.append(_op_layout(Wh[208:].T, fp16))
+    fl.extend([bd, w["dense_1/kernel"].ravel(), w["dense_1/bias"].ravel(), w["value_head/kernel"].ravel(),
+               w["value_head/bias"].ravel()])
+    blob = np.ascontiguousarray(np.concatenate(ops))
+    floats = np.ascontiguousarray(np.concatenate([np.asarray(f, dtype=np.float64).ravel() for f in fl]).astype(np.float32))
+    return blob, floats
+
+
 class Model:
     """model.py:15-47"""
 
@@ -67,13 +111,38 @@ class ResidualCNN(Model):
         from .engine import Engine
         self.eng = engine or Engine(0)
         self.loaded = False
+        self.kernel = "tc"
+        self.tc_dtype = "fp16"      # IEEE-half operands: 8x smaller error than bf16 at the same speed
 
     def load_weights(self, filepath):
-        packed = pack_weights(read_weight_file(filepath))
+        weights = read_weight_file(filepath)
+        packed = pack_weights(weights)
         if packed.size != self.eng.L.ccx_net_num_weights():
             raise _lib.CcxError("weight file does not describe the 9-block ResidualCNN")
         self.eng.call("ccx_net_load", ctypes.c_void_p(packed.ctypes.data), packed.size)
+        self._weights = weights
+        self._load_tc()
         self.loaded = True
+        self.set_kernel(self.kernel)
+        return self
+
+    def _load_tc(self):
+        blob, floats = pack_weights_tc(self._weights, fp16=self.tc_dtype == "fp16")
+        assert blob.nbytes == self.eng.L.ccx_net_tc_blob_bytes() and floats.size == self.eng.L.ccx_net_tc_num_floats()
+        self.eng.call("ccx_net_load_tc", ctypes.c_void_p(blob.ctypes.data), blob.nbytes, ctypes.c_void_p(floats.ctypes.data),
+                      floats.size, 1 if self.tc_dtype == "fp16" else 0)
+
+    def set_kernel(self, kernel, tc_dtype=None):
+        """'tc' = tcgen05 tensor-core kernels (default; operands bf16 or fp16, fp32 accumulation), 'simt' = fp32 SIMT kernel."""
+        assert kernel in ("tc", "simt")
+        self.kernel = kernel
+        if tc_dtype is not None and tc_dtype != self.tc_dtype:
+            assert tc_dtype in ("bf16", "fp16")
+            self.tc_dtype = tc_dtype
+            if self.loaded:
+                self._load_tc()
+        if self.loaded:
+            self.eng.call("ccx_net_set_mode", 1 if kernel == "tc" else 0)
         return self
 
     # -- batched inference ---------------------------------------------------------------------------
@@ -85,6 +154,12 @@ class ResidualCNN(Model):
         n = planes.shape[0]
         logits = self.eng.empty((n, NUM_ACTIONS), torch.float32)
         value = self.eng.empty((n,), torch.float32)
+        if self.kernel == "tc":
+            if planes.dtype != torch.uint8:
+                planes = planes.to(torch.uint8)          # plane values are the integers 0..6 (utils.py:123-128)
+            self.eng.call("ccx_net_forward_tc", n, ctypes.c_void_p(planes.data_ptr()), ctypes.c_void_p(logits.data_ptr()),
+                          ctypes.c_void_p(value.data_ptr()))
+            return logits, value
         self.eng.call("ccx_net_forward", n, ctypes.c_void_p(planes.data_ptr()), dt,
                       ctypes.c_void_p(logits.data_ptr()), ctypes.c_void_p(value.data_ptr()))
         return logits, value

@@ -171,6 +171,17 @@ int ccx_net_load(ccx_handle *h, const float *packed_host, int64_t count);
 int ccx_net_forward(ccx_handle *h, int64_t n, const void *planes, int dtype, float *logits, float *value);
 int ccx_softmax_f64(ccx_handle *h, int64_t n, const float *logits, const float *value, double *p, double *v);
 int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p, double *v);
+/* bf16 tensor-core path (tcgen05.mma + TMEM, activations resident in shared memory): the weights arrive as
+ * a bf16 blob already arranged in the UMMA operand layout plus an fp32 blob of biases (model.py
+ * pack_weights_tc; sizes from ccx_net_tc_blob_bytes / ccx_net_tc_num_floats; HOST pointers).
+ * ccx_net_forward_tc takes uint8 planes (n,7,7,7).  ccx_net_set_mode(1) makes ccx_net_eval use it. */
+int ccx_net_tc_blob_bytes(void);
+int ccx_net_tc_num_floats(void);
+/* fp16 = 0: the blob holds bf16 operands (kind::f16 with BF16 formats); fp16 = 1: IEEE half operands */
+int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_bytes, const float *f32_host, int64_t n_floats,
+                    int32_t fp16);
+int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value);
+int ccx_net_set_mode(ccx_handle *h, int32_t mode);
 
 /* ---- self-play (selfplay.py:11-133) and trajectory packing (utils.py:60-73) -------------------------
  * One game slot per tree, all slots advanced one ply per iteration; see chinesecheckersagent_b200/selfplay.py
@@ -200,6 +211,10 @@ int ccx_selfplay_finish(ccx_handle *h, int64_t n, uint64_t *state, int32_t iter,
                         const uint64_t *rec_state, uint8_t *rec_flag, int32_t rec_iters, int32_t restart, uint64_t *counters);
 int ccx_traj_pack(ccx_handle *h, int64_t m, const int64_t *rows, const uint64_t *rec_state, const uint16_t *rec_visits,
                   const uint8_t *rec_flag, uint64_t *out_state, float *pi_y, int8_t *v_y);
+
+/* Self-test of the tcgen05/TMEM plumbing used by the bf16 net kernel: D[128][N] = A[128][K] * Bt[N][K]^T
+ * (bf16 in, fp32 out; K multiple of 16 up to 512, N multiple of 16 up to 64).  Used by the GPU tests. */
+int ccx_debug_umma_gemm(ccx_handle *h, const void *A, const void *Bt, int32_t K, int32_t N, float *D);
 
 /* ---- host-buffer variants: the reference-facing path with H2D/D2H inside the call -------------- */
 int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host);
