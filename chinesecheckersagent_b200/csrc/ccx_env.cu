@@ -33,6 +33,15 @@ __device__ __forceinline__ void store_game(u64 *__restrict__ st, int64_t n, int6
     st[4 * n + i] = g.meta;
 }
 
+// ray-jump table: built once per handle in global memory, staged into shared memory by every block
+__global__ void k_build_jump_table(uint8_t *T) { build_jump_table(T, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+
+#define LOAD_JUMP_TABLE(sT, gT)                                                                   \
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];                                            \
+    for (int q__ = threadIdx.x; q__ < CCX_JT_BYTES / 16; q__ += blockDim.x)                        \
+        reinterpret_cast<uint4 *>(sT)[q__] = reinterpret_cast<const uint4 *>(gT)[q__];             \
+    __syncthreads();
+
 // --------------------------------------------------------------------------------------------------
 // K0 reset  (board.py:10-57, 61-85)
 
@@ -74,13 +83,14 @@ k_reset(u64 *__restrict__ st, int64_t n, int mode, u32 k0, u32 k1, int64_t gid0)
 // K1 movegen  (board.py:139-222)
 
 __global__ void __launch_bounds__(ENV_THREADS)
-k_movegen(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ masks)
+k_movegen(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ masks, const uint8_t *__restrict__ jt)
 {
+    LOAD_JUMP_TABLE(sT, jt)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Game g = load_game(st, n, i);
     u64 dest[6];
-    movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+    movegen_rays(g.occ_me | g.occ_op, g.cells_me, dest, sT);
 #pragma unroll
     for (int k = 0; k < 6; k++) masks[k * n + i] = dest[k];
 }
@@ -132,8 +142,9 @@ k_info(const u64 *__restrict__ st, int64_t n, int16_t *__restrict__ out)
 template <bool TRACE>
 __global__ void __launch_bounds__(ENV_THREADS)
 k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies,
-              u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games)
+              u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games, const uint8_t *__restrict__ jt)
 {
+    LOAD_JUMP_TABLE(sT, jt)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Game g = load_game(st, n, i);
@@ -141,7 +152,7 @@ k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32
     u32 w1 = 0, w2 = 0;
     for (int t = 0; t < plies; t++) {
         u64 dest[6];
-        movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+        movegen_rays(g.occ_me | g.occ_op, g.cells_me, dest, sT);
         u32 nonempty = 0;
 #pragma unroll
         for (int k = 0; k < 6; k++) nonempty += dest[k] != 0;
@@ -177,13 +188,14 @@ k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32
 // K4 greedy  (player.py:99-121, board_utils.py:3-7)
 
 __global__ void __launch_bounds__(ENV_THREADS)
-k_greedy_candidates(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ masks)
+k_greedy_candidates(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ masks, const uint8_t *__restrict__ jt)
 {
+    LOAD_JUMP_TABLE(sT, jt)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Game g = load_game(st, n, i);
     u64 dest[6], cand[6];
-    movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+    movegen_rays(g.occ_me | g.occ_op, g.cells_me, dest, sT);
     greedy_candidates(g, dest, cand);
 #pragma unroll
     for (int k = 0; k < 6; k++) masks[k * n + i] = cand[k];
@@ -192,8 +204,9 @@ k_greedy_candidates(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ mas
 // Game.start (game.py:58-100) with two GreedyPlayers
 __global__ void __launch_bounds__(ENV_THREADS)
 k_play_greedy(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, int max_plies,
-              u64 *__restrict__ counters)
+              u64 *__restrict__ counters, const uint8_t *__restrict__ jt)
 {
+    LOAD_JUMP_TABLE(sT, jt)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     u32 played = 0, w1 = 0, w2 = 0, rep = 0;
     if (i < n) {
@@ -203,7 +216,7 @@ k_play_greedy(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, int
         int status = (int)(g.meta >> 56);
         for (int t = 0; status == CCX_ST_RUNNING && t < max_plies; t++) {
             u64 dest[6], cand[6];
-            movegen(g.occ_me | g.occ_op, g.cells_me, dest);
+            movegen_rays(g.occ_me | g.occ_op, g.cells_me, dest, sT);
             int total = greedy_candidates(g, dest, cand);
             if (total == 0) { status = CCX_ST_NO_MOVES; break; }     // reference raises (player.py:113)
             u32 ply = (u32)((g.meta >> 32) & 0xFFFF);
@@ -331,6 +344,9 @@ int ccx_create(int device_ordinal, ccx_handle **out)
     if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return CCX_ERR_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    if (cudaMalloc(&h->jump_table, CCX_JT_BYTES) != cudaSuccess) { delete h; return CCX_ERR_NOMEM; }
+    k_build_jump_table<<<7, 128>>>(h->jump_table);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(h->jump_table); delete h; return CCX_ERR_CUDA; }
     *out = h;
     return CCX_OK;
 }
@@ -344,6 +360,7 @@ int ccx_destroy(ccx_handle *h)
     ccx_trees_free(h);
     ccx_scratch *s[] = {&h->d_state, &h->d_aux0, &h->d_aux1, &h->d_aux2};
     for (auto *p : s) if (p->ptr) cudaFree(p->ptr);
+    if (h->jump_table) cudaFree(h->jump_table);
     delete h;
     return CCX_OK;
 }
@@ -377,7 +394,7 @@ int ccx_movegen(ccx_handle *h, int64_t n, const uint64_t *state, uint64_t *dest_
 {
     if (!h || n < 0 || (n && (!state || !dest_masks))) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
-    k_movegen<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((const u64 *)state, n, (u64 *)dest_masks);
+    k_movegen<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((const u64 *)state, n, (u64 *)dest_masks, h->jump_table);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -408,10 +425,10 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
     unsigned grid = blocks_for(n, ENV_THREADS);
     if (trace && trace_games > 0)
         k_step_random<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed, (u32)(seed >> 32),
-                                                                  step0, plies, (u64 *)wins, (u64 *)trace, trace_games);
+                                                                  step0, plies, (u64 *)wins, (u64 *)trace, trace_games, h->jump_table);
     else
         k_step_random<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed, (u32)(seed >> 32),
-                                                                   step0, plies, (u64 *)wins, nullptr, 0);
+                                                                   step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -420,7 +437,7 @@ int ccx_greedy_candidates(ccx_handle *h, int64_t n, const uint64_t *state, uint6
 {
     if (!h || n < 0 || (n && (!state || !cand_masks))) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
-    k_greedy_candidates<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((const u64 *)state, n, (u64 *)cand_masks);
+    k_greedy_candidates<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((const u64 *)state, n, (u64 *)cand_masks, h->jump_table);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -431,7 +448,7 @@ int ccx_play_greedy(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
     if (!h || n < 0 || max_plies < 0 || (n && !state)) return CCX_ERR_ARG;
     if (n == 0 || max_plies == 0) return CCX_OK;
     k_play_greedy<<<blocks_for(n, ENV_THREADS), ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed,
-                                                                              (u32)(seed >> 32), max_plies, (u64 *)counters);
+                                                                              (u32)(seed >> 32), max_plies, (u64 *)counters, h->jump_table);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

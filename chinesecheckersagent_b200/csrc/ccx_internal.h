@@ -26,6 +26,7 @@ struct ccx_handle {
     ccx_net *net = nullptr;
     ccx_trees *trees = nullptr;
     ccx_net_tc *net_tc = nullptr;
+    uint8_t *jump_table = nullptr;   // CCX_JT_BYTES, device: ray-jump lookup table (ccx_device.cuh)
     int net_mode = 0;           // 0 = fp32 SIMT kernel, 1 = bf16 tcgen05 kernels (ccx_net_set_mode)
 };
 

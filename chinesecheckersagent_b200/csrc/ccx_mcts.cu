@@ -217,15 +217,20 @@ __device__ __forceinline__ void backup(const TreeView &tv, int lane, int path_le
 // Lanes 0..5 run one checker's flood fill each; the six masks are then broadcast and every lane writes a
 // strided share of the edge list.  prior(idx) is supplied by the evaluator functor.
 template <typename PriorFn>
-__device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int node, const Game &g, PriorFn prior)
+__device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int node, const Game &g, PriorFn prior, const uint8_t *sT)
 {
     u64 mine = 0;
     if (lane < 6) {
         u64 occ_all = g.occ_me | g.occ_op;
         u64 o = 1ULL << ((g.cells_me >> (8 * lane)) & 0xFF);
         u64 occ = occ_all & ~o, empty = ~occ & CCX_VALID;
-        u64 F = o, reach = 0;
-        while (F) { u64 nw = jump_round(F, occ, empty) & ~(reach | o); reach |= nw; F = nw; }
+        u64 todo = o, reach = 0;
+        while (todo) {                                        // ray expansion of one cell per iteration (ccx_device.cuh)
+            int i = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            u64 nw = expand_cell(i, occ, sT) & ~(reach | o);
+            reach |= nw; todo |= nw;
+        }
         mine = (neighbours(o) & empty) | reach;
     }
     u64 dest[6]; int pre[7]; pre[0] = 0;
@@ -269,7 +274,7 @@ struct TablePrior {      // priors from an evaluator's output row p[294] (float6
 
 // evaluate + expand + backup of one leaf with an in-kernel evaluator
 template <int EVAL>
-__device__ __forceinline__ void eval_expand_backup(const TreeView &tv, int lane, int leaf, int path_len)
+__device__ __forceinline__ void eval_expand_backup(const TreeView &tv, int lane, int leaf, int path_len, const uint8_t *sT)
 {
     Game g = load_node_game(tv, leaf);
     double v = 0.0;
@@ -278,9 +283,9 @@ __device__ __forceinline__ void eval_expand_backup(const TreeView &tv, int lane,
         u64 h = leaf_hash(g, lane);
         HashPrior pr = {(u32)h, (u32)(h >> 32)};
         v = (double)philox4x32_10(pr.k0, pr.k1, 294u, 7u, 0u, 0u).x / 2147483648.0 - 1.0;
-        ok = expand_node(tv, lane, leaf, g, pr);
+        ok = expand_node(tv, lane, leaf, g, pr, sT);
     } else {
-        ok = expand_node(tv, lane, leaf, g, UniformPrior());
+        ok = expand_node(tv, lane, leaf, g, UniformPrior(), sT);
     }
     if (ok) backup(tv, lane, path_len, v, false);
 }
@@ -325,15 +330,18 @@ __device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u6
 template <int EVAL>
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num_itr, double cpuct, int pre_expand,
-              const double *__restrict__ noise, int noise_stride)
+              const double *__restrict__ noise, int noise_stride, const uint8_t *__restrict__ jt)
 {
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
+    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
+    __syncthreads();
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
     init_tree(tv, lane, roots, n, tree, -1);
     if (pre_expand && ((tv.node[5] >> 48) & 0xFF) == 0) {                    // selfplay.py:117
-        eval_expand_backup<EVAL>(tv, lane, 0, 0);
+        eval_expand_backup<EVAL>(tv, lane, 0, 0, sT);
         if (noise) mix_root_noise(tv, lane, noise + tree * noise_stride);
     }
     for (int it = 0; it < num_itr; it++) {                                   // MCTS.py:123-125
@@ -341,7 +349,7 @@ k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num
         int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
         __syncwarp();
         if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
-        else if (kind == LEAF_EVAL) eval_expand_backup<EVAL>(tv, lane, leaf, path_len);
+        else if (kind == LEAF_EVAL) eval_expand_backup<EVAL>(tv, lane, leaf, path_len, sT);
         __syncwarp();
         if (tv.meta[META_OVERFLOW]) break;
     }
@@ -379,8 +387,11 @@ k_mcts_select(ccx_trees trees, int64_t n, double cpuct, u64 *__restrict__ leaf_s
 // and back up v[n]; root_only_noise != NULL mixes Dirichlet noise into the root priors (first call).
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, const double *__restrict__ v,
-                     const double *__restrict__ noise, int noise_stride, int noise_normalize)
+                     const double *__restrict__ noise, int noise_stride, int noise_normalize, const uint8_t *__restrict__ jt)
 {
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
+    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
+    __syncthreads();
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (tree >= n) return;
@@ -389,7 +400,7 @@ k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, c
     int leaf = tv.meta[META_LEAF], path_len = tv.meta[META_PATHLEN];
     Game g = load_node_game(tv, leaf);
     TablePrior pr = {p + tree * CCX_NUM_ACTIONS};
-    if (expand_node(tv, lane, leaf, g, pr)) backup(tv, lane, path_len, v[tree], false);
+    if (expand_node(tv, lane, leaf, g, pr, sT)) backup(tv, lane, path_len, v[tree], false);
     if (noise && leaf == 0) mix_root_noise(tv, lane, noise + tree * noise_stride, noise_normalize != 0);
 }
 
@@ -530,10 +541,10 @@ int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t eva
     unsigned grid = tree_blocks(n);
     if (evaluator == EVAL_UNIFORM)
         k_mcts_search<EVAL_UNIFORM><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, num_itr,
-                                                                                      cpuct, pre_expand, root_noise, noise_stride);
+                                                                                      cpuct, pre_expand, root_noise, noise_stride, h->jump_table);
     else
         k_mcts_search<EVAL_HASH><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, num_itr,
-                                                                                   cpuct, pre_expand, root_noise, noise_stride);
+                                                                                   cpuct, pre_expand, root_noise, noise_stride, h->jump_table);
     CCX_LAUNCHED(h);
     k_mcts_finalize<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, 1.0 / tau, visits, pi, q, n_nodes);
     CCX_LAUNCHED(h);
@@ -565,7 +576,7 @@ int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const doub
 {
     if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || (n && (!p || !v))) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
-    k_mcts_expand_backup<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, p, v, root_noise, noise_stride, noise_normalize);
+    k_mcts_expand_backup<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, p, v, root_noise, noise_stride, noise_normalize, h->jump_table);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

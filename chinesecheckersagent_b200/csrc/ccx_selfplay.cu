@@ -52,8 +52,11 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
                    u32 k0, u32 k1, int iter, int64_t uid0, const int64_t *__restrict__ serial, int64_t total_slots,
                    int random_plies, int tau_switch, int move_limit,
                    u64 *__restrict__ rec_state, uint16_t *__restrict__ rec_visits, uint8_t *__restrict__ rec_flag,
-                   int rec_iters, u64 *__restrict__ counters, u32 *__restrict__ move_log)
+                   int rec_iters, u64 *__restrict__ counters, u32 *__restrict__ move_log, const uint8_t *__restrict__ jt)
 {
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
+    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
+    __syncthreads();
     int64_t g = (int64_t)blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (g >= n) return;
@@ -73,7 +76,7 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
     if (ply < random_plies) {
         // selfplay.make_random_move (selfplay.py:83-104)
         u64 dest[6];
-        movegen(gm.occ_me | gm.occ_op, gm.cells_me, dest);
+        movegen_rays(gm.occ_me | gm.occ_op, gm.cells_me, dest, sT);
         u32 nonempty = 0;
 #pragma unroll
         for (int k = 0; k < 6; k++) nonempty += dest[k] != 0;
@@ -263,7 +266,7 @@ int ccx_selfplay_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32
     if (n == 0) return CCX_OK;
     k_selfplay_advance<<<(unsigned)((n + SP_WARPS - 1) / SP_WARPS), 32 * SP_WARPS, 0, h->stream>>>(
         (u64 *)state, n, visits, tree_nodes, (u32)seed, (u32)(seed >> 32), iter, uid0, serial, total_slots, random_plies,
-        tau_switch, move_limit, (u64 *)rec_state, rec_visits, rec_flag, rec_iters, (u64 *)counters, move_log);
+        tau_switch, move_limit, (u64 *)rec_state, rec_visits, rec_flag, rec_iters, (u64 *)counters, move_log, h->jump_table);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

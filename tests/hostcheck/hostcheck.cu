@@ -35,6 +35,18 @@ void hc_movegen(const u64 *st, int64_t n, u64 *masks)
     }
 }
 
+void hc_movegen_rays(const u64 *st, int64_t n, u64 *masks)
+{
+    static uint8_t T[CCX_JT_BYTES];
+    build_jump_table(T, 0, 1);
+    for (int64_t i = 0; i < n; i++) {
+        Game g = load_game_h(st, n, i);
+        u64 dest[6];
+        movegen_rays(g.occ_me | g.occ_op, g.cells_me, dest, T);
+        for (int k = 0; k < 6; k++) masks[k * n + i] = dest[k];
+    }
+}
+
 void hc_greedy(const u64 *st, int64_t n, u64 *masks)
 {
     for (int64_t i = 0; i < n; i++) {

@@ -19,6 +19,7 @@ def hc():
     vp, i64, i32, u64, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32
     L.hc_movegen.argtypes = [vp, i64, vp]
     L.hc_greedy.argtypes = [vp, i64, vp]
+    L.hc_movegen_rays.argtypes = [vp, i64, vp]
     L.hc_apply.argtypes = [vp, i64, vp, vp, vp]
     L.hc_step_random.argtypes = [vp, i64, i64, u64, u32, i32, vp, vp, i64]
     L.hc_play_greedy.argtypes = [vp, i64, i64, u64, i32]
@@ -52,6 +53,23 @@ def test_movegen_vs_oracle_random_boards(hc):
     st = orc.random_states(20000, seed=7)
     masks = np.zeros((6, st.shape[1]), dtype=np.uint64)
     hc.hc_movegen(P(st), st.shape[1], P(masks))
+    assert np.array_equal(masks, orc.movegen(st))
+
+
+def test_ray_movegen_vs_reference_and_oracle(hc, env_golden):
+    """The table-driven ray formulation (movegen_rays) == the reference on the fixture and == the oracle on
+    40,000 random boards and on positions from long random games."""
+    st = np.ascontiguousarray(env_golden["state"])
+    masks = np.zeros((6, st.shape[1]), dtype=np.uint64)
+    hc.hc_movegen_rays(P(st), st.shape[1], P(masks))
+    assert np.array_equal(masks, canonical_masks(env_golden["ref_moves"], env_golden["ref_nmoves"]))
+    st = orc.random_states(40000, seed=21)
+    masks = np.zeros((6, st.shape[1]), dtype=np.uint64)
+    hc.hc_movegen_rays(P(st), st.shape[1], P(masks))
+    assert np.array_equal(masks, orc.movegen(st))
+    st, _, _ = orc.step_random(orc.start_states(4000), 5, 0, 150, nthreads=8)
+    masks = np.zeros((6, st.shape[1]), dtype=np.uint64)
+    hc.hc_movegen_rays(P(st), st.shape[1], P(masks))
     assert np.array_equal(masks, orc.movegen(st))
 
 
