@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--impl", default="ccx", choices=["ccx", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="games per GPU (BASELINE config: 65536)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ccx" else args.warmup
 
@@ -147,7 +148,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
-    n = GAMES_PER_GPU
+    n = args.games
     env = BatchedEnv(n, engine=eng, seed=SEED, game_id0=rank * n)     # global game ids: sharding-invariant RNG
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 

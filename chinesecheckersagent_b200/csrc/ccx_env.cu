@@ -3,6 +3,7 @@
 // SoA words so that a warp's loads and stores are 256-byte contiguous.
 #include <cuda_bf16.h>
 #include <new>
+#include <cstdlib>
 #include "ccx_device.cuh"
 #include "ccx_internal.h"
 
@@ -178,6 +179,106 @@ k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32
             w1 += win == 1; w2 += win == 2;
             reset_start(g);
         }
+    }
+    store_game(st, n, i, g);
+    if (w1) atomicAdd(&wins[0], (u64)w1);
+    if (w2) atomicAdd(&wins[1], (u64)w2);
+}
+
+// --------------------------------------------------------------------------------------------------
+// Flattened fused env step.  k_step_random above re-synchronises a warp after every checker (the compiler
+// turns its single loop back into "for each checker: expand until every lane is done": 6 x 10.1 iterations
+// per ply with 11 of 32 lanes busy, profiles/r01_k_step_random_rays_ncu.md).  Here every lane walks through
+// its own plies and checkers independently: one loop whose body expands ONE cell for every lane that has
+// one; a lane that exhausts a checker parks the destination mask in shared memory and starts its next
+// checker in the same iteration; lanes that finished a ply wait until READY_THRESHOLD of them can run the
+// expensive pick / apply / win / Philox tail together.  The per-iteration __ballot_sync calls keep the body
+// warp-convergent so the compiler cannot re-nest it.  Results are bit-identical to k_step_random (same
+// per-game Philox counters), which the parity tests check.
+// Tried and dropped (r01): two lanes per game (three checkers each, redundant tails) to double the warp
+// count at 65,536 games — 3.90e9 steps/s against 4.35e9 for this kernel; the pair votes and waits cost more
+// than the extra latency hiding buys.
+#define READY_THRESHOLD 8
+
+template <bool TRACE>
+__global__ void __launch_bounds__(ENV_THREADS)
+k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies,
+                   u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games, const uint8_t *__restrict__ jt)
+{
+    LOAD_JUMP_TABLE(sT, jt)
+    __shared__ u64 sD[6][ENV_THREADS];          // destination masks of the current ply, per checker
+    __shared__ u64 sNB[64];                     // on-board neighbours of every cell
+    const int tid = threadIdx.x;
+    if (tid < 64) sNB[tid] = ((CCX_VALID >> tid) & 1) ? (neighbours(1ULL << tid) & CCX_VALID) : 0ULL;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, i < n);
+    if (i >= n) return;
+    Game g = load_game(st, n, i);
+    const u64 gid = (u64)(gid0 + i);
+    u32 w1 = 0, w2 = 0;
+    int t = 0, id = 0;
+    u64 occ_all = g.occ_me | g.occ_op;
+    int cell = (int)(g.cells_me & 0xFF);
+    u64 o = 1ULL << cell, occ = occ_all & ~o, todo = o, reach = 0;
+    bool leave = false;
+    for (;;) {
+        if (todo) {                                         // expand one cell (ray formulation, ccx_device.cuh)
+            int c = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            u64 nw = expand_cell(c, occ, sT) & ~(reach | o);
+            reach |= nw;
+            todo |= nw;
+        }
+        if (todo == 0 && id < 6) {                          // checker exhausted: park its mask, start the next one
+            sD[id][tid] = (sNB[cell] & ~occ) | reach;
+            if (++id < 6) {
+                cell = (int)((g.cells_me >> (8 * id)) & 0xFF);
+                o = 1ULL << cell; occ = occ_all & ~o; todo = o; reach = 0;
+            }
+        }
+        // every lane now either has a cell to expand or is ready (id == 6); one vote per iteration is the
+        // warp-convergent point that keeps the compiler from re-nesting the loop
+        const bool ready = id == 6;
+        const unsigned r = __ballot_sync(mask, ready);
+        if (!(__popc(r) >= READY_THRESHOLD || r == mask)) continue;
+        if (ready) {
+            u64 dest[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) dest[k] = sD[k][tid];
+            u32 nonempty = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) nonempty += dest[k] != 0;
+            u64 *row = nullptr;
+            if (TRACE && i < trace_games) {
+                row = trace + ((int64_t)t * trace_games + i) * CCX_TRACE_WORDS;
+                bool p2 = (g.meta >> 48) & 1;
+                row[0] = p2 ? g.occ_op : g.occ_me; row[1] = p2 ? g.occ_me : g.occ_op;
+                row[2] = p2 ? g.cells_op : g.cells_me; row[3] = p2 ? g.cells_me : g.cells_op;
+                row[4] = g.meta & 0x00FFFFFFFFFFFFFFULL;
+#pragma unroll
+                for (int k = 0; k < 6; k++) row[5 + k] = dest[k];
+                row[11] = 0xFFULL | (0xFFULL << 8) | (0xFFULL << 24);
+            }
+            if (nonempty) {
+                Philox4 rnd = philox4x32_10(k0, k1, step0 + (u32)t, 0u, (u32)gid, (u32)(gid >> 32));
+                int from, to;
+                int pid = pick_random(g, dest, nonempty, rnd.x, rnd.y, from, to);
+                apply_move(g, pid, from, to);
+                int win = winner_of(g);
+                if (TRACE && row) row[11] = (u64)from | ((u64)to << 8) | ((u64)win << 16) | ((u64)pid << 24);
+                if (win) { w1 += win == 1; w2 += win == 2; reset_start(g); }
+            }
+            if (++t == plies) leave = true;
+            else {
+                occ_all = g.occ_me | g.occ_op;
+                id = 0;
+                cell = (int)(g.cells_me & 0xFF);
+                o = 1ULL << cell; occ = occ_all & ~o; todo = o; reach = 0;
+            }
+        }
+        mask = __ballot_sync(mask, !leave);     // only reached on iterations that ran a tail (uniform branch above)
+        if (leave) break;
     }
     store_game(st, n, i, g);
     if (w1) atomicAdd(&wins[0], (u64)w1);
@@ -423,12 +524,15 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
     if (!h || n < 0 || plies < 0 || (n && (!state || !wins)) || (trace_games > 0 && !trace)) return CCX_ERR_ARG;
     if (n == 0 || plies == 0) return CCX_OK;
     unsigned grid = blocks_for(n, ENV_THREADS);
-    if (trace && trace_games > 0)
-        k_step_random<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed, (u32)(seed >> 32),
-                                                                  step0, plies, (u64 *)wins, (u64 *)trace, trace_games, h->jump_table);
-    else
-        k_step_random<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, (u32)seed, (u32)(seed >> 32),
-                                                                   step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);
+    static const bool nested = getenv("CCX_STEP_NESTED") != nullptr;     // A/B switch for profiling the older kernel
+    const u32 s0 = (u32)seed, s1 = (u32)(seed >> 32);
+    if (trace && trace_games > 0) {
+        if (nested) k_step_random<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, (u64 *)trace, trace_games, h->jump_table);
+        else k_step_random_flat<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, (u64 *)trace, trace_games, h->jump_table);
+    } else {
+        if (nested) k_step_random<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);
+        else k_step_random_flat<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);
+    }
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
