@@ -10,7 +10,7 @@
 __global__ void __launch_bounds__(128)
 k_umma_selftest(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ Bt, int K, int N, float *__restrict__ D)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     uint8_t *sa = smem, *sb = smem + umma::op_bytes(128, K);
@@ -85,10 +85,18 @@ constexpr int POLD_C0 = 160 * 208 * 2, POLD_C1 = 160 * 192 * 2, POLD_HALF = POLD
 constexpr int W_TOTAL = W_POLD + 2 * POLD_HALF;                // 507,904 bytes
 constexpr int F_CONV1 = 0, F_HEADS = 64, F_BLOCK0 = 96, F_BLOCK = 128, F_POLD = F_BLOCK0 + 9 * F_BLOCK;
 constexpr int F_D1W = F_POLD + 320, F_D1B = F_D1W + 800, F_VHW = F_D1B + 32, F_VHB = F_VHW + 32, F_TOTAL = F_VHB + 1;
-// shared memory map of the trunk kernel (bytes)
-constexpr int S_XA = 0, S_IM = S_XA + 128 * 64 * 2, S_M2 = S_IM + 128 * 288 * 2, S_WRES = S_M2 + 128 * 32 * 2;
-constexpr int S_WBUF = S_WRES + 12288, S_PLANES = S_WBUF + 2 * W_BLOCK, S_VALC = S_PLANES + 5 * 343 + 13;
+// shared memory map of the trunk kernel (bytes): 110,784 B so that TWO CTAs are resident per SM
+constexpr int S_XA = 0;                                  // [128 x 64] operand: block input / conv1 im2col
+constexpr int S_IM0 = S_XA + 128 * 64 * 2;               // [128 x 96] im2col operand of one kernel row (dy) of the 3x3 conv
+constexpr int S_IM1 = S_IM0 + 128 * 96 * 2;              //   ... double buffered across the three kernel rows
+constexpr int S_M2 = S_IM1 + 128 * 96 * 2;               // [128 x 32] operand: 3x3 conv output
+constexpr int S_WC1 = S_M2 + 128 * 32 * 2;               // conv1 weights, resident
+constexpr int S_WA = S_WC1 + 8192;                       // streamed: conv A of the current block (then the heads)
+constexpr int S_WB = S_WA + 4096;                        // streamed: conv B
+constexpr int S_WC = S_WB + 18432;                       // streamed: conv C
+constexpr int S_PLANES = S_WC + 4096, S_VALC = S_PLANES + 5 * 343 + 13;
 constexpr int S_TOTAL = S_VALC + 128 * 4;
+static_assert(S_TOTAL == 110784, "trunk kernel shared memory budget (2 CTAs / SM)");
 }  // namespace tcl
 
 struct ccx_net_tc {
@@ -114,45 +122,59 @@ template <bool FP16> __device__ __forceinline__ uint32_t pack2(float a, float b)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// cooperative 16-byte-granular global -> shared copy as one cp.async group (an empty group if bytes == 0)
+__device__ __forceinline__ void refill(uint32_t dst, const uint8_t *src, int bytes, int t)
+{
+    for (int i = t; i < bytes / 16; i += 128) cp_async16(dst + i * 16, src + i * 16);
+    cp_async_commit();
+}
+
 template <bool FP16>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 k_net_trunk_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
                __nv_bfloat16 *__restrict__ polc, float *__restrict__ value)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar, bar_g;                  // bar: "this layer's MMAs are done"; bar_g: "kernel row 0 of the 3x3 is done"
     __shared__ uint32_t tmem_slot;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t sbase = umma::smem_u32(smem);
     const int64_t n_tiles = (n + 4) / 5;
 
-    // one-time setup: zero the im2col operand (padding taps stay zero for ever), resident weights, TMEM
-    for (int i = t; i < (tcl::S_WRES - tcl::S_XA) / 16; i += 128) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = t; i < 12288 / 16; i += 128) cp_async16(sbase + tcl::S_WRES + i * 16, wb + i * 16);     // CONV1 + HEADS
-    cp_async_commit();
-    if (t == 0) umma::mbar_init(&bar, 1);
+    // Weight streaming: wA / wB / wC each hold ONE layer and are refilled with the next layer that will use the
+    // slot as soon as the layer that was using it has finished (the refill then has two layer-times to land).
+    // Every phase issues exactly one cp.async group (possibly empty), so "the group that loaded my weights" is
+    // always at least three groups old and cp.async.wait_group 2 in front of each phase is sufficient.
+    for (int i = t; i < 8192 / 16; i += 128) cp_async16(sbase + tcl::S_WC1 + i * 16, wb + tcl::W_CONV1 + i * 16);
+    refill(sbase + tcl::S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096, t);            // group: conv1 + A0
+    refill(sbase + tcl::S_WB, wb + tcl::W_BLOCK0 + tcl::W_BB, 18432, t);           // group: B0
+    refill(sbase + tcl::S_WC, wb + tcl::W_BLOCK0 + tcl::W_BC, 4096, t);            // group: C0
+    if (t == 0) { umma::mbar_init(&bar, 1); umma::mbar_init(&bar_g, 1); }
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
-    // prefetch block 0's weights for the first tile
-    for (int i = t; i < tcl::W_BLOCK / 16; i += 128) cp_async16(sbase + tcl::S_WBUF + i * 16, wb + tcl::W_BLOCK0 + i * 16);
-    cp_async_commit();
-    cp_async_wait<1>();                     // resident weights have landed (block 0 may still be in flight)
-    umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 TMEM lanes
-    uint32_t phase = 0;
-    int wslot = 0;                          // which half of the double buffer holds the block about to run
+    uint32_t phase = 0, phase_g = 0;
 
     const int p_local = t / 25, cell = t % 25, cy = cell / 5, cx = cell % 5;
     const bool row_live = t < 125;
+
+    // one layer = operands ready -> MMA -> completion.  `pre` runs after cp.async.wait and before the barrier.
+    auto layer_sync = [&]() {
+        cp_async_wait<2>();
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+    };
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t pos0 = tile * 5;
         const int n_pos = (int)min((int64_t)5, n - pos0);
         // ---- stage the input planes (uint8, values 0..6) ------------------------------------------------
         for (int i = t; i < n_pos * 343; i += 128) smem[tcl::S_PLANES + i] = planes[pos0 * 343 + i];
+        cp_async_commit();                                   // (empty group: keeps the group count per phase uniform)
         __syncthreads();
         // ---- conv1 operand: im2col of the 3x3 'valid' window, K = 63 (+1 zero) (model.py:62) ---------------
         {
@@ -171,15 +193,14 @@ k_net_trunk_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, con
                 *reinterpret_cast<uint4 *>(smem + tcl::S_XA + umma::op_offset(t, c8 * 8, 64)) = o;
             }
         }
-        umma::fence_async_smem();
-        umma::fence_before_sync();
-        __syncthreads();
+        layer_sync();
         float x[64];                        // residual stream of this row, fp32
         if (t == 0) {
             umma::fence_after_sync();
-            umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, sbase + tcl::S_WRES + tcl::W_CONV1, 64, 0, 64, 64, false, FP16);
+            umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, sbase + tcl::S_WC1, 64, 0, 64, 64, false, FP16);
             umma::commit(&bar);
         }
+        cp_async_commit();                                   // (empty group)
         umma::mbar_wait(&bar, phase); phase ^= 1;
         umma::fence_after_sync();
 #pragma unroll
@@ -197,63 +218,77 @@ k_net_trunk_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, con
 
         // ---- 9 bottleneck residual blocks (model.py:120-145) --------------------------------------------------
         for (int b = 0; b < 9; b++) {
-            // prefetch the next block's weights (cyclic: block 0 of the next tile after block 8) into the other slot
-            {
-                const uint8_t *src = wb + tcl::W_BLOCK0 + ((b + 1) % 9) * tcl::W_BLOCK;
-                const uint32_t dst = sbase + tcl::S_WBUF + (wslot ^ 1) * tcl::W_BLOCK;
-                for (int i = t; i < tcl::W_BLOCK / 16; i += 128) cp_async16(dst + i * 16, src + i * 16);
-                cp_async_commit();
-            }
-            cp_async_wait<1>();             // this block's weights (committed one block ago) have landed
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            __syncthreads();
-            const uint32_t wcur = sbase + tcl::S_WBUF + wslot * tcl::W_BLOCK;
+            const uint8_t *wblk = wb + tcl::W_BLOCK0 + b * tcl::W_BLOCK;
+            const uint8_t *wnext = wb + tcl::W_BLOCK0 + ((b + 1) % 9) * tcl::W_BLOCK;
             const float *bias = fb + tcl::F_BLOCK0 + b * tcl::F_BLOCK;
+            (void)wblk;
             // A: 1x1 conv 64 -> 32, ReLU
+            layer_sync();
             if (t == 0) {
                 umma::fence_after_sync();
-                umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, wcur + tcl::W_BA, 64, 0, 64, 32, false, FP16);
+                umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, sbase + tcl::S_WA, 64, 0, 64, 32, false, FP16);
                 umma::commit(&bar);
             }
+            float bv[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) bv[j] = __ldg(bias + j);           // bias loads overlap the MMA
             umma::mbar_wait(&bar, phase); phase ^= 1;
             umma::fence_after_sync();
+            // the A slot is free: stream in conv A of the next block, or the heads after the last block
+            refill(sbase + tcl::S_WA, b < 8 ? wnext + tcl::W_BA : wb + tcl::W_HEADS, 4096, t);
+            uint4 o[4];
             {
                 float v[32];
                 umma::tmem_ld32(trow, v);
-                uint4 o[4];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     float r[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) r[q] = fmaxf(v[c * 8 + q] + __ldg(bias + c * 8 + q), 0.f);
+                    for (int q = 0; q < 8; q++) r[q] = fmaxf(v[c * 8 + q] + bv[c * 8 + q], 0.f);
                     o[c] = make_uint4(pack2<FP16>(r[0], r[1]), pack2<FP16>(r[2], r[3]), pack2<FP16>(r[4], r[5]), pack2<FP16>(r[6], r[7]));
                 }
-                // im2col scatter for the 3x3 'same' conv: this cell is input tap (dy,dx) of output cell (cy-dy, cx-dx)
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j++) bv[j] = __ldg(bias + 32 + j);
+            // B: 3x3 'same' conv 32 -> 32 as three accumulating K = 96 GEMMs, one per kernel row dy; the im2col
+            // operand of a kernel row is scattered by the threads that own the source cells, the zero padding is
+            // written by the thread that owns the output cell
+#pragma unroll
+            for (int g = 0; g < 3; g++) {
+                const int dy = g - 1;
+                const int im = (g & 1) ? tcl::S_IM1 : tcl::S_IM0;
+                if (g == 2) { umma::mbar_wait(&bar_g, phase_g); phase_g ^= 1; umma::fence_after_sync(); }   // kernel row 0 has released IM0
                 if (row_live) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; tap++) {
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        const int oy = cy - dy, ox = cx - dx;
-                        if (oy < 0 || oy > 4 || ox < 0 || ox > 4) continue;
-                        const int orow = p_local * 25 + oy * 5 + ox;
+                    for (int dxi = 0; dxi < 3; dxi++) {
+                        const int dx = dxi - 1;
+                        const int oy = cy - dy, ox = cx - dx;               // output cell that reads this cell through tap (dy, dx)
+                        if (oy >= 0 && oy <= 4 && ox >= 0 && ox <= 4) {
+                            const int orow = p_local * 25 + oy * 5 + ox;
 #pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            *reinterpret_cast<uint4 *>(smem + tcl::S_IM + umma::op_offset(orow, tap * 32 + c * 8, 288)) = o[c];
+                            for (int c = 0; c < 4; c++)
+                                *reinterpret_cast<uint4 *>(smem + im + umma::op_offset(orow, dxi * 32 + c * 8, 96)) = o[c];
+                        }
+                        const int iy = cy + dy, ix = cx + dx;               // source cell of MY output through tap (dy, dx)
+                        if (iy < 0 || iy > 4 || ix < 0 || ix > 4) {
+#pragma unroll
+                            for (int c = 0; c < 4; c++)
+                                *reinterpret_cast<uint4 *>(smem + im + umma::op_offset(t, dxi * 32 + c * 8, 96)) = make_uint4(0, 0, 0, 0);
+                        }
                     }
                 }
-            }
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            __syncthreads();
-            // B: 3x3 conv 32 -> 32 as one K = 288 GEMM, ReLU
-            if (t == 0) {
-                umma::fence_after_sync();
-                umma::gemm_issue(tmem + 32, sbase + tcl::S_IM, 288, 0, wcur + tcl::W_BB, 288, 0, 288, 32, false, FP16);
-                umma::commit(&bar);
+                if (g == 0) layer_sync();
+                else { umma::fence_async_smem(); umma::fence_before_sync(); __syncthreads(); }
+                if (t == 0) {
+                    umma::fence_after_sync();
+                    umma::gemm_issue(tmem + 32, sbase + im, 96, 0, sbase + tcl::S_WB, 288, 96 * g, 96, 32, g > 0, FP16);
+                    if (g == 0) umma::commit(&bar_g);
+                    if (g == 2) umma::commit(&bar);
+                }
             }
             umma::mbar_wait(&bar, phase); phase ^= 1;
             umma::fence_after_sync();
+            refill(sbase + tcl::S_WB, wnext + tcl::W_BB, 18432, t);
             {
                 float v[32];
                 umma::tmem_ld32(trow + 32, v);
@@ -261,22 +296,21 @@ k_net_trunk_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, con
                 for (int c = 0; c < 4; c++) {
                     float r[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) r[q] = fmaxf(v[c * 8 + q] + __ldg(bias + 32 + c * 8 + q), 0.f);
+                    for (int q = 0; q < 8; q++) r[q] = fmaxf(v[c * 8 + q] + bv[c * 8 + q], 0.f);
                     *reinterpret_cast<uint4 *>(smem + tcl::S_M2 + umma::op_offset(t, c * 8, 32)) =
                         make_uint4(pack2<FP16>(r[0], r[1]), pack2<FP16>(r[2], r[3]), pack2<FP16>(r[4], r[5]), pack2<FP16>(r[6], r[7]));
                 }
             }
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            __syncthreads();
             // C: 1x1 conv 32 -> 64, + skip, ReLU (model.py:137-144)
+            layer_sync();
             if (t == 0) {
                 umma::fence_after_sync();
-                umma::gemm_issue(tmem + 64, sbase + tcl::S_M2, 32, 0, wcur + tcl::W_BC, 32, 0, 32, 64, false, FP16);
+                umma::gemm_issue(tmem + 64, sbase + tcl::S_M2, 32, 0, sbase + tcl::S_WC, 32, 0, 32, 64, false, FP16);
                 umma::commit(&bar);
             }
             umma::mbar_wait(&bar, phase); phase ^= 1;
             umma::fence_after_sync();
+            refill(sbase + tcl::S_WC, wnext + tcl::W_BC, 4096, t);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 float v[32];
@@ -289,19 +323,17 @@ k_net_trunk_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, con
                 *reinterpret_cast<uint4 *>(smem + tcl::S_XA + umma::op_offset(t, c8 * 8, 64)) =
                     make_uint4(pack2<FP16>(x[c8 * 8], x[c8 * 8 + 1]), pack2<FP16>(x[c8 * 8 + 2], x[c8 * 8 + 3]),
                                pack2<FP16>(x[c8 * 8 + 4], x[c8 * 8 + 5]), pack2<FP16>(x[c8 * 8 + 6], x[c8 * 8 + 7]));
-            wslot ^= 1;
         }
-        umma::fence_async_smem();
-        umma::fence_before_sync();
-        __syncthreads();
-        // ---- heads: policy conv 64 -> 16 and value conv 64 -> 1 in one N = 32 GEMM (model.py:91, 108) ------------
+        // ---- heads: policy conv 64 -> 16 and value conv 64 -> 1 in one N = 32 GEMM (model.py:91, 108); weights in the A slot
+        layer_sync();
         if (t == 0) {
             umma::fence_after_sync();
-            umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, sbase + tcl::S_WRES + tcl::W_HEADS, 64, 0, 64, 32, false, FP16);
+            umma::gemm_issue(tmem, sbase + tcl::S_XA, 64, 0, sbase + tcl::S_WA, 64, 0, 64, 32, false, FP16);
             umma::commit(&bar);
         }
         umma::mbar_wait(&bar, phase); phase ^= 1;
         umma::fence_after_sync();
+        refill(sbase + tcl::S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096, t);          // conv A of block 0 for the next tile
         {
             float v[32];
             umma::tmem_ld32(trow, v);
@@ -346,7 +378,7 @@ __global__ void __launch_bounds__(128, 1)
 k_policy_dense_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const __nv_bfloat16 *__restrict__ polc, int64_t n,
                   float *__restrict__ logits)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int t = threadIdx.x, warp = t >> 5;
@@ -459,7 +491,7 @@ int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *l
         tc->cap = n;
     }
     int64_t tiles = (n + 4) / 5;
-    unsigned grid = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);     // two resident CTAs per SM
     if (tc->fp16) k_net_trunk_tc<true><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
     else k_net_trunk_tc<false><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
     CCX_LAUNCHED(h);
