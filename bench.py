@@ -217,7 +217,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("k_step_random")
+                traffic = json.load(f).get("k_step_random_flat")
         except Exception:
             pass
         line = {
@@ -228,7 +228,7 @@ def main():
                        "plies_per_step": PLIES_PER_STEP, "start": "Board() start position, won games restart",
                        "l2": "flushed between timed steps (256 MiB write, untimed)", "parallelism": "games sharded, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_step_random<false>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_step_random_flat<false>",
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * PLIES_PER_STEP,
                          "launch_ms": launch_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
