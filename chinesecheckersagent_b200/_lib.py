@@ -50,6 +50,7 @@ SIGNATURES = {
     "ccx_net_forward_tc": (i32, [vp, i64, vp, vp, vp]),
     "ccx_net_set_mode": (i32, [vp, i32]),
     "ccx_debug_umma_gemm": (i32, [vp, vp, vp, i32, i32, vp]),
+    "ccx_debug_umma_gemm_rows": (i32, [vp, vp, i32, i32, vp, i32, i32, vp]),
     "ccx_movegen_host": (i32, [vp, i64, vp, vp]),
     "ccx_apply_host": (i32, [vp, i64, vp, vp, vp, vp]),
     "ccx_step_random_host": (i32, [vp, i64, vp, i64, u64, u32, i32, vp]),

@@ -5,6 +5,7 @@
 #include "ccx_internal.h"
 #include "ccx_umma.cuh"
 #include <new>
+#include <cstdlib>
 
 // ---- self-test of the UMMA plumbing: D[128 x N] = A[128 x K] * Bt[N x K]^T -------------------------------
 __global__ void __launch_bounds__(128)
@@ -47,7 +48,68 @@ k_umma_selftest(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__rest
     if (warp == 0) umma::tmem_free(tmem, 64);
 }
 
+// Second self-test: the A operand in the ROW-CONTIGUOUS layout the 3x3 conv uses — element (r, k) at
+// (k/8)*LBO + r*16 + (k%8)*2 with LBO = rows*16, SBO = 128 — and a descriptor whose start address is moved by
+// `shift` rows (16 B each, NOT a multiple of the 128-byte core matrix): D = A[shift .. shift+127] * Bt^T.
+__global__ void __launch_bounds__(128)
+k_umma_selftest_rows(const __nv_bfloat16 *__restrict__ A, int rows, int shift, const __nv_bfloat16 *__restrict__ Bt, int K, int N,
+                     float *__restrict__ D)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t *sa = smem, *sb = smem + (size_t)rows * K * 2;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < rows * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16 *>(sa + (k >> 3) * rows * 16 + r * 16 + (k & 7) * 2) = A[i];
+    }
+    for (int i = t; i < N * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16 *>(sb + umma::op_offset(r, k, K)) = Bt[i];
+    }
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 64);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (t == 0) {
+        const uint32_t idesc = umma::make_idesc(N, false);
+        for (int s = 0; s < K / 16; s++) {
+            uint64_t ad = umma::make_desc(umma::smem_u32(sa) + (uint32_t)(2 * s) * rows * 16u + (uint32_t)shift * 16u, (uint32_t)rows * 16u, 128u);
+            uint64_t bd = umma::make_desc(umma::smem_u32(sb) + (uint32_t)(2 * s) * 128u, 128u, (uint32_t)(K >> 3) * 128u);
+            umma::mma_bf16(tmem, ad, bd, idesc, s > 0);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    for (int c = 0; c < N; c += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (c + j < N) D[t * N + c + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 64);
+}
+
 extern "C" {
+
+int ccx_debug_umma_gemm_rows(ccx_handle *h, const void *A, int32_t rows, int32_t shift, const void *Bt, int32_t K, int32_t N, float *D)
+{
+    if (!h || !A || !Bt || !D || K % 16 || K < 16 || K > 128 || N % 16 || N < 16 || N > 64 || rows % 8 || shift < 0 || shift + 128 > rows)
+        return CCX_ERR_ARG;
+    size_t smem = (size_t)rows * K * 2 + umma::op_bytes(N, K);
+    if (smem > 200 * 1024) return CCX_ERR_ARG;
+    CCX_CUDA(h, cudaFuncSetAttribute(k_umma_selftest_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest_rows<<<1, 128, smem, h->stream>>>((const __nv_bfloat16 *)A, rows, shift, (const __nv_bfloat16 *)Bt, K, N, D);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
 
 int ccx_debug_umma_gemm(ccx_handle *h, const void *A, const void *Bt, int32_t K, int32_t N, float *D)
 {
@@ -372,6 +434,317 @@ k_net_trunk_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, con
     if (warp == 0) umma::tmem_free(tmem, 128);
 }
 
+// =====================================================================================================
+// Trunk kernel v3.  Same arithmetic and weight blobs as k_net_trunk_tc; what changes is the machinery
+// around the 3x3 conv and the epilogues:
+//  * a tile is FOUR positions whose 5x5 cells sit at row  p*30 + y*6 + x  of the 128-row operand (a guard row
+//    after every board row, 8 idle rows at the end).  The 3x3 conv input is kept as three copies (one per
+//    kernel row dy, pre-shifted vertically by the epilogue that produces it) in a ROW-CONTIGUOUS operand
+//    layout, and the horizontal taps dx = -1, 0, +1 are the same copy addressed one row earlier / later
+//    through the matrix descriptor (16-byte granular start address) — the guard rows supply the zero
+//    padding.  Nine accumulating K = 32 GEMMs, ONE barrier phase, 6 shared-memory stores per thread instead
+//    of an explicit im2col (36 stores per thread and three barrier phases in v2);
+//  * 256 threads: warps w and w+4 share TMEM lane group w and split the output columns, so every epilogue
+//    is half as long and 16 warps per SM (2 CTAs) hide each other's latencies;
+//  * biases and the value-head dense live in shared memory (v2 re-read them from global inside every
+//    epilogue, on the critical path), the next tile's input planes are prefetched into registers.
+#ifdef CCX_TRUNK_TIMING
+__device__ long long g_trunk_ts[2][1024];
+#define TS(k) do { if (blockIdx.x == 0 && tile == blockIdx.x && (t == 0 || t == 255) && ts_n < 1024) g_trunk_ts[t ? 1 : 0][ts_n++] = clock64(); } while (0)
+#else
+#define TS(k) do { } while (0)
+#endif
+namespace tc3 {
+constexpr int THREADS = 256, POS = 4, POS_ROWS = 30, LIVE_ROWS = 120;
+constexpr int YROWS = 136, Y_LBO = YROWS * 16, Y_COPY = 4 * Y_LBO;        // 1 guard row + 128 + 1 guard row, padded to 8
+constexpr int S_X = 0;                                   // [128 x 64] operand (block input / conv1 im2col); first half doubles as
+                                                         // the [128 x 32] operand of conv C
+constexpr int S_Y = S_X + 128 * 64 * 2;                  // three row-contiguous [136 x 32] copies of conv A's output
+constexpr int S_WC1 = S_Y + 3 * Y_COPY;                  // conv1 weights, resident
+constexpr int S_WA = S_WC1 + 8192, S_WB = S_WA + 4096, S_WC = S_WB + 18432;     // streamed per layer
+constexpr int S_F = S_WC + 4096;                         // fp32 blob (biases, value-head dense)
+constexpr int F_BYTES = ((tcl::F_TOTAL * 4 + 15) / 16) * 16;
+constexpr int PLANES_BYTES = 1376;                       // 4 x 343 = 1372, padded
+constexpr int S_PLANES = S_F + F_BYTES;                  // double buffer
+constexpr int S_VALC = S_PLANES + 2 * PLANES_BYTES;
+constexpr int S_TOTAL = S_VALC + 512;
+static_assert(S_TOTAL <= 113 * 1024, "two CTAs per SM");
+static_assert(S_Y % 128 == 0 && S_WC1 % 128 == 0 && S_F % 16 == 0 && S_PLANES % 16 == 0, "alignment");
+}  // namespace tc3
+
+template <bool FP16>
+__global__ void __launch_bounds__(tc3::THREADS, 2)
+k_net_trunk_tc3(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
+                __nv_bfloat16 *__restrict__ polc, float *__restrict__ value)
+{
+    using namespace tc3;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int rg = warp & 3, h = warp >> 2;                  // TMEM lane group, column half
+    const int r = rg * 32 + lane;                            // operand row of this thread
+    const int p_local = r / POS_ROWS, rem = r % POS_ROWS, cy = rem / 6, cx = rem % 6;
+    const bool live = r < LIVE_ROWS && cx < 5;
+    const int cell = cy * 5 + cx;
+    const uint32_t sbase = umma::smem_u32(smem);
+    const float *sF = reinterpret_cast<const float *>(smem + S_F);
+    const int64_t n_tiles = (n + POS - 1) / POS;
+    const bool planes_aligned = (reinterpret_cast<uintptr_t>(planes) & 3) == 0;
+
+    auto refill3 = [&](int dst, const uint8_t *src, int bytes) {
+        for (int i = t; i < bytes / 16; i += THREADS) cp_async16(sbase + dst + i * 16, src + i * 16);
+        cp_async_commit();
+    };
+    // words q*256 + t (< 343) of a tile's input planes; bytes past the last position read as zero
+    auto load_planes = [&](int64_t tile, uint32_t (&w)[2]) {
+        const int64_t pos0 = tile * POS;
+        const int bytes = (int)min((int64_t)POS, n - pos0) * 343;
+        const uint8_t *src = planes + pos0 * 343;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int idx = q * THREADS + t;
+            uint32_t v = 0;
+            if (idx * 4 + 4 <= bytes && planes_aligned) v = __ldg(reinterpret_cast<const uint32_t *>(src) + idx);
+            else
+                for (int k = 0; k < 4; k++) if (idx * 4 + k < bytes) v |= (uint32_t)__ldg(src + idx * 4 + k) << (8 * k);
+            w[q] = v;
+        }
+    };
+    auto store_planes = [&](int buf, const uint32_t (&w)[2]) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int idx = q * THREADS + t;
+            if (idx < 344) reinterpret_cast<uint32_t *>(smem + S_PLANES + buf * PLANES_BYTES)[idx] = w[q];
+        }
+    };
+
+    for (int i = t; i < 8192 / 16; i += THREADS) cp_async16(sbase + S_WC1 + i * 16, wb + tcl::W_CONV1 + i * 16);
+    refill3(S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);                // group: conv1 + A0
+    refill3(S_WB, wb + tcl::W_BLOCK0 + tcl::W_BB, 18432);               // group: B0
+    refill3(S_WC, wb + tcl::W_BLOCK0 + tcl::W_BC, 4096);                // group: C0
+    for (int i = t; i < S_WC1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows stay zero
+    for (int i = t; i < tcl::F_TOTAL; i += THREADS) reinterpret_cast<float *>(smem + S_F)[i] = __ldg(fb + i);
+    {
+        uint32_t w0[2];
+        load_planes(blockIdx.x, w0);
+        store_planes(0, w0);
+    }
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(rg * 32) << 16);
+    uint32_t phase = 0;
+    int buf = 0;
+    // base descriptors of every operand (constant for the whole kernel) and the instruction descriptors
+    const umma::DescBase dX64 = umma::desc_base(sbase + S_X, 128u, 64 / 8 * 128u), dX32 = umma::desc_base(sbase + S_X, 128u, 32 / 8 * 128u);
+    const umma::DescBase dY = umma::desc_base(sbase + S_Y, Y_LBO, 128u);
+    const umma::DescBase dWC1 = umma::desc_base(sbase + S_WC1, 128u, 64 / 8 * 128u), dWA = umma::desc_base(sbase + S_WA, 128u, 64 / 8 * 128u);
+    const umma::DescBase dWB = umma::desc_base(sbase + S_WB, 128u, 288 / 8 * 128u), dWC = umma::desc_base(sbase + S_WC, 128u, 32 / 8 * 128u);
+    constexpr uint32_t ID32 = umma::make_idesc(32, FP16), ID64 = umma::make_idesc(64, FP16);
+#ifdef CCX_TRUNK_TIMING
+    int ts_n = 0;
+    int64_t tile = blockIdx.x;
+#endif
+
+    auto layer_sync = [&]() {
+        TS(0);
+        cp_async_wait<2>();
+        TS(1);
+        umma::fence_async_smem();
+        TS(2);
+        umma::fence_before_sync();
+        __syncthreads();
+        TS(3);
+    };
+    auto wait_mma = [&]() {
+        TS(4);
+        umma::mbar_wait(&bar, phase); phase ^= 1;
+        umma::fence_after_sync();
+        TS(5);
+    };
+    auto pack8 = [&](const float *rr) {
+        return make_uint4(pack2<FP16>(rr[0], rr[1]), pack2<FP16>(rr[2], rr[3]), pack2<FP16>(rr[4], rr[5]), pack2<FP16>(rr[6], rr[7]));
+    };
+
+#ifdef CCX_TRUNK_TIMING
+    for (tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#else
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#endif
+        const int64_t pos0 = tile * POS;
+        const int n_pos = (int)min((int64_t)POS, n - pos0);
+        uint32_t pw[2] = {0u, 0u};
+        if (tile + gridDim.x < n_tiles) load_planes(tile + gridDim.x, pw);       // lands while this tile computes
+        cp_async_commit();                                   // (empty group: keeps the group count per phase uniform)
+        // ---- conv1 operand: im2col of the 3x3 'valid' window, K = 63 (+1 zero) (model.py:62); this thread: 32 of the 64 columns
+        {
+            const uint8_t *pl = smem + S_PLANES + buf * PLANES_BYTES + (live ? p_local * 343 : 0);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; c8++) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int kk = h * 32 + c8 * 8 + q;
+                    const int tap = kk / 7, ch = kk % 7, dy = tap / 3, dx = tap % 3;
+                    v[q] = (live && kk < 63) ? (float)pl[((cy + dy) * 7 + (cx + dx)) * 7 + ch] : 0.f;
+                }
+                *reinterpret_cast<uint4 *>(smem + S_X + umma::op_offset(r, h * 32 + c8 * 8, 64)) = pack8(v);
+            }
+        }
+        layer_sync();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::gemm_issue_d<64>(tmem + 64, dX64, 0, dWC1, 0, ID64, false);
+                umma::commit(&bar);
+            }
+            __syncwarp();
+        }
+        cp_async_commit();                                   // (empty group)
+        wait_mma();
+        float x[32];                                         // residual stream: 32 of this row's 64 channels, fp32
+        {
+            float v[32];
+            umma::tmem_ld32(trow + 64 + h * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) x[j] = fmaxf(v[j] + sF[tcl::F_CONV1 + h * 32 + j], 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(smem + S_X + umma::op_offset(r, h * 32 + c * 8, 64)) = pack8(x + c * 8);
+        }
+        // ---- 9 bottleneck residual blocks (model.py:120-145) --------------------------------------------------
+        for (int b = 0; b < 9; b++) {
+            const uint8_t *wnext = wb + tcl::W_BLOCK0 + ((b + 1) % 9) * tcl::W_BLOCK;
+            const float *bias = sF + tcl::F_BLOCK0 + b * tcl::F_BLOCK;
+            // A: 1x1 conv 64 -> 32, ReLU
+            layer_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::gemm_issue_d<64>(tmem, dX64, 0, dWA, 0, ID32, false);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            refill3(S_WA, b < 8 ? wnext + tcl::W_BA : wb + tcl::W_HEADS, 4096);
+            {
+                float v[16];
+                umma::tmem_ld16(trow + h * 16, v);
+#pragma unroll
+                for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q] + bias[h * 16 + q], 0.f);
+                const uint4 o0 = pack8(v), o1 = pack8(v + 8);
+                if (live) {
+                    // copy d serves kernel row dy = d - 1: output cell (y - dy, x) reads this cell, so the value goes to row r - 6*dy
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const int oy = cy - (d - 1);
+                        if (oy >= 0 && oy <= 4) {
+                            uint8_t *dst = smem + S_Y + d * Y_COPY + (2 * h) * Y_LBO + (1 + r - 6 * (d - 1)) * 16;
+                            *reinterpret_cast<uint4 *>(dst) = o0;
+                            *reinterpret_cast<uint4 *>(dst + Y_LBO) = o1;
+                        }
+                    }
+                }
+            }
+            // B: 3x3 'same' conv 32 -> 32 = nine accumulating K = 32 GEMMs on row-shifted views of the three copies
+            layer_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++)
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; dxi++)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ks++)
+                                umma::mma_bf16(tmem + 32, umma::desc_at(dY, (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO)),
+                                               umma::desc_at(dWB, (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128)), ID32, (d | dxi | ks) != 0);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            refill3(S_WB, wnext + tcl::W_BB, 18432);
+            {
+                float v[16];
+                umma::tmem_ld16(trow + 32 + h * 16, v);
+#pragma unroll
+                for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q] + bias[32 + h * 16 + q], 0.f);
+                *reinterpret_cast<uint4 *>(smem + S_X + umma::op_offset(r, h * 16, 32)) = pack8(v);
+                *reinterpret_cast<uint4 *>(smem + S_X + umma::op_offset(r, h * 16 + 8, 32)) = pack8(v + 8);
+            }
+            // C: 1x1 conv 32 -> 64, + skip, ReLU (model.py:137-144)
+            layer_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::gemm_issue_d<32>(tmem + 64, dX32, 0, dWC, 0, ID64, false);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            refill3(S_WC, wnext + tcl::W_BC, 4096);
+            {
+                float v[32];
+                umma::tmem_ld32(trow + 64 + h * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) x[j] = fmaxf(v[j] + bias[64 + h * 32 + j] + x[j], 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(smem + S_X + umma::op_offset(r, h * 32 + c * 8, 64)) = pack8(x + c * 8);
+            }
+        }
+        // ---- heads: policy conv 64 -> 16 and value conv 64 -> 1 in one N = 32 GEMM (model.py:91, 108); weights in the A slot
+        layer_sync();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::gemm_issue_d<64>(tmem, dX64, 0, dWA, 0, ID32, false);
+                umma::commit(&bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        refill3(S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);                 // conv A of block 0 for the next tile
+        {
+            float v[16];
+            umma::tmem_ld16(trow + h * 16, v);
+            if (live && p_local < n_pos) {
+                if (h == 0) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q] + sF[tcl::F_HEADS + q], 0.f);
+                    uint4 *dst = reinterpret_cast<uint4 *>(polc + (pos0 + p_local) * 400 + cell * 16);      // Flatten in (y, x, c) order
+                    dst[0] = pack8(v); dst[1] = pack8(v + 8);
+                } else {
+                    reinterpret_cast<float *>(smem + S_VALC)[p_local * 25 + cell] = fmaxf(v[0] + sF[tcl::F_HEADS + 16], 0.f);
+                }
+            }
+        }
+        store_planes(buf ^ 1, pw);
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- value head: dense_1 25 -> 32 ReLU, value_head 32 -> 1 tanh (model.py:95-103), fp32 ---------------------
+        if (warp < n_pos) {
+            const float *valc = reinterpret_cast<const float *>(smem + S_VALC) + warp * 25;
+            float acc = sF[tcl::F_D1B + lane];
+            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], sF[tcl::F_D1W + k * 32 + lane], acc);
+            float sv = fmaxf(acc, 0.f) * sF[tcl::F_VHW + lane];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, off);
+            if (lane == 0) value[pos0 + warp] = tanhf(sv + sF[tcl::F_VHB]);
+        }
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 128);
+}
+
 // logits[B x 294] = polc[B x 400] (bf16) * W (bf16) + b  —  128 positions x 160 outputs per CTA, K in two chunks
 template <bool FP16>
 __global__ void __launch_bounds__(128, 1)
@@ -454,6 +827,9 @@ void ccx_net_tc_free(ccx_handle *h)
 
 extern "C" {
 
+#ifdef CCX_TRUNK_TIMING
+int ccx_debug_trunk_timing(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_trunk_ts, sizeof(long long) * 2048); }
+#endif
 int ccx_net_tc_blob_bytes(void) { return tcl::W_TOTAL; }
 int ccx_net_tc_num_floats(void) { return tcl::F_TOTAL; }
 
@@ -472,6 +848,8 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
     tc->fp16 = fp16;
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 208 * 2 + 160 * 208 * 2));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 208 * 2 + 160 * 208 * 2));
     return CCX_OK;
@@ -490,10 +868,18 @@ int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *l
         CCX_CUDA(h, cudaMalloc(&tc->polc, sizeof(__nv_bfloat16) * 400 * (size_t)n));
         tc->cap = n;
     }
-    int64_t tiles = (n + 4) / 5;
-    unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);     // two resident CTAs per SM
-    if (tc->fp16) k_net_trunk_tc<true><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
-    else k_net_trunk_tc<false><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+    static const bool use_v2 = getenv("CCX_TRUNK_V2") != nullptr;        // A/B switch for profiling the older kernel
+    if (use_v2) {
+        int64_t tiles = (n + 4) / 5;
+        unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);     // two resident CTAs per SM
+        if (tc->fp16) k_net_trunk_tc<true><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+        else k_net_trunk_tc<false><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+    } else {
+        int64_t tiles = (n + tc3::POS - 1) / tc3::POS;
+        unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);     // two resident CTAs per SM
+        if (tc->fp16) k_net_trunk_tc3<true><<<grid, tc3::THREADS, tc3::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+        else k_net_trunk_tc3<false><<<grid, tc3::THREADS, tc3::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+    }
     CCX_LAUNCHED(h);
     dim3 g2((unsigned)((n + 127) / 128), 2);
     constexpr int SM2 = 128 * 208 * 2 + 160 * 208 * 2;

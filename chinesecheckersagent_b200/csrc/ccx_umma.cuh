@@ -64,6 +64,38 @@ __device__ __forceinline__ void gemm_issue(uint32_t tmem_d, uint32_t a_base, int
     }
 }
 
+// Descriptor arithmetic for issue loops: only the 14-bit start-address field changes between the MMAs of a
+// layer, so a layer keeps (lo, hi) words of its operands' base descriptors and adds byte offsets to `lo`
+// (one integer add per MMA instead of rebuilding the descriptor; shared memory < 256 KB so no carry).
+struct DescBase { uint32_t lo, hi; };
+__device__ __forceinline__ DescBase desc_base(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    DescBase d;
+    d.lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    d.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+    return d;
+}
+__device__ __forceinline__ uint64_t desc_at(DescBase b, uint32_t byte_off)
+{
+    return ((uint64_t)b.hi << 32) | (uint64_t)(b.lo + (byte_off >> 4));
+}
+// one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+// K-major standard-layout operands (op_offset): D (+)= A[., ka0 .. ka0+K) * B[., kb0 .. kb0+K)^T
+template <int K>
+__device__ __forceinline__ void gemm_issue_d(uint32_t tmem_d, DescBase a, int ka0, DescBase b, int kb0, uint32_t idesc, bool accumulate_first)
+{
+#pragma unroll
+    for (int s = 0; s < K / 16; s++)
+        mma_bf16(tmem_d, desc_at(a, (uint32_t)((ka0 >> 3) + 2 * s) * 128u), desc_at(b, (uint32_t)((kb0 >> 3) + 2 * s) * 128u), idesc,
+                 accumulate_first || s > 0);
+}
+
 __device__ __forceinline__ void commit(uint64_t *bar)     // arrives on `bar` when all prior MMAs of this thread are done
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -117,6 +149,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    __syncwarp();
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// D[128 x N] (+)= A * B^T with the A operand in the ROW-CONTIGUOUS layout: element (r, k) at
+// (k/8)*lbo_a + r*16 + (k%8)*2 (SBO = 128).  a_start already includes the row shift (16 B per row), so a 3x3
+// conv tap is the same buffer addressed one or more rows further on.  B as in gemm_issue.
+__device__ __forceinline__ void gemm_issue_rows(uint32_t tmem_d, uint32_t a_start, uint32_t lbo_a, uint32_t b_base, int Kb, int kb0,
+                                                int K, int N, bool accumulate_first, bool fp16 = false)
+{
+    const uint32_t idesc = make_idesc(N, fp16);
+#pragma unroll
+    for (int s = 0; s < K / 16; s++) {
+        uint64_t ad = make_desc(a_start + (uint32_t)(2 * s) * lbo_a, lbo_a, 128u);
+        uint64_t bd = make_desc(b_base + (uint32_t)((kb0 >> 3) + 2 * s) * 128u, 128u, (uint32_t)(Kb >> 3) * 128u);
+        mma_bf16(tmem_d, ad, bd, idesc, accumulate_first || s > 0);
+    }
 }
 
 }  // namespace umma

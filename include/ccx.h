@@ -215,6 +215,10 @@ int ccx_traj_pack(ccx_handle *h, int64_t m, const int64_t *rows, const uint64_t 
 /* Self-test of the tcgen05/TMEM plumbing used by the bf16 net kernel: D[128][N] = A[128][K] * Bt[N][K]^T
  * (bf16 in, fp32 out; K multiple of 16 up to 512, N multiple of 16 up to 64).  Used by the GPU tests. */
 int ccx_debug_umma_gemm(ccx_handle *h, const void *A, const void *Bt, int32_t K, int32_t N, float *D);
+/* same, with A [rows x K] held in the row-contiguous operand layout of the 3x3 conv and the descriptor start moved by
+ * `shift` rows: D[128 x N] = A[shift .. shift+127] * Bt^T (self-test of 16-byte-granular descriptor starts). */
+int ccx_debug_umma_gemm_rows(ccx_handle *h, const void *A, int32_t rows, int32_t shift, const void *Bt, int32_t K, int32_t N,
+                             float *D);
 
 /* ---- host-buffer variants: the reference-facing path with H2D/D2H inside the call -------------- */
 int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host);

@@ -21,3 +21,23 @@ def test_umma_gemm_matches_torch(K, N):
     ref = A.float() @ Bt.float().t()
     assert torch.allclose(D, ref, atol=1e-2, rtol=1e-3), (D - ref).abs().max().item()
     eng.close()
+
+
+@pytest.mark.parametrize("shift", [0, 1, 5, 7, 8, 13])
+@pytest.mark.parametrize("K,N", [(32, 32), (64, 64)])
+def test_umma_row_shifted_descriptor(K, N, shift):
+    """The 3x3 conv addresses its A operand through descriptors whose start is offset by whole rows (16 B) in a
+    row-contiguous layout; the result must equal the GEMM on the shifted row window."""
+    from chinesecheckersagent_b200.engine import Engine
+    eng = Engine(0)
+    rows = 144
+    g = torch.Generator(device="cuda").manual_seed(K * 1000 + N + shift)
+    A = torch.randn((rows, K), device="cuda", generator=g).to(torch.bfloat16)
+    Bt = torch.randn((N, K), device="cuda", generator=g).to(torch.bfloat16)
+    D = torch.zeros((128, N), device="cuda", dtype=torch.float32)
+    eng.call("ccx_debug_umma_gemm_rows", ctypes.c_void_p(A.data_ptr()), rows, shift, ctypes.c_void_p(Bt.data_ptr()), K, N,
+             ctypes.c_void_p(D.data_ptr()))
+    torch.cuda.synchronize()
+    ref = A[shift:shift + 128].float() @ Bt.float().t()
+    assert torch.allclose(D, ref, atol=1e-2, rtol=1e-3), (D - ref).abs().max().item()
+    eng.close()
