@@ -30,6 +30,7 @@ SIGNATURES = {
     "ccx_mcts_search": (i32, [vp, i64, vp, i32, i32, f64, f64, i32, vp, i32, i32, vp, vp, vp, vp]),
     "ccx_mcts_begin": (i32, [vp, i64, vp, i32, i32, i32]),
     "ccx_mcts_select": (i32, [vp, i64, f64, vp]),
+    "ccx_mcts_run_net": (i32, [vp, i64, i32, f64, vp, i32, i32]),
     "ccx_mcts_expand_backup": (i32, [vp, i64, vp, vp, vp, i32, i32]),
     "ccx_mcts_finalize": (i32, [vp, i64, f64, vp, vp, vp, vp]),
     "ccx_mcts_get_root": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "ccx_net_forward_tc": (i32, [vp, i64, vp, vp, vp]),
     "ccx_net_set_mode": (i32, [vp, i32]),
     "ccx_debug_umma_gemm": (i32, [vp, vp, vp, i32, i32, vp]),
+    "ccx_debug_umma_gemm_ts": (i32, [vp, vp, vp, i32, vp]),
     "ccx_debug_umma_gemm_rows": (i32, [vp, vp, i32, i32, vp, i32, i32, vp]),
     "ccx_movegen_host": (i32, [vp, i64, vp, vp]),
     "ccx_apply_host": (i32, [vp, i64, vp, vp, vp, vp]),

@@ -60,6 +60,11 @@ static inline int ccx_reserve(ccx_handle *h, ccx_scratch &s, size_t bytes)
     return CCX_OK;
 }
 
+// scratch of the net evaluator (planes uint8[n][343], logits float[n][294], value float[n]) and the forward pass in
+// the active mode (ccx_net_set_mode) — used by ccx_net_eval and by the fused MCTS round loop (ccx_mcts_run_net)
+int ccx_net_scratch(ccx_handle *h, int64_t n, uint8_t **planes, float **logits, float **value);
+int ccx_net_forward_active(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value);
+
 // sub-module teardown hooks (defined where the sub-module lives)
 void ccx_net_free(ccx_handle *h);
 void ccx_trees_free(ccx_handle *h);

@@ -12,6 +12,7 @@
 #include "ccx_device.cuh"
 #include "ccx_internal.h"
 #include <new>
+#include <cstdlib>
 
 #define FULL 0xFFFFFFFFu
 #define MCTS_WARPS_PER_BLOCK 4
@@ -30,6 +31,8 @@ struct ccx_trees {
     u32 *eN = nullptr;          // [T][EPT]
     double *eW = nullptr, *eP = nullptr;
     int32_t *eChild = nullptr;  // node index inside the tree or -1
+    u64 *eInfo = nullptr;       // [T][EPT] copy of the child node's info word (valid once eChild >= 0): the descent reads it
+                                // together with eChild, so a tree level costs two dependent memory round trips, not four
     uint16_t *eMove = nullptr;  // checker id << 8 | destination cell
     int32_t *path = nullptr;    // [T][PATH_MAX] edge indices of the current simulation
     int32_t *tree_meta = nullptr;   // [T][8]: n_nodes, n_edges, overflow, path_len, leaf_node, leaf_kind, sims_done, spare
@@ -37,7 +40,7 @@ struct ccx_trees {
 };
 
 struct TreeView {
-    u64 *node; u32 *eN; double *eW; double *eP; int32_t *eChild; uint16_t *eMove; int32_t *path; int32_t *meta;
+    u64 *node; u32 *eN; double *eW; double *eP; int32_t *eChild; u64 *eInfo; uint16_t *eMove; int32_t *path; int32_t *meta;
     int32_t npt, ept, path_max;
 };
 
@@ -49,6 +52,7 @@ __device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
     v.eW = t.eW + tree * t.edges_per_tree;
     v.eP = t.eP + tree * t.edges_per_tree;
     v.eChild = t.eChild + tree * t.edges_per_tree;
+    v.eInfo = t.eInfo + tree * t.edges_per_tree;
     v.eMove = t.eMove + tree * t.edges_per_tree;
     v.path = t.path + tree * t.path_max;
     v.meta = t.tree_meta + tree * 8;
@@ -141,26 +145,38 @@ __device__ __forceinline__ u64 leaf_hash(const Game &g, int lane)
 __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double cpuct, int &path_len, int &leaf_kind)
 {
     int node = 0, depth = 0;
+    u64 info = tv.node[5];
     for (;;) {
-        u64 info = tv.node[(int64_t)node * NODE_WORDS + 5];
         int winner = (int)((info >> 48) & 0xFF);
         int ne = (int)((info >> 32) & 0xFFFF);
         if (winner) { leaf_kind = LEAF_TERMINAL; break; }
         if (ne == 0) { leaf_kind = LEAF_EVAL; break; }           // Node.isLeaf()
         int eb = (int)(u32)info;
-        // N_sum (MCTS.py:58-59)
+        // one pass over the edges: N, W, P of edges lane, lane+32, ... stay in registers (<= 126 legal moves)
+        u32 Nr[4]; double Wr[4], Pr[4];
         u32 nsum = 0;
-        for (int j = lane; j < ne; j += 32) nsum += tv.eN[eb + j];
-        nsum = __reduce_add_sync(FULL, nsum);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int j = lane + 32 * c;
+            bool in = j < ne;
+            Nr[c] = in ? tv.eN[eb + j] : 0u;
+            Wr[c] = in ? tv.eW[eb + j] : 0.0;
+            Pr[c] = in ? tv.eP[eb + j] : 0.0;
+            nsum += Nr[c];
+        }
+        nsum = __reduce_add_sync(FULL, nsum);                    // N_sum (MCTS.py:58-59)
         double sq = sqrt((double)nsum);                          // np.sqrt(N_sum)
         double best = -INFINITY; int besti = 0x7FFFFFFF;
-        for (int j = lane; j < ne; j += 32) {
-            u32 N = tv.eN[eb + j];
-            double W = tv.eW[eb + j], P = tv.eP[eb + j];
-            double Q = N ? __ddiv_rn(W, (double)N) : 0.0;                                   // MCTS.py:89,118
-            double U = __ddiv_rn(__dmul_rn(__dmul_rn(cpuct, P), sq), __dadd_rn(1.0, (double)N));   // :62
-            double QU = __dadd_rn(Q, U);                                                    // :63
-            if (QU > best) { best = QU; besti = j; }                                        // :65-67
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int j = lane + 32 * c;
+            if (j < ne) {
+                u32 N = Nr[c];
+                double Q = N ? __ddiv_rn(Wr[c], (double)N) : 0.0;                                  // MCTS.py:89,118
+                double U = __ddiv_rn(__dmul_rn(__dmul_rn(cpuct, Pr[c]), sq), __dadd_rn(1.0, (double)N));   // :62
+                double QU = __dadd_rn(Q, U);                                                    // :63
+                if (QU > best) { best = QU; besti = j; }                                        // :65-67
+            }
         }
         // warp arg-max, ties to the smallest edge index (= first maximal edge in list order)
 #pragma unroll
@@ -173,6 +189,7 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
         if (lane == 0 && depth < tv.path_max) tv.path[depth] = e;
         depth++;
         int child = tv.eChild[e];
+        u64 cinfo = tv.eInfo[e];                                 // same round trip as eChild; meaningful iff child >= 0
         if (child < 0) {
             // first visit: materialise the child state = Board.place on a copy (MCTS.py:104-105)
             int nn = tv.meta[META_NNODES];
@@ -187,6 +204,7 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
             if (lane == 0) {
                 store_node(tv, nn, g, make_info(0, 0, (u32)w, 0));
                 tv.eChild[e] = nn;
+                tv.eInfo[e] = make_info(0, 0, (u32)w, 0);
                 tv.meta[META_NNODES] = nn + 1;
             }
             __syncwarp();
@@ -195,6 +213,7 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
             break;
         }
         node = child;
+        info = cinfo;
     }
     path_len = depth;
     return node;
@@ -216,8 +235,10 @@ __device__ __forceinline__ void backup(const TreeView &tv, int lane, int path_le
 // ---- expand (MCTS.py:95-109) ---------------------------------------------------------------------------
 // Lanes 0..5 run one checker's flood fill each; the six masks are then broadcast and every lane writes a
 // strided share of the edge list.  prior(idx) is supplied by the evaluator functor.
+// parent_edge = the edge that leads to `node` (last edge of the path), -1 for the root: its eInfo copy is refreshed.
 template <typename PriorFn>
-__device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int node, const Game &g, PriorFn prior, const uint8_t *sT)
+__device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int node, const Game &g, PriorFn prior, const uint8_t *sT,
+                                            int parent_edge)
 {
     u64 mine = 0;
     if (lane < 6) {
@@ -257,6 +278,7 @@ __device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int no
         tv.meta[META_NEDGES] = eb + total;
         u64 *info = tv.node + (int64_t)node * NODE_WORDS + 5;
         *info = make_info((u32)eb, (u32)total, 0, 1);
+        if (parent_edge >= 0) tv.eInfo[parent_edge] = make_info((u32)eb, (u32)total, 0, 1);
     }
     __syncwarp();
     return true;
@@ -277,15 +299,16 @@ template <int EVAL>
 __device__ __forceinline__ void eval_expand_backup(const TreeView &tv, int lane, int leaf, int path_len, const uint8_t *sT)
 {
     Game g = load_node_game(tv, leaf);
+    const int parent_edge = path_len > 0 ? tv.path[path_len - 1] : -1;
     double v = 0.0;
     bool ok;
     if (EVAL == EVAL_HASH) {
         u64 h = leaf_hash(g, lane);
         HashPrior pr = {(u32)h, (u32)(h >> 32)};
         v = (double)philox4x32_10(pr.k0, pr.k1, 294u, 7u, 0u, 0u).x / 2147483648.0 - 1.0;
-        ok = expand_node(tv, lane, leaf, g, pr, sT);
+        ok = expand_node(tv, lane, leaf, g, pr, sT, parent_edge);
     } else {
-        ok = expand_node(tv, lane, leaf, g, UniformPrior(), sT);
+        ok = expand_node(tv, lane, leaf, g, UniformPrior(), sT, parent_edge);
     }
     if (ok) backup(tv, lane, path_len, v, false);
 }
@@ -400,7 +423,97 @@ k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, c
     int leaf = tv.meta[META_LEAF], path_len = tv.meta[META_PATHLEN];
     Game g = load_node_game(tv, leaf);
     TablePrior pr = {p + tree * CCX_NUM_ACTIONS};
-    if (expand_node(tv, lane, leaf, g, pr, sT)) backup(tv, lane, path_len, v[tree], false);
+    if (expand_node(tv, lane, leaf, g, pr, sT, path_len > 0 ? tv.path[path_len - 1] : -1)) backup(tv, lane, path_len, v[tree], false);
+    if (noise && leaf == 0) mix_root_noise(tv, lane, noise + tree * noise_stride, noise_normalize != 0);
+}
+
+// ---- fused round pieces for the built-in net evaluator (ccx_mcts_run_net) -------------------------------
+// phase A': select + utils.to_model_input of the leaf (utils.py:101-160) written straight into the net's uint8
+// input batch, one warp per tree (the leaf's 343 bytes are staged in shared memory: zero, scatter the 36
+// labels, copy out)
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_select_encode(ccx_trees trees, int64_t n, double cpuct, uint8_t *__restrict__ planes)
+{
+    __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    uint8_t *sp = sP[threadIdx.x >> 5];
+    Game g;
+    if (tv.meta[META_OVERFLOW]) {
+        // inactive / overflowed tree: hand the evaluator a well-formed dummy position (its output is ignored)
+        if (lane == 0) tv.meta[META_LEAFKIND] = LEAF_DEAD;
+        reset_start(g);
+    } else {
+        int path_len, kind;
+        int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
+        __syncwarp();
+        if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
+        if (lane == 0) { tv.meta[META_PATHLEN] = path_len; tv.meta[META_LEAF] = leaf; tv.meta[META_LEAFKIND] = kind; }
+        g = load_node_game(tv, leaf);
+    }
+    for (int i = lane; i < 88; i += 32) reinterpret_cast<uint32_t *>(sp)[i] = 0u;
+    __syncwarp();
+    {
+        const int plies = (int)((g.meta >> 32) & 0xFFFF);
+        const u64 cur0 = g.cells_me, opp0 = g.cells_op;
+        const u64 opp1 = undo_in_cells(opp0, (int)(g.meta & 0xFF), (int)((g.meta >> 8) & 0xFF));
+        const u64 cur2 = undo_in_cells(cur0, (int)((g.meta >> 16) & 0xFF), (int)((g.meta >> 24) & 0xFF));
+        for (int e = lane; e < 36; e += 32) {
+            int hs = e / 12, side = (e / 6) & 1, id = e % 6;
+            if (hs > plies) continue;
+            u64 cells = side ? (hs >= 1 ? opp1 : opp0) : (hs >= 2 ? cur2 : cur0);
+            int c = (int)((cells >> (8 * id)) & 0xFF);
+            if (c < 55 && (c & 7) < 7) sp[((c >> 3) * 7 + (c & 7)) * 7 + 2 * hs + side] = (uint8_t)(id + 1);
+        }
+        if ((g.meta >> 48) & 1)
+            for (int c = lane; c < 49; c += 32) sp[c * 7 + 6] = 1;                // utils.py:157-158
+    }
+    __syncwarp();
+    uint8_t *dst = planes + tree * 343;
+    for (int i = lane; i < 343; i += 32) dst[i] = sp[i];
+}
+
+// phase B': float64 softmax over all 294 logits (model.py:21-24, utils.py:187-192; same arithmetic as
+// k_softmax_f64) + expand + backup, one warp per tree; the priors never touch global memory
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_softmax_expand_backup(ccx_trees trees, int64_t n, const float *__restrict__ logits, const float *__restrict__ value,
+                             const double *__restrict__ noise, int noise_stride, int noise_normalize, const uint8_t *__restrict__ jt)
+{
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
+    __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
+    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
+    __syncthreads();
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    if (tv.meta[META_LEAFKIND] != LEAF_EVAL) return;
+    double *pr = sPr[threadIdx.x >> 5];
+    {
+        double x[10], mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            int i = lane + 32 * j;
+            x[j] = i < 294 ? (double)logits[tree * 294 + i] : -INFINITY;
+            mx = fmax(mx, x[j]);
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, off));
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 10; j++) { x[j] = (lane + 32 * j) < 294 ? exp(x[j] - mx) : 0.0; sum += x[j]; }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(FULL, sum, off);
+#pragma unroll
+        for (int j = 0; j < 10; j++) if (lane + 32 * j < 294) pr[lane + 32 * j] = x[j] / sum;
+    }
+    __syncwarp();
+    int leaf = tv.meta[META_LEAF], path_len = tv.meta[META_PATHLEN];
+    Game g = load_node_game(tv, leaf);
+    TablePrior tp = {pr};
+    if (expand_node(tv, lane, leaf, g, tp, sT, path_len > 0 ? tv.path[path_len - 1] : -1)) backup(tv, lane, path_len, (double)value[tree], false);
     if (noise && leaf == 0) mix_root_noise(tv, lane, noise + tree * noise_stride, noise_normalize != 0);
 }
 
@@ -493,7 +606,7 @@ void ccx_trees_free(ccx_handle *h)
 {
     ccx_trees *t = h->trees;
     if (!t) return;
-    void *ptrs[] = {t->node, t->eN, t->eW, t->eP, t->eChild, t->eMove, t->path, t->tree_meta};
+    void *ptrs[] = {t->node, t->eN, t->eW, t->eP, t->eChild, t->eInfo, t->eMove, t->path, t->tree_meta};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete t;
     h->trees = nullptr;
@@ -517,10 +630,11 @@ static int trees_reserve(ccx_handle *h, int64_t n, int32_t num_itr, int32_t edge
     CCX_CUDA(h, cudaMalloc(&t->eW, T * ept * 8));
     CCX_CUDA(h, cudaMalloc(&t->eP, T * ept * 8));
     CCX_CUDA(h, cudaMalloc(&t->eChild, T * ept * 4));
+    CCX_CUDA(h, cudaMalloc(&t->eInfo, T * ept * 8));
     CCX_CUDA(h, cudaMalloc(&t->eMove, T * ept * 2));
     CCX_CUDA(h, cudaMalloc(&t->path, T * pm * 4));
     CCX_CUDA(h, cudaMalloc(&t->tree_meta, T * 8 * 4));
-    t->bytes = T * ((size_t)npt * NODE_WORDS * 8 + (size_t)ept * 26 + (size_t)pm * 4 + 32);
+    t->bytes = T * ((size_t)npt * NODE_WORDS * 8 + (size_t)ept * 34 + (size_t)pm * 4 + 32);
     return CCX_OK;
 }
 
@@ -578,6 +692,45 @@ int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const doub
     if (n == 0) return CCX_OK;
     k_mcts_expand_backup<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, p, v, root_noise, noise_stride, noise_normalize, h->jump_table);
     CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_mcts_run_net(ccx_handle *h, int64_t n, int32_t rounds, double cpuct, const double *root_noise, int32_t noise_stride,
+                     int32_t noise_normalize)
+{
+    if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || rounds < 0) return CCX_ERR_ARG;
+    if (root_noise && noise_stride < 1) return CCX_ERR_ARG;
+    if (n == 0 || rounds == 0) return CCX_OK;
+    uint8_t *planes; float *logits, *value;
+    int rc;
+    if ((rc = ccx_net_scratch(h, n, &planes, &logits, &value))) return rc;
+    const unsigned grid = tree_blocks(n);
+    static const bool timing = getenv("CCX_RUN_NET_TIMING") != nullptr;      // debug: per-kernel in-situ times of rounds 100..103
+    cudaEvent_t ev[16];
+    if (timing) for (auto &e : ev) cudaEventCreate(&e);
+    for (int r = 0; r < rounds; r++) {
+        const bool tr = timing && r >= 100 && r < 104;
+        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 0], h->stream);
+        k_mcts_select_encode<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, planes);
+        CCX_LAUNCHED(h);
+        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 1], h->stream);
+        if ((rc = ccx_net_forward_active(h, n, planes, logits, value))) return rc;
+        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 2], h->stream);
+        k_mcts_softmax_expand_backup<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, logits, value,
+                                                                                        r == 0 ? root_noise : nullptr, noise_stride,
+                                                                                        noise_normalize, h->jump_table);
+        CCX_LAUNCHED(h);
+        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 3], h->stream);
+    }
+    if (timing && rounds >= 104) {
+        cudaStreamSynchronize(h->stream);
+        for (int i = 0; i + 1 < 16; i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            fprintf(stderr, "run_net round %d seg %d: %.2f us\n", 100 + i / 4, i % 4, ms * 1e3f);
+        }
+    }
+    if (timing) for (auto &e : ev) cudaEventDestroy(e);
     return CCX_OK;
 }
 

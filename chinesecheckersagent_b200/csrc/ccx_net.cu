@@ -330,6 +330,19 @@ int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p
     if (!h || n < 0 || (n && (!leaf_state || !p || !v))) return CCX_ERR_ARG;
     if (!h->net || !h->net->w) return CCX_ERR_STATE;
     if (n == 0) return CCX_OK;
+    uint8_t *planes; float *logits, *value;
+    int rc;
+    if ((rc = ccx_net_scratch(h, n, &planes, &logits, &value))) return rc;
+    if ((rc = ccx_encode(h, n, leaf_state, planes, CCX_DTYPE_U8))) return rc;
+    if ((rc = ccx_net_forward_active(h, n, planes, logits, value))) return rc;
+    return ccx_softmax_f64(h, n, logits, value, p, v);
+}
+
+}  // extern "C"
+
+int ccx_net_scratch(ccx_handle *h, int64_t n, uint8_t **planes, float **logits, float **value)
+{
+    if (!h->net || !h->net->w) return CCX_ERR_STATE;
     ccx_net *nt = h->net;
     if (nt->cap < n) {
         void *ptrs[] = {nt->logits, nt->value, nt->planes};
@@ -337,15 +350,15 @@ int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p
         nt->logits = nullptr; nt->value = nullptr; nt->planes = nullptr; nt->cap = 0;
         CCX_CUDA(h, cudaMalloc(&nt->logits, sizeof(float) * 294 * (size_t)n));
         CCX_CUDA(h, cudaMalloc(&nt->value, sizeof(float) * (size_t)n));
-        CCX_CUDA(h, cudaMalloc(&nt->planes, 343 * (size_t)n));
+        CCX_CUDA(h, cudaMalloc(&nt->planes, 343 * (size_t)n + 16));
         nt->cap = n;
     }
-    int rc;
-    if ((rc = ccx_encode(h, n, leaf_state, nt->planes, CCX_DTYPE_U8))) return rc;
-    if (h->net_mode == 1) rc = ccx_net_forward_tc(h, n, nt->planes, nt->logits, nt->value);
-    else rc = ccx_net_forward(h, n, nt->planes, CCX_DTYPE_U8, nt->logits, nt->value);
-    if (rc) return rc;
-    return ccx_softmax_f64(h, n, nt->logits, nt->value, p, v);
+    *planes = nt->planes; *logits = nt->logits; *value = nt->value;
+    return CCX_OK;
 }
 
-}  // extern "C"
+int ccx_net_forward_active(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value)
+{
+    if (h->net_mode == 1) return ccx_net_forward_tc(h, n, planes, logits, value);
+    return ccx_net_forward(h, n, planes, CCX_DTYPE_U8, logits, value);
+}

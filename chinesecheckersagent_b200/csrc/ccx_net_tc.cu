@@ -97,7 +97,67 @@ k_umma_selftest_rows(const __nv_bfloat16 *__restrict__ A, int rows, int shift, c
     if (warp == 0) umma::tmem_free(tmem, 64);
 }
 
+// Third self-test: the A operand read from TMEM (packed 16-bit pairs written with tcgen05.st): D = A * Bt^T, K = 64.
+__global__ void __launch_bounds__(128)
+k_umma_selftest_ts(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ Bt, int N, float *__restrict__ D)
+{
+    constexpr int K = 64;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < N * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16 *>(smem + umma::op_offset(r, k, K)) = Bt[i];
+    }
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) w[j] = reinterpret_cast<const uint32_t *>(A + (size_t)t * K)[j];   // elements 2j (low), 2j+1 (high)
+        umma::tmem_st32(trow + 64, w);
+        umma::tmem_wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        umma::fence_after_sync();
+        if (umma::elect_one()) {
+            umma::gemm_issue_ts<K>(tmem, tmem + 64, umma::desc_base(umma::smem_u32(smem), 128u, K / 8 * 128u), 0, umma::make_idesc(N, false), false);
+            umma::commit(&bar);
+        }
+        __syncwarp();
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        umma::tmem_ld16(trow + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 16; j++) D[t * N + c + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 128);
+}
+
 extern "C" {
+
+int ccx_debug_umma_gemm_ts(ccx_handle *h, const void *A, const void *Bt, int32_t N, float *D)
+{
+    if (!h || !A || !Bt || !D || N % 16 || N < 16 || N > 64) return CCX_ERR_ARG;
+    size_t smem = umma::op_bytes(N, 64);
+    k_umma_selftest_ts<<<1, 128, smem, h->stream>>>((const __nv_bfloat16 *)A, (const __nv_bfloat16 *)Bt, N, D);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
 
 int ccx_debug_umma_gemm_rows(ccx_handle *h, const void *A, int32_t rows, int32_t shift, const void *Bt, int32_t K, int32_t N, float *D)
 {
@@ -810,6 +870,94 @@ k_policy_dense_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, 
     if (warp == 0) umma::tmem_free(tmem, 256);
 }
 
+// Policy dense v2: 128 positions x 80 outputs per CTA (grid = row tiles x 4 column quarters: 128 CTAs at the
+// self-play batch of 4,096 instead of 64), both K chunks in flight at once (two cp.async groups, the first
+// chunk's MMAs run while the second lands), logits staged through shared memory for coalesced stores.
+namespace pd2 {
+constexpr int NQ = 80;
+constexpr int S_A0 = 0, S_A1 = S_A0 + 128 * 208 * 2, S_W0 = S_A1 + 128 * 192 * 2, S_W1 = S_W0 + NQ * 208 * 2;
+constexpr int S_TOTAL = S_W1 + NQ * 192 * 2;           // 166,400 B
+constexpr int OUT_LD = NQ + 1;                          // fp32 staging [128][81] over the A region once the MMAs are done
+static_assert(128 * OUT_LD * 4 <= S_W0, "staging fits in the A region");
+}  // namespace pd2
+
+template <bool FP16>
+__global__ void __launch_bounds__(128, 1)
+k_policy_dense_tc2(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const __nv_bfloat16 *__restrict__ polc, int64_t n,
+                   float *__restrict__ logits)
+{
+    using namespace pd2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    const int quarter = blockIdx.y, half = quarter >> 1, c0 = (quarter & 1) * NQ;
+    const int64_t row0 = (int64_t)blockIdx.x * 128;
+    const uint32_t sbase = umma::smem_u32(smem);
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+#pragma unroll
+    for (int chunk = 0; chunk < 2; chunk++) {
+        const int k0 = chunk ? 208 : 0, Kc = chunk ? 192 : 208, pieces = Kc / 8;
+        const int sa = chunk ? S_A1 : S_A0, sw = chunk ? S_W1 : S_W0;
+        for (int i = t; i < 128 * pieces; i += 128) {
+            const int r = i / pieces, k8 = i % pieces;
+            const int64_t row = row0 + r;
+            if (row < n) cp_async16(sbase + sa + umma::op_offset(r, k8 * 8, Kc), polc + row * 400 + k0 + k8 * 8);
+            else *reinterpret_cast<uint4 *>(smem + sa + umma::op_offset(r, k8 * 8, Kc)) = make_uint4(0, 0, 0, 0);
+        }
+        // this quarter's 80 weight rows are a contiguous slice of the half's [160 x Kc] operand
+        const uint8_t *wsrc = wb + tcl::W_POLD + half * tcl::POLD_HALF + (chunk ? tcl::POLD_C0 : 0) + (c0 / 8) * pieces * 128;
+        for (int i = t; i < NQ * Kc * 2 / 16; i += 128) cp_async16(sbase + sw + i * 16, wsrc + i * 16);
+        cp_async_commit();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    constexpr uint32_t ID = umma::make_idesc(NQ, FP16);
+    cp_async_wait<1>();
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        umma::fence_after_sync();
+        if (umma::elect_one())
+            umma::gemm_issue_d<208>(tmem, umma::desc_base(sbase + S_A0, 128u, 208 / 8 * 128u), 0, umma::desc_base(sbase + S_W0, 128u, 208 / 8 * 128u), 0, ID, false);
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        umma::fence_after_sync();
+        if (umma::elect_one()) {
+            umma::gemm_issue_d<192>(tmem, umma::desc_base(sbase + S_A1, 128u, 192 / 8 * 128u), 0, umma::desc_base(sbase + S_W1, 128u, 192 / 8 * 128u), 0, ID, true);
+            umma::commit(&bar);
+        }
+        __syncwarp();
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    float *stage = reinterpret_cast<float *>(smem);
+#pragma unroll
+    for (int c = 0; c < NQ; c += 16) {
+        float v[16];
+        umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 16; j++) stage[t * OUT_LD + c + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    const int col_base = half * 160 + c0;
+    for (int i = t; i < 128 * NQ; i += 128) {
+        const int r = i / NQ, c = i % NQ, col = col_base + c;
+        if (row0 + r < n && col < CCX_NUM_ACTIONS) logits[(row0 + r) * CCX_NUM_ACTIONS + col] = stage[r * OUT_LD + c] + __ldg(fb + tcl::F_POLD + col);
+    }
+    if (warp == 0) umma::tmem_free(tmem, 128);
+}
+
 static ccx_net_tc *tc_of(ccx_handle *h, bool create)
 {
     if (!h->net_tc && create) h->net_tc = new (std::nothrow) ccx_net_tc();
@@ -848,6 +996,8 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
     tc->fp16 = fp16;
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd2::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd2::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 208 * 2 + 160 * 208 * 2));
@@ -881,10 +1031,16 @@ int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *l
         else k_net_trunk_tc3<false><<<grid, tc3::THREADS, tc3::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
     }
     CCX_LAUNCHED(h);
-    dim3 g2((unsigned)((n + 127) / 128), 2);
-    constexpr int SM2 = 128 * 208 * 2 + 160 * 208 * 2;
-    if (tc->fp16) k_policy_dense_tc<true><<<g2, 128, SM2, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
-    else k_policy_dense_tc<false><<<g2, 128, SM2, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+    if (use_v2) {
+        dim3 g2((unsigned)((n + 127) / 128), 2);
+        constexpr int SM2 = 128 * 208 * 2 + 160 * 208 * 2;
+        if (tc->fp16) k_policy_dense_tc<true><<<g2, 128, SM2, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+        else k_policy_dense_tc<false><<<g2, 128, SM2, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+    } else {
+        dim3 g2((unsigned)((n + 127) / 128), 4);
+        if (tc->fp16) k_policy_dense_tc2<true><<<g2, 128, pd2::S_TOTAL, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+        else k_policy_dense_tc2<false><<<g2, 128, pd2::S_TOTAL, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+    }
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

@@ -111,6 +111,7 @@ class ResidualCNN(Model):
         from .engine import Engine
         self.eng = engine or Engine(0)
         self.loaded = False
+        self.fused_mcts = True      # engine.BatchedMCTS.search_net / BatchedSelfPlay may run the rounds inside libccx (ccx_mcts_run_net)
         self.kernel = "tc"
         self.tc_dtype = "fp16"      # IEEE-half operands: 8x smaller error than bf16 at the same speed
 

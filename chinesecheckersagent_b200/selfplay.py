@@ -27,8 +27,13 @@ class UniformEvaluator:
 
 class BatchedSelfPlay:
     def __init__(self, engine, evaluate, n_slots=4096, seed=DEFAULT_SEED, rank=0, world=1, num_itr=MCTS_SIMULATIONS,
-                 cpuct=C_PUCT, max_iters=256, edges_per_tree=0, dirichlet=True, log_moves=False):
+                 cpuct=C_PUCT, max_iters=256, edges_per_tree=0, dirichlet=True, log_moves=False, fused=None):
         self.eng, self.evaluate = engine, evaluate
+        # `evaluate` = ResidualCNN.evaluate_states of a model living in this engine -> fused C round loop (ccx_mcts_run_net);
+        # any other callable (stub evaluators, tests) -> one select / evaluate / expand_backup round trip per simulation
+        owner = getattr(evaluate, "__self__", None)
+        auto = getattr(owner, "fused_mcts", False) and getattr(owner, "eng", None) is engine and getattr(evaluate, "__name__", "") == "evaluate_states"
+        self.fused = bool(auto) if fused is None else bool(fused)
         self.n, self.seed, self.rank, self.world = int(n_slots), int(seed), int(rank), int(world)
         self.num_itr, self.cpuct, self.max_iters, self.ept = int(num_itr), float(cpuct), int(max_iters), int(edges_per_tree)
         self.dirichlet = dirichlet
@@ -57,11 +62,15 @@ class BatchedSelfPlay:
         e.call("ccx_mcts_begin", n, _p(st), self.num_itr + 1, self.ept, INITIAL_RANDOM_MOVES)
         if self.dirichlet:
             e.call("ccx_gamma_noise", n, NOISE_STRIDE, DIRICHLET_ALPHA, self.seed, it, uid0, _p(self.noise))
-        for r in range(self.num_itr + 1):               # round 0 = make_move's root expansion (selfplay.py:117)
-            e.call("ccx_mcts_select", n, self.cpuct, _p(self.leaf))
-            p, v = self.evaluate(self.leaf)
-            noise = self.noise if (r == 0 and self.dirichlet) else None
-            e.call("ccx_mcts_expand_backup", n, _p(p), _p(v), _p(noise), NOISE_STRIDE if noise is not None else 0, 1)
+        if self.fused:                                   # the library's own net: all rounds in one C call, fused round kernels
+            e.call("ccx_mcts_run_net", n, self.num_itr + 1, self.cpuct, _p(self.noise) if self.dirichlet else None,
+                   NOISE_STRIDE, 1)
+        else:
+            for r in range(self.num_itr + 1):           # round 0 = make_move's root expansion (selfplay.py:117)
+                e.call("ccx_mcts_select", n, self.cpuct, _p(self.leaf))
+                p, v = self.evaluate(self.leaf)
+                noise = self.noise if (r == 0 and self.dirichlet) else None
+                e.call("ccx_mcts_expand_backup", n, _p(p), _p(v), _p(noise), NOISE_STRIDE if noise is not None else 0, 1)
         e.call("ccx_mcts_finalize", n, 1.0, _p(self.visits), None, None, _p(self.tree_nodes))
         e.call("ccx_selfplay_advance", n, _p(st), _p(self.visits), _p(self.tree_nodes), self.seed, it, uid0, _p(self.serial),
                self.world * n, INITIAL_RANDOM_MOVES, TOTAL_MOVES_TILL_TAU0, PROGRESS_MOVE_LIMIT, _p(self.rec_state),

@@ -143,6 +143,12 @@ int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t eva
 int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree,
                    int32_t min_ply);
 int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state);
+/* The same rounds with the library's own net as the evaluator (ccx_net_load / ccx_net_load_tc, mode from
+ * ccx_net_set_mode), fused: per round  select + to_model_input -> net forward -> float64 softmax + expand +
+ * backup  (4 launches, priors never leave the SM).  Equivalent to `rounds` x (ccx_mcts_select, ccx_net_eval,
+ * ccx_mcts_expand_backup); root_noise is applied in the first round only (selfplay.py:117-124). */
+int ccx_mcts_run_net(ccx_handle *h, int64_t n, int32_t rounds, double cpuct, const double *root_noise, int32_t noise_stride,
+                     int32_t noise_normalize);
 /* root_noise is applied to trees whose expanded leaf is the root; noise_normalize != 0 divides each
  * tree's first n_edges values by their sum first (raw gamma draws -> Dirichlet, selfplay.py:121). */
 int ccx_mcts_expand_backup(ccx_handle *h, int64_t n, const double *p, const double *v, const double *root_noise,
@@ -217,6 +223,8 @@ int ccx_traj_pack(ccx_handle *h, int64_t m, const int64_t *rows, const uint64_t 
 int ccx_debug_umma_gemm(ccx_handle *h, const void *A, const void *Bt, int32_t K, int32_t N, float *D);
 /* same, with A [rows x K] held in the row-contiguous operand layout of the 3x3 conv and the descriptor start moved by
  * `shift` rows: D[128 x N] = A[shift .. shift+127] * Bt^T (self-test of 16-byte-granular descriptor starts). */
+/* same with the A operand [128 x 64] read from TMEM (tcgen05.mma "ts" form; packed pairs written with tcgen05.st) */
+int ccx_debug_umma_gemm_ts(ccx_handle *h, const void *A, const void *Bt, int32_t N, float *D);
 int ccx_debug_umma_gemm_rows(ccx_handle *h, const void *A, int32_t rows, int32_t shift, const void *Bt, int32_t K, int32_t N,
                              float *D);
 

@@ -112,3 +112,22 @@ def test_mcts_with_net_runs_and_is_deterministic(model):
     b = m.search_with(roots, model.evaluate_states)
     assert torch.equal(a["visits"], b["visits"])
     assert np.all(a["visits"].cpu().numpy().sum(1) == 39)
+
+
+@pytest.mark.parametrize("kernel", ["simt", "tc"])
+@pytest.mark.parametrize("pre_expand", [False, True])
+def test_fused_round_loop_equals_round_trips(model, kernel, pre_expand):
+    """ccx_mcts_run_net (select+encode, net, softmax+expand+backup fused, all rounds in one C call) must build
+    exactly the trees of the select / ccx_net_eval / expand_backup round trips: same visit counts, same root Q."""
+    from chinesecheckersagent_b200.engine import BatchedMCTS
+    model.set_kernel(kernel)
+    st, _, _ = orc.step_random(orc.start_states(257), 11, 0, 9)
+    roots = torch.from_numpy(np.ascontiguousarray(st).view(np.int64)).cuda()
+    noise = torch.rand((257, 128), dtype=torch.float64, device="cuda") if pre_expand else None
+    m = BatchedMCTS(model.eng, num_itr=48)
+    a = m.search_with(roots, model.evaluate_states, pre_expand=pre_expand, root_noise=noise)
+    b = m.search_net(roots, pre_expand=pre_expand, root_noise=noise)
+    assert torch.equal(a["visits"], b["visits"])
+    assert torch.equal(a["q"].view(torch.int64), b["q"].view(torch.int64))
+    assert torch.equal(a["n_nodes"], b["n_nodes"])
+    model.set_kernel("tc")

@@ -41,3 +41,19 @@ def test_umma_row_shifted_descriptor(K, N, shift):
     ref = A[shift:shift + 128].float() @ Bt.float().t()
     assert torch.allclose(D, ref, atol=1e-2, rtol=1e-3), (D - ref).abs().max().item()
     eng.close()
+
+
+@pytest.mark.parametrize("N", [32, 64])
+def test_umma_a_operand_from_tmem(N):
+    """1x1 convs read their A operand from TMEM (packed 16-bit pairs, element 2j in the low half of column j)."""
+    from chinesecheckersagent_b200.engine import Engine
+    eng = Engine(0)
+    g = torch.Generator(device="cuda").manual_seed(N)
+    A = torch.randn((128, 64), device="cuda", generator=g).to(torch.bfloat16)
+    Bt = torch.randn((N, 64), device="cuda", generator=g).to(torch.bfloat16)
+    D = torch.zeros((128, N), device="cuda", dtype=torch.float32)
+    eng.call("ccx_debug_umma_gemm_ts", ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(Bt.data_ptr()), N, ctypes.c_void_p(D.data_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float() @ Bt.float().t()
+    assert torch.allclose(D, ref, atol=1e-2, rtol=1e-3), (D - ref).abs().max().item()
+    eng.close()
