@@ -870,6 +870,306 @@ k_policy_dense_tc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, 
     if (warp == 0) umma::tmem_free(tmem, 256);
 }
 
+// =====================================================================================================
+// Trunk kernel v4 = v3 with the 1x1 convs' A operands and the residual stream moved into TENSOR MEMORY:
+//  * the fp32 residual x lives in TMEM columns [0,64): conv C accumulates straight onto it (D += m2 * Wc with
+//    D = x), its epilogue applies bias + ReLU in place and writes the 16-bit copy of x that conv A of the next
+//    block reads — also in TMEM (columns [64,96), two channels per column, tcgen05.mma "ts" form).  conv B's
+//    output goes the same way to conv C (columns [64,80)).  Only the 3x3 conv still reads its A operand from
+//    shared memory (the three row-shifted copies), so a block's tensor-core operand traffic out of shared
+//    memory drops from 122 KB to 98 KB per tile and two of its three epilogues need no shared-memory store and
+//    no generic->async proxy fence;
+//  * no residual registers and no [128 x 64] shared operand: 70 KB of shared memory, <= 85 registers,
+//    128 TMEM columns per CTA -> THREE CTAs (24 warps) per SM instead of two.
+// TMEM columns: X fp32 [0,64) | XB: 16-bit x [64,96), reused as M2B: 16-bit conv-B output [64,80) |
+//               AO: conv A / conv B / heads accumulator [96,128).
+namespace tc4 {
+constexpr int THREADS = 256, POS = 4, POS_ROWS = 30, LIVE_ROWS = 120;
+constexpr int YROWS = 130, Y_LBO = YROWS * 16, Y_COPY = 4 * Y_LBO;        // 1 guard row + 128 + 1 guard row
+constexpr int T_X = 0, T_XB = 64, T_AO = 96;
+constexpr int S_Y = 0;
+constexpr int S_WC1 = S_Y + 3 * Y_COPY;
+constexpr int S_WA = S_WC1 + 8192, S_WB = S_WA + 4096, S_WC = S_WB + 18432;
+constexpr int S_F = S_WC + 4096;                         // floats [0, F_POLD) then [F_D1W, F_TOTAL)
+constexpr int NF_A = tcl::F_POLD, NF_B = tcl::F_TOTAL - tcl::F_D1W;
+constexpr int F_BYTES = (((NF_A + NF_B) * 4 + 15) / 16) * 16;
+constexpr int FO_D1W = NF_A, FO_D1B = FO_D1W + 800, FO_VHW = FO_D1B + 32, FO_VHB = FO_VHW + 32;
+constexpr int S_PLANES = S_F + F_BYTES;
+constexpr int S_VALC = S_PLANES + 1376;
+constexpr int S_TOTAL = S_VALC + 512;
+static_assert(S_TOTAL <= 74 * 1024, "three CTAs per SM");
+static_assert(S_WC1 % 128 == 0 && S_F % 16 == 0 && S_PLANES % 16 == 0, "alignment");
+}  // namespace tc4
+
+template <bool FP16>
+__global__ void __launch_bounds__(tc4::THREADS, 3)
+k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
+                __nv_bfloat16 *__restrict__ polc, float *__restrict__ value)
+{
+    using namespace tc4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int rg = warp & 3, h = warp >> 2;                  // TMEM lane group, column half
+    const int r = rg * 32 + lane;                            // operand row of this thread
+    const int p_local = r / POS_ROWS, rem = r % POS_ROWS, cy = rem / 6, cx = rem % 6;
+    const bool live = r < LIVE_ROWS && cx < 5;
+    const int cell = cy * 5 + cx;
+    const uint32_t sbase = umma::smem_u32(smem);
+    const float *sF = reinterpret_cast<const float *>(smem + S_F);
+    const int64_t n_tiles = (n + POS - 1) / POS;
+    const bool planes_aligned = (reinterpret_cast<uintptr_t>(planes) & 3) == 0;
+
+    auto refill3 = [&](int dst, const uint8_t *src, int bytes) {
+        for (int i = t; i < bytes / 16; i += THREADS) cp_async16(sbase + dst + i * 16, src + i * 16);
+        cp_async_commit();
+    };
+    auto load_planes = [&](int64_t tile, uint32_t (&w)[2]) {
+        const int64_t pos0 = tile * POS;
+        const int bytes = (int)min((int64_t)POS, n - pos0) * 343;
+        const uint8_t *src = planes + pos0 * 343;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int idx = q * THREADS + t;
+            uint32_t v = 0;
+            if (idx * 4 + 4 <= bytes && planes_aligned) v = __ldg(reinterpret_cast<const uint32_t *>(src) + idx);
+            else
+                for (int k = 0; k < 4; k++) if (idx * 4 + k < bytes) v |= (uint32_t)__ldg(src + idx * 4 + k) << (8 * k);
+            w[q] = v;
+        }
+    };
+    auto store_planes = [&](const uint32_t (&w)[2]) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int idx = q * THREADS + t;
+            if (idx < 344) reinterpret_cast<uint32_t *>(smem + S_PLANES)[idx] = w[q];
+        }
+    };
+
+    for (int i = t; i < 8192 / 16; i += THREADS) cp_async16(sbase + S_WC1 + i * 16, wb + tcl::W_CONV1 + i * 16);
+    refill3(S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);                // group: conv1 + A0
+    refill3(S_WB, wb + tcl::W_BLOCK0 + tcl::W_BB, 18432);               // group: B0
+    refill3(S_WC, wb + tcl::W_BLOCK0 + tcl::W_BC, 4096);                // group: C0
+    for (int i = t; i < S_WC1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows stay zero
+    for (int i = t; i < NF_A + NF_B; i += THREADS) reinterpret_cast<float *>(smem + S_F)[i] = __ldg(fb + (i < NF_A ? i : tcl::F_D1W + i - NF_A));
+    {
+        uint32_t w0[2];
+        load_planes(blockIdx.x, w0);
+        store_planes(w0);
+    }
+    if (t == 0) umma::mbar_init(&bar, 1);
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(rg * 32) << 16);
+    uint32_t phase = 0;
+    const umma::DescBase dY = umma::desc_base(sbase + S_Y, Y_LBO, 128u);
+    const umma::DescBase dWC1 = umma::desc_base(sbase + S_WC1, 128u, 64 / 8 * 128u), dWA = umma::desc_base(sbase + S_WA, 128u, 64 / 8 * 128u);
+    const umma::DescBase dWB = umma::desc_base(sbase + S_WB, 128u, 288 / 8 * 128u), dWC = umma::desc_base(sbase + S_WC, 128u, 32 / 8 * 128u);
+    constexpr uint32_t ID32 = umma::make_idesc(32, FP16), ID64 = umma::make_idesc(64, FP16);
+
+    // operands written to TMEM: make the stores visible to the tensor core, then the CTA barrier
+    auto tmem_sync = [&]() {
+        cp_async_wait<2>();
+        umma::tmem_wait_st();
+        umma::fence_before_sync();
+        __syncthreads();
+    };
+    // operands written to shared memory (conv A's output copies)
+    auto smem_sync = [&]() {
+        cp_async_wait<2>();
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+    };
+    auto wait_mma = [&]() {
+        umma::mbar_wait(&bar, phase); phase ^= 1;
+        umma::fence_after_sync();
+    };
+    auto pack8 = [&](const float *rr) {
+        return make_uint4(pack2<FP16>(rr[0], rr[1]), pack2<FP16>(rr[2], rr[3]), pack2<FP16>(rr[4], rr[5]), pack2<FP16>(rr[6], rr[7]));
+    };
+    // x (32 fp32 columns of this thread, already bias+ReLU'ed) -> TMEM X in place and its 16-bit copy XB, 16 columns at a time
+    auto finish_x = [&](const float *bias32, bool add_bias_from_tmem_value_only) {
+        (void)add_bias_from_tmem_value_only;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            float v[16];
+            umma::tmem_ld16(trow + T_X + h * 32 + half * 16, v);
+            uint32_t f[16], pk[8];
+#pragma unroll
+            for (int j = 0; j < 16; j++) { v[j] = fmaxf(v[j] + bias32[half * 16 + j], 0.f); f[j] = __float_as_uint(v[j]); }
+#pragma unroll
+            for (int j = 0; j < 8; j++) pk[j] = pack2<FP16>(v[2 * j], v[2 * j + 1]);
+            umma::tmem_st16(trow + T_X + h * 32 + half * 16, f);
+            umma::tmem_st8(trow + T_XB + h * 16 + half * 8, pk);
+        }
+    };
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t pos0 = tile * POS;
+        const int n_pos = (int)min((int64_t)POS, n - pos0);
+        uint32_t pw[2] = {0u, 0u};
+        if (tile + gridDim.x < n_tiles) load_planes(tile + gridDim.x, pw);       // lands while this tile computes
+        cp_async_commit();                                   // (empty group: keeps the group count per phase uniform)
+        // ---- conv1 operand: im2col of the 3x3 'valid' window, K = 63 (+1 zero) (model.py:62), packed into TMEM XB
+        {
+            const uint8_t *pl = smem + S_PLANES + (live ? p_local * 343 : 0);
+#pragma unroll
+            for (int c8 = 0; c8 < 2; c8++) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    float v2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int kk = h * 32 + c8 * 16 + q * 2 + e;
+                        const int tap = kk / 7, ch = kk % 7, dy = tap / 3, dx = tap % 3;
+                        v2[e] = (live && kk < 63) ? (float)pl[((cy + dy) * 7 + (cx + dx)) * 7 + ch] : 0.f;
+                    }
+                    pk[q] = pack2<FP16>(v2[0], v2[1]);
+                }
+                umma::tmem_st8(trow + T_XB + h * 16 + c8 * 8, pk);
+            }
+        }
+        tmem_sync();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::gemm_issue_ts<64>(tmem + T_X, tmem + T_XB, dWC1, 0, ID64, false);
+                umma::commit(&bar);
+            }
+            __syncwarp();
+        }
+        cp_async_commit();                                   // (empty group)
+        wait_mma();
+        finish_x(sF + tcl::F_CONV1 + h * 32, false);
+        // ---- 9 bottleneck residual blocks (model.py:120-145) --------------------------------------------------
+        for (int b = 0; b < 9; b++) {
+            const uint8_t *wnext = wb + tcl::W_BLOCK0 + ((b + 1) % 9) * tcl::W_BLOCK;
+            const float *bias = sF + tcl::F_BLOCK0 + b * tcl::F_BLOCK;
+            // A: 1x1 conv 64 -> 32, ReLU; A operand = XB in TMEM
+            tmem_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XB, dWA, 0, ID32, false);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            refill3(S_WA, b < 8 ? wnext + tcl::W_BA : wb + tcl::W_HEADS, 4096);
+            {
+                float v[16];
+                umma::tmem_ld16(trow + T_AO + h * 16, v);
+#pragma unroll
+                for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q] + bias[h * 16 + q], 0.f);
+                const uint4 o0 = pack8(v), o1 = pack8(v + 8);
+                if (live) {
+                    // copy d serves kernel row dy = d - 1: output cell (y - dy, x) reads this cell, so the value goes to row r - 6*dy
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const int oy = cy - (d - 1);
+                        if (oy >= 0 && oy <= 4) {
+                            uint8_t *dst = smem + S_Y + d * Y_COPY + (2 * h) * Y_LBO + (1 + r - 6 * (d - 1)) * 16;
+                            *reinterpret_cast<uint4 *>(dst) = o0;
+                            *reinterpret_cast<uint4 *>(dst + Y_LBO) = o1;
+                        }
+                    }
+                }
+            }
+            // B: 3x3 'same' conv 32 -> 32 = nine accumulating K = 32 GEMMs on row-shifted views of the three copies
+            smem_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++)
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; dxi++)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ks++)
+                                umma::mma_bf16(tmem + T_AO, umma::desc_at(dY, (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO)),
+                                               umma::desc_at(dWB, (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128)), ID32, (d | dxi | ks) != 0);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            refill3(S_WB, wnext + tcl::W_BB, 18432);
+            {
+                float v[16];
+                umma::tmem_ld16(trow + T_AO + h * 16, v);
+                uint32_t pk[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    pk[q] = pack2<FP16>(fmaxf(v[2 * q] + bias[32 + h * 16 + 2 * q], 0.f), fmaxf(v[2 * q + 1] + bias[32 + h * 16 + 2 * q + 1], 0.f));
+                umma::tmem_st8(trow + T_XB + h * 8, pk);         // M2B: 32 channels = 16 columns
+            }
+            // C: 1x1 conv 32 -> 64 accumulated onto the residual (model.py:137-144): X += M2B * Wc, then bias + ReLU in place
+            tmem_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::gemm_issue_ts<32>(tmem + T_X, tmem + T_XB, dWC, 0, ID64, true);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            refill3(S_WC, wnext + tcl::W_BC, 4096);
+            finish_x(bias + 64 + h * 32, true);
+        }
+        // ---- heads: policy conv 64 -> 16 and value conv 64 -> 1 in one N = 32 GEMM (model.py:91, 108); weights in the A slot
+        tmem_sync();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XB, dWA, 0, ID32, false);
+                umma::commit(&bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        refill3(S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);                 // conv A of block 0 for the next tile
+        {
+            float v[16];
+            umma::tmem_ld16(trow + T_AO + h * 16, v);
+            if (live && p_local < n_pos) {
+                if (h == 0) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q] + sF[tcl::F_HEADS + q], 0.f);
+                    uint4 *dst = reinterpret_cast<uint4 *>(polc + (pos0 + p_local) * 400 + cell * 16);      // Flatten in (y, x, c) order
+                    dst[0] = pack8(v); dst[1] = pack8(v + 8);
+                } else {
+                    reinterpret_cast<float *>(smem + S_VALC)[p_local * 25 + cell] = fmaxf(v[0] + sF[tcl::F_HEADS + 16], 0.f);
+                }
+            }
+        }
+        store_planes(pw);
+        umma::fence_before_sync();
+        __syncthreads();
+        // ---- value head: dense_1 25 -> 32 ReLU, value_head 32 -> 1 tanh (model.py:95-103), fp32 ---------------------
+        if (warp < n_pos) {
+            const float *valc = reinterpret_cast<const float *>(smem + S_VALC) + warp * 25;
+            float acc = sF[FO_D1B + lane];
+            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], sF[FO_D1W + k * 32 + lane], acc);
+            float sv = fmaxf(acc, 0.f) * sF[FO_VHW + lane];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, off);
+            if (lane == 0) value[pos0 + warp] = tanhf(sv + sF[FO_VHB]);
+        }
+    }
+    cp_async_wait<0>();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 128);
+}
+
 // Policy dense v2: 128 positions x 80 outputs per CTA (grid = row tiles x 4 column quarters: 128 CTAs at the
 // self-play batch of 4,096 instead of 64), both K chunks in flight at once (two cp.async groups, the first
 // chunk's MMAs run while the second lands), logits staged through shared memory for coalesced stores.
@@ -998,6 +1298,8 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcl::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd2::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd2::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 208 * 2 + 160 * 208 * 2));
@@ -1018,17 +1320,23 @@ int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *l
         CCX_CUDA(h, cudaMalloc(&tc->polc, sizeof(__nv_bfloat16) * 400 * (size_t)n));
         tc->cap = n;
     }
-    static const bool use_v2 = getenv("CCX_TRUNK_V2") != nullptr;        // A/B switch for profiling the older kernel
+    static const bool use_v2 = getenv("CCX_TRUNK_V2") != nullptr;        // A/B switches for profiling the older kernels
+    static const bool use_v3 = getenv("CCX_TRUNK_V3") != nullptr;
     if (use_v2) {
         int64_t tiles = (n + 4) / 5;
         unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);     // two resident CTAs per SM
         if (tc->fp16) k_net_trunk_tc<true><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
         else k_net_trunk_tc<false><<<grid, 128, tcl::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
-    } else {
+    } else if (use_v3) {
         int64_t tiles = (n + tc3::POS - 1) / tc3::POS;
         unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);     // two resident CTAs per SM
         if (tc->fp16) k_net_trunk_tc3<true><<<grid, tc3::THREADS, tc3::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
         else k_net_trunk_tc3<false><<<grid, tc3::THREADS, tc3::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+    } else {
+        int64_t tiles = (n + tc4::POS - 1) / tc4::POS;
+        unsigned grid = (unsigned)(tiles < 3 * h->num_sms ? tiles : 3 * h->num_sms);     // three resident CTAs per SM
+        if (tc->fp16) k_net_trunk_tc4<true><<<grid, tc4::THREADS, tc4::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+        else k_net_trunk_tc4<false><<<grid, tc4::THREADS, tc4::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
     }
     CCX_LAUNCHED(h);
     if (use_v2) {
