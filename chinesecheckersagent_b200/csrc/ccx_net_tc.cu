@@ -908,7 +908,7 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
 {
     using namespace tc4;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, barW[4];                // MMAs of a phase done; weight slots A, B, C and conv1 landed
     __shared__ uint32_t tmem_slot;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int rg = warp & 3, h = warp >> 2;                  // TMEM lane group, column half
@@ -921,22 +921,26 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     const int64_t n_tiles = (n + POS - 1) / POS;
     const bool planes_aligned = (reinterpret_cast<uintptr_t>(planes) & 3) == 0;
 
-    auto refill3 = [&](int dst, const uint8_t *src, int bytes) {
-        for (int i = t; i < bytes / 16; i += THREADS) cp_async16(sbase + dst + i * 16, src + i * 16);
-        cp_async_commit();
+    // weight slots are refilled by ONE lane with a bulk copy (TMA engine); only the MMA-issuing lane ever waits for them
+    auto refill_slot = [&](int slot, int dst, const uint8_t *src, uint32_t bytes) {
+        umma::mbar_expect_tx(&barW[slot], bytes);
+        umma::bulk_g2s(sbase + dst, src, bytes, &barW[slot]);
     };
+    // words t and 256 + t (< 343) of a tile's input planes; bytes past the last position read as zero
     auto load_planes = [&](int64_t tile, uint32_t (&w)[2]) {
-        const int64_t pos0 = tile * POS;
-        const int bytes = (int)min((int64_t)POS, n - pos0) * 343;
-        const uint8_t *src = planes + pos0 * 343;
+        const int bytes = (int)min((int64_t)POS, n - tile * POS) * 343;
+        const uint8_t *src = planes + tile * (POS * 343);
+        w[0] = 0u; w[1] = 0u;
+        if (bytes == POS * 343 && planes_aligned) {
+            w[0] = __ldg(reinterpret_cast<const uint32_t *>(src) + t);
+            if (t < 343 - THREADS) w[1] = __ldg(reinterpret_cast<const uint32_t *>(src) + THREADS + t);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int idx = q * THREADS + t;
-            uint32_t v = 0;
-            if (idx * 4 + 4 <= bytes && planes_aligned) v = __ldg(reinterpret_cast<const uint32_t *>(src) + idx);
-            else
-                for (int k = 0; k < 4; k++) if (idx * 4 + k < bytes) v |= (uint32_t)__ldg(src + idx * 4 + k) << (8 * k);
-            w[q] = v;
+            for (int q = 0; q < 2; q++)
+                for (int k = 0; k < 4; k++) {
+                    const int byte = (q * THREADS + t) * 4 + k;
+                    if (byte < bytes) w[q] |= (uint32_t)__ldg(src + byte) << (8 * k);
+                }
         }
     };
     auto store_planes = [&](const uint32_t (&w)[2]) {
@@ -947,10 +951,6 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         }
     };
 
-    for (int i = t; i < 8192 / 16; i += THREADS) cp_async16(sbase + S_WC1 + i * 16, wb + tcl::W_CONV1 + i * 16);
-    refill3(S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);                // group: conv1 + A0
-    refill3(S_WB, wb + tcl::W_BLOCK0 + tcl::W_BB, 18432);               // group: B0
-    refill3(S_WC, wb + tcl::W_BLOCK0 + tcl::W_BC, 4096);                // group: C0
     for (int i = t; i < S_WC1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows stay zero
     for (int i = t; i < NF_A + NF_B; i += THREADS) reinterpret_cast<float *>(smem + S_F)[i] = __ldg(fb + (i < NF_A ? i : tcl::F_D1W + i - NF_A));
     {
@@ -958,11 +958,22 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         load_planes(blockIdx.x, w0);
         store_planes(w0);
     }
-    if (t == 0) umma::mbar_init(&bar, 1);
+    if (t == 0) {
+        umma::mbar_init(&bar, 1);
+#pragma unroll
+        for (int q = 0; q < 4; q++) umma::mbar_init(&barW[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        refill_slot(3, S_WC1, wb + tcl::W_CONV1, 8192);
+        refill_slot(0, S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);
+        refill_slot(1, S_WB, wb + tcl::W_BLOCK0 + tcl::W_BB, 18432);
+        refill_slot(2, S_WC, wb + tcl::W_BLOCK0 + tcl::W_BC, 4096);
+    }
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
+    uint32_t phW0 = 0, phW1 = 0, phW2 = 0;           // parities of the weight-slot barriers (tracked by the issuing lane)
+    bool conv1_ready = false;
     const uint32_t tmem = tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(rg * 32) << 16);
     uint32_t phase = 0;
@@ -973,14 +984,12 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
 
     // operands written to TMEM: make the stores visible to the tensor core, then the CTA barrier
     auto tmem_sync = [&]() {
-        cp_async_wait<2>();
         umma::tmem_wait_st();
         umma::fence_before_sync();
         __syncthreads();
     };
     // operands written to shared memory (conv A's output copies)
     auto smem_sync = [&]() {
-        cp_async_wait<2>();
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
@@ -1014,7 +1023,6 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         const int n_pos = (int)min((int64_t)POS, n - pos0);
         uint32_t pw[2] = {0u, 0u};
         if (tile + gridDim.x < n_tiles) load_planes(tile + gridDim.x, pw);       // lands while this tile computes
-        cp_async_commit();                                   // (empty group: keeps the group count per phase uniform)
         // ---- conv1 operand: im2col of the 3x3 'valid' window, K = 63 (+1 zero) (model.py:62), packed into TMEM XB
         {
             const uint8_t *pl = smem + S_PLANES + (live ? p_local * 343 : 0);
@@ -1039,12 +1047,12 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         if (warp == 0) {
             umma::fence_after_sync();
             if (umma::elect_one()) {
+                if (!conv1_ready) { umma::mbar_wait(&barW[3], 0); conv1_ready = true; }
                 umma::gemm_issue_ts<64>(tmem + T_X, tmem + T_XB, dWC1, 0, ID64, false);
                 umma::commit(&bar);
             }
             __syncwarp();
         }
-        cp_async_commit();                                   // (empty group)
         wait_mma();
         finish_x(sF + tcl::F_CONV1 + h * 32, false);
         // ---- 9 bottleneck residual blocks (model.py:120-145) --------------------------------------------------
@@ -1056,13 +1064,14 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
             if (warp == 0) {
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[0], phW0); phW0 ^= 1;
                     umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XB, dWA, 0, ID32, false);
                     umma::commit(&bar);
                 }
                 __syncwarp();
             }
             wait_mma();
-            refill3(S_WA, b < 8 ? wnext + tcl::W_BA : wb + tcl::W_HEADS, 4096);
+            if (warp == 0 && umma::elect_one()) refill_slot(0, S_WA, b < 8 ? wnext + tcl::W_BA : wb + tcl::W_HEADS, 4096);
             {
                 float v[16];
                 umma::tmem_ld16(trow + T_AO + h * 16, v);
@@ -1087,6 +1096,7 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
             if (warp == 0) {
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
 #pragma unroll
                     for (int d = 0; d < 3; d++)
 #pragma unroll
@@ -1100,7 +1110,7 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
                 __syncwarp();
             }
             wait_mma();
-            refill3(S_WB, wnext + tcl::W_BB, 18432);
+            if (warp == 0 && umma::elect_one()) refill_slot(1, S_WB, wnext + tcl::W_BB, 18432);
             {
                 float v[16];
                 umma::tmem_ld16(trow + T_AO + h * 16, v);
@@ -1115,13 +1125,14 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
             if (warp == 0) {
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[2], phW2); phW2 ^= 1;
                     umma::gemm_issue_ts<32>(tmem + T_X, tmem + T_XB, dWC, 0, ID64, true);
                     umma::commit(&bar);
                 }
                 __syncwarp();
             }
             wait_mma();
-            refill3(S_WC, wnext + tcl::W_BC, 4096);
+            if (warp == 0 && umma::elect_one()) refill_slot(2, S_WC, wnext + tcl::W_BC, 4096);
             finish_x(bias + 64 + h * 32, true);
         }
         // ---- heads: policy conv 64 -> 16 and value conv 64 -> 1 in one N = 32 GEMM (model.py:91, 108); weights in the A slot
@@ -1129,13 +1140,14 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         if (warp == 0) {
             umma::fence_after_sync();
             if (umma::elect_one()) {
+                umma::mbar_wait(&barW[0], phW0); phW0 ^= 1;
                 umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XB, dWA, 0, ID32, false);
                 umma::commit(&bar);
             }
             __syncwarp();
         }
         wait_mma();
-        refill3(S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);                 // conv A of block 0 for the next tile
+        if (warp == 0 && umma::elect_one()) refill_slot(0, S_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, 4096);   // conv A of block 0 for the next tile
         {
             float v[16];
             umma::tmem_ld16(trow + T_AO + h * 16, v);
@@ -1164,7 +1176,11 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
             if (lane == 0) value[pos0 + warp] = tanhf(sv + sF[FO_VHB]);
         }
     }
-    cp_async_wait<0>();
+    // the last refills (block 0's weights for a tile that never comes) must land before the CTA's shared memory is released
+    if (warp == 0 && umma::elect_one()) {
+        umma::mbar_wait(&barW[0], phW0); umma::mbar_wait(&barW[1], phW1); umma::mbar_wait(&barW[2], phW2);
+        if (!conv1_ready) umma::mbar_wait(&barW[3], 0);
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_free(tmem, 128);

@@ -117,6 +117,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// ---- bulk asynchronous copy global -> shared (TMA engine, no tensor map): one thread issues, completion is
+// signalled on an mbarrier as a transaction-byte count.  dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy (the tensor core reads operands through it)
