@@ -66,6 +66,17 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
                               "games_per_sec": world * GREEDY_GAMES * reps / t, "games_per_gpu": GREEDY_GAMES,
                               "mean_plies_per_game": c[0] / (GREEDY_GAMES * reps), "p1_win_frac": c[1] / (GREEDY_GAMES * reps),
                               "p2_win_frac": c[2] / (GREEDY_GAMES * reps), "repetition_stop_frac": c[3] / (GREEDY_GAMES * reps)}
+    # ---- §8f f3: greedy supervised-data generator (data_generators.py), records + pi + planes on the device ---------
+    from .data_generators import BatchedGreedyGenerator
+    gen = BatchedGreedyGenerator(eng, seed=DEFAULT_SEED, rank=rank, world=world)
+    gen.generate(GREEDY_GAMES)
+    barrier()
+    made = {}
+    t = _timed(lambda: made.update(gen.generate(GREEDY_GAMES)), 2, world)
+    out["greedy_datagen"] = {"metric": "games_per_sec", "value": world * GREEDY_GAMES * 2 / t, "unit": "games/s",
+                             "records_per_sec": world * int(made["v_y"].shape[0]) * 2 / t, "games_per_gpu": GREEDY_GAMES,
+                             "outputs": "board_x u8 (M,7,7,7), pi_y f32 (M,294), v_y i8 (M,)"}
+    del made, gen
     # ---- plane encoder (utils.to_model_input) straight into a bf16 NHWC tensor ----------------------------
     eenv = BatchedEnv(1 << 20, engine=eng, seed=DEFAULT_SEED)
     eenv.step_random(8)

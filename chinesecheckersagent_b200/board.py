@@ -47,6 +47,25 @@ class Board:
             self.randomise_initial_state()
         self._sync_ids()
 
+    @classmethod
+    def from_packed(cls, words, engine=None):
+        """Board from uint64 state words (include/ccx.h layout; words 0-4 suffice).  hist_moves holds the last two moves —
+        all that utils.to_model_input reads (utils.py:135-150)."""
+        b = cls.__new__(cls)
+        b._eng = engine or default_engine()
+        b.directions = [(-1, 0), (0, 1), (1, 1), (1, 0), (0, -1), (-1, -1)]
+        c1, c2, meta = int(words[2]), int(words[3]), int(words[4])
+        b.checkers_pos = [None, {i: _rc((c1 >> (8 * i)) & 0xFF) for i in range(NUM_CHECKERS)},
+                          {i: _rc((c2 >> (8 * i)) & 0xFF) for i in range(NUM_CHECKERS)}]
+        b._plies = (meta >> 32) & 0xFFFF
+        b.hist_moves = deque()
+        for k in (1, 0):
+            f, t = (meta >> (16 * k)) & 0xFF, (meta >> (16 * k + 8)) & 0xFF
+            if f != 0xFF and k < b._plies:
+                b.hist_moves.append((_rc(f), _rc(t)))
+        b._sync_ids()
+        return b
+
     # -- packed state <-> python attributes ------------------------------------------------------------
     def _sync_ids(self):
         self.checkers_id = [None, {p: i for i, p in self.checkers_pos[1].items()},

@@ -228,6 +228,23 @@ int ccx_debug_umma_gemm_ts(ccx_handle *h, const void *A, const void *Bt, int32_t
 int ccx_debug_umma_gemm_rows(ccx_handle *h, const void *A, int32_t rows, int32_t shift, const void *Bt, int32_t K, int32_t N,
                              float *D);
 
+/* ---- greedy supervised-data generator (data_generators.py:14-80; train_on_greedy.py:17-42) ---------------
+ * Batched GreedyDataGenerator.generate_play: every game starts from state[.][i] (ccx_reset: start position or
+ * randomised), optionally plays `random_plies` random legal plies (random_start), then both sides play
+ * GreedyPlayer.decide_move(training=True) with a uniform pick among filtered_best_moves until a win.  Every
+ * position is a record (state words 0-4, candidate masks); records of randomised games lose their first
+ * `drop_first` entries (data_generators.py:74-75).  The reference's 0.1 s "stuck" limit is a ply count here:
+ * a game that reaches `stuck_plies` records keeps its first `stuck_keep` with reward 0 (data_generators.py:65-67).
+ * Two passes: offsets == NULL counts (n_records[n], winner[n] out); then with offsets = exclusive prefix sum of
+ * n_records and total_records = their sum, the same call writes rec_state uint64[5][M], rec_cand uint64[6][M],
+ * rec_v int8[M] (+1/-1/0 from the side to move's point of view, utils.py:65-71) and optionally rec_game int32[M].
+ * ccx_cand_to_pi turns candidate masks into pi_y float32[M][294] (uniform over the candidates, :45-51). */
+int ccx_greedy_generate(ccx_handle *h, int64_t n, const uint64_t *state, int64_t game_id0, uint64_t seed, int32_t random_plies,
+                        int32_t drop_first, int32_t stuck_plies, int32_t stuck_keep, int32_t *n_records, uint8_t *winner,
+                        const int64_t *offsets, int64_t total_records, uint64_t *rec_state, uint64_t *rec_cand, int8_t *rec_v,
+                        int32_t *rec_game);
+int ccx_cand_to_pi(ccx_handle *h, int64_t m, const uint64_t *rec_cand, float *pi_y);
+
 /* ---- host-buffer variants: the reference-facing path with H2D/D2H inside the call -------------- */
 int ccx_movegen_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *dest_masks_host);
 int ccx_apply_host(ccx_handle *h, int64_t n, uint64_t *state_host, const uint8_t *from_host,
