@@ -45,6 +45,44 @@ k_gamma_noise(double *__restrict__ out, int64_t n, int stride, double alpha, u32
     out[t] = g;
 }
 
+// np.random.choice(294, p=pi) with pi = N^(1/tau) / sum (MCTS.py:131-140), warp-cooperative: each lane owns ten
+// consecutive actions, an inclusive scan of the lane sums locates the lane whose interval holds rnd * total.
+__device__ __forceinline__ int sample_action(const u32 *__restrict__ vis, bool det, double inv_tau, u32 rnd, int lane)
+{
+    double w[10], local = 0.0;
+#pragma unroll
+    for (int q = 0; q < 10; q++) {
+        int a = lane * 10 + q;
+        double N = a < CCX_NUM_ACTIONS ? (double)vis[a] : 0.0;
+        w[q] = det ? pow(N, inv_tau) : N;
+        local += w[q];
+    }
+    double incl = local;                                  // inclusive warp scan of the lane sums
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { double o = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += o; }
+    double total = __shfl_sync(FULL, incl, 31);
+    double target = u01(rnd) * total;                     // np.random.choice(294, p=pi) (MCTS.py:140)
+    double excl = incl - local;
+    int mine = -1;
+    if (target >= excl && target < incl) {
+        double acc = excl;
+#pragma unroll
+        for (int q = 0; q < 10; q++) { acc += w[q]; if (mine < 0 && w[q] > 0.0 && target < acc) mine = lane * 10 + q; }
+    }
+    // lowest lane that found an action wins; fall back to the most visited action on rounding edge cases
+    u32 have = __ballot_sync(FULL, mine >= 0);
+    if (have) return __shfl_sync(FULL, mine, __ffs(have) - 1);
+    u32 bestN = 0; int besta = 0;
+#pragma unroll
+    for (int q = 0; q < 10; q++) { int a = lane * 10 + q; if (a < CCX_NUM_ACTIONS && vis[a] > bestN) { bestN = vis[a]; besta = a; } }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        u32 oN = __shfl_xor_sync(FULL, bestN, off); int oa = __shfl_xor_sync(FULL, besta, off);
+        if (oN > bestN || (oN == bestN && oa < besta)) { bestN = oN; besta = oa; }
+    }
+    return besta;
+}
+
 // ---- advance one ply per running game -----------------------------------------------------------------------
 // warp per game; visits = MCTS result of this iteration (ignored for opening plies).
 __global__ void __launch_bounds__(32 * SP_WARPS)
@@ -91,42 +129,8 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
         bool det = recorded + random_plies > tau_switch;
         double inv_tau = det ? 1.0 / 0.01 : 1.0;
         const u32 *vis = visits + g * CCX_NUM_ACTIONS;
-        double w[10], local = 0.0;
-#pragma unroll
-        for (int q = 0; q < 10; q++) {
-            int a = lane * 10 + q;
-            double N = a < CCX_NUM_ACTIONS ? (double)vis[a] : 0.0;
-            w[q] = det ? pow(N, inv_tau) : N;
-            local += w[q];
-        }
-        double incl = local;                                  // inclusive warp scan of the lane sums
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { double o = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += o; }
-        double total = __shfl_sync(FULL, incl, 31);
         Philox4 r = philox4x32_10(k0, k1, (u32)ply, 3u, (u32)uid, (u32)(uid >> 32));
-        double target = u01(r.x) * total;                     // np.random.choice(294, p=pi) (MCTS.py:140)
-        double excl = incl - local;
-        int mine = -1;
-        if (target >= excl && target < incl) {
-            double acc = excl;
-#pragma unroll
-            for (int q = 0; q < 10; q++) { acc += w[q]; if (mine < 0 && w[q] > 0.0 && target < acc) mine = lane * 10 + q; }
-        }
-        // lowest lane that found an action wins; fall back to the most visited action on rounding edge cases
-        u32 have = __ballot_sync(FULL, mine >= 0);
-        int action;
-        if (have) action = __shfl_sync(FULL, mine, __ffs(have) - 1);
-        else {
-            u32 bestN = 0; int besta = 0;
-#pragma unroll
-            for (int q = 0; q < 10; q++) { int a = lane * 10 + q; if (a < CCX_NUM_ACTIONS && vis[a] > bestN) { bestN = vis[a]; besta = a; } }
-#pragma unroll
-            for (int off = 16; off; off >>= 1) {
-                u32 oN = __shfl_xor_sync(FULL, bestN, off); int oa = __shfl_xor_sync(FULL, besta, off);
-                if (oN > bestN || (oN == bestN && oa < besta)) { bestN = oN; besta = oa; }
-            }
-            action = besta;
-        }
+        int action = sample_action(vis, det, inv_tau, r.x, lane);
         id = action / 49;                                     // utils.decode_checker_index (utils.py:175-183)
         int off = action % 49;
         to = (off / 7) * 8 + (off % 7);
@@ -170,6 +174,79 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
     if (move_log && iter < rec_iters)       // from | to<<8 | status after the move<<16 | 1<<24 (valid) | recorded-by-MCTS<<25
         move_log[(int64_t)iter * n + g] = (u32)from | ((u32)to << 8) | ((u32)status << 16) | (1u << 24) |
                                           ((ply - 1 >= random_plies ? 1u : 0u) << 25);
+}
+
+// ---- Game.start (game.py:58-100) for arena / evaluation games: one ply per running game ------------------------
+// visits != NULL: the mover is an AiPlayer (player.py:136-166): MCTS.search was run on the unexpanded root, the move is
+// sampled from pi = N^(1/tau), tau = DET_TREE_TAU once total_moves > TOTAL_MOVES_TILL_TAU0 (player.py:151-154).
+// visits == NULL: the mover is the GreedyPlayer (player.py:72-76, 99-121): uniform pick among filtered_best_moves.
+// Then game.py:65-89: winner, 16-deque of destinations + repetition stop, optional move limit.
+// counters: [0] plies, [1] P1 wins, [2] P2 wins, [3] stopped (repetition / move limit / overflow / no moves)
+__global__ void __launch_bounds__(32 * SP_WARPS)
+k_game_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visits, const int32_t *__restrict__ tree_nodes,
+               u32 k0, u32 k1, int64_t uid0, double tau, int tau0_after, int move_limit, u64 *__restrict__ counters,
+               const uint8_t *__restrict__ jt)
+{
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
+    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
+    __syncthreads();
+    int64_t g = (int64_t)blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (g >= n) return;
+    u64 meta = st[4 * n + g];
+    if ((meta >> 56) != CCX_ST_RUNNING) return;
+    bool p2 = (meta >> 48) & 1;
+    u64 occ1 = st[0 * n + g], occ2 = st[1 * n + g], c1 = st[2 * n + g], c2 = st[3 * n + g];
+    Game gm;
+    gm.meta = meta;
+    gm.occ_me = p2 ? occ2 : occ1; gm.occ_op = p2 ? occ1 : occ2;
+    gm.cells_me = p2 ? c2 : c1;   gm.cells_op = p2 ? c1 : c2;
+    u64 lo = st[5 * n + g], hi = st[6 * n + g];
+    int ply = (int)((meta >> 32) & 0xFFFF);
+    u64 uid = (u64)(uid0 + g);
+    int id, from, to, status = CCX_ST_RUNNING;
+    if (visits) {
+        if (tree_nodes && tree_nodes[g] < 0) status = CCX_ST_MOVE_LIMIT;        // pool overflow: the search result is unusable
+        else {
+            bool det = tau != 1.0 || ply > tau0_after;                          // total_moves == plies played so far
+            double inv_tau = ply > tau0_after ? 1.0 / 0.01 : 1.0 / tau;
+            Philox4 r = philox4x32_10(k0, k1, (u32)ply, 4u, (u32)uid, (u32)(uid >> 32));
+            int action = sample_action(visits + g * CCX_NUM_ACTIONS, det, inv_tau, r.x, lane);
+            id = action / 49;
+            int off = action % 49;
+            to = (off / 7) * 8 + (off % 7);
+            from = (int)((gm.cells_me >> (8 * id)) & 0xFF);
+        }
+    } else {
+        u64 dest[6], cand[6];
+        movegen_rays(gm.occ_me | gm.occ_op, gm.cells_me, dest, sT);
+        int total = greedy_candidates(gm, dest, cand);
+        if (total == 0) status = CCX_ST_NO_MOVES;                               // the reference raises (player.py:113)
+        else {
+            Philox4 r = philox4x32_10(k0, k1, (u32)ply, 1u, (u32)uid, (u32)(uid >> 32));
+            id = pick_candidate(gm, cand, total, r.x, from, to);                // player.py:121
+        }
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    if (status == CCX_ST_RUNNING) {
+        apply_move(gm, id, from, to);                                           // game.py:65
+        push_hist(lo, hi, to);
+        ply++;
+        int win = winner_of(gm);
+        if (win) status = win;                                                  // game.py:70-71
+        else if (ply >= 16 && repetition_stop(lo, hi)) status = CCX_ST_REPETITION;       // game.py:73-82
+        else if (move_limit > 0 && ply >= move_limit) status = CCX_ST_MOVE_LIMIT;        // game.py:84-89
+        atomicAdd(&counters[0], 1ULL);
+    }
+    if (status == CCX_ST_WON_P1) atomicAdd(&counters[1], 1ULL);
+    else if (status == CCX_ST_WON_P2) atomicAdd(&counters[2], 1ULL);
+    else if (status != CCX_ST_RUNNING) atomicAdd(&counters[3], 1ULL);
+    gm.meta = (gm.meta & 0x00FFFFFFFFFFFFFFULL) | ((u64)status << 56);
+    bool np2 = (gm.meta >> 48) & 1;
+    st[0 * n + g] = np2 ? gm.occ_op : gm.occ_me; st[1 * n + g] = np2 ? gm.occ_me : gm.occ_op;
+    st[2 * n + g] = np2 ? gm.cells_op : gm.cells_me; st[3 * n + g] = np2 ? gm.cells_me : gm.cells_op;
+    st[4 * n + g] = gm.meta; st[5 * n + g] = lo; st[6 * n + g] = hi;
 }
 
 // ---- finish: label or drop the records of every game that ended this iteration, restart the slot -----------
@@ -279,6 +356,18 @@ int ccx_selfplay_finish(ccx_handle *h, int64_t n, uint64_t *state, int32_t iter,
     k_selfplay_finish<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>((u64 *)state, n, iter, start_iter, serial,
                                                                          (const u64 *)rec_state, rec_flag, rec_iters, restart,
                                                                          (u64 *)counters);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+int ccx_game_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32_t *visits, const int32_t *tree_nodes, uint64_t seed,
+                     int64_t uid0, double tau, int32_t tau0_after, int32_t move_limit, uint64_t *counters)
+{
+    if (!h || n < 0 || !(tau > 0.0) || (n && (!state || !counters))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    k_game_advance<<<(unsigned)((n + SP_WARPS - 1) / SP_WARPS), 32 * SP_WARPS, 0, h->stream>>>((u64 *)state, n, visits, tree_nodes, (u32)seed,
+                                                                                              (u32)(seed >> 32), uid0, tau, tau0_after,
+                                                                                              move_limit, (u64 *)counters, h->jump_table);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

@@ -218,14 +218,15 @@ class BatchedMCTS:
         e.call("ccx_mcts_finalize", n, self.tree_tau, _p(visits), _p(pi), _p(q), _p(nodes))
         return dict(visits=visits, pi=pi, q=q, n_nodes=nodes)
 
-    def search_net(self, roots, pre_expand=False, root_noise=None):
+    def search_net(self, roots, pre_expand=False, root_noise=None, min_ply_status=False):
         """The library's own policy/value net as the evaluator (the weights loaded into this engine by
         model.ResidualCNN.load_weights), all rounds in one C call with the fused round kernels
         (ccx_mcts_run_net).  Same results as search_with(roots, model.evaluate_states, ...)."""
         n = roots.shape[1]
         e = self.eng
         stride = 0 if root_noise is None else root_noise.shape[1]
-        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree, -1)
+        # min_ply_status: roots whose status is not RUNNING get an inactive tree (finished arena / self-play games)
+        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree, 0 if min_ply_status else -1)
         rounds = self.num_itr + (1 if pre_expand else 0)
         e.call("ccx_mcts_run_net", n, rounds, self.cpuct, _p(root_noise) if pre_expand else None, stride, 0)
         visits, pi, q, nodes = self._outputs(n)

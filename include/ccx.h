@@ -228,6 +228,15 @@ int ccx_debug_umma_gemm_ts(ccx_handle *h, const void *A, const void *Bt, int32_t
 int ccx_debug_umma_gemm_rows(ccx_handle *h, const void *A, int32_t rows, int32_t shift, const void *Bt, int32_t K, int32_t N,
                              float *D);
 
+/* ---- arena / evaluation games (game.py:58-100; ai_vs_ai.py:28-52; ai_vs_greedy.py:26-59; train.py:150-231) ----
+ * One Game.start ply for every RUNNING game.  visits != NULL: the mover is an AiPlayer whose MCTS result this is
+ * (uint32[n][294] from ccx_mcts_finalize, tree_nodes its n_nodes): the move is sampled from N^(1/tau), tau switching
+ * to DET_TREE_TAU once more than tau0_after plies were played (player.py:151-154).  visits == NULL: the mover is the
+ * GreedyPlayer (uniform among filtered_best_moves).  Then winner / repetition stop / optional move limit
+ * (move_limit = 0: off).  counters uint64[4] += {plies, P1 wins, P2 wins, stopped games}. */
+int ccx_game_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32_t *visits, const int32_t *tree_nodes, uint64_t seed,
+                     int64_t uid0, double tau, int32_t tau0_after, int32_t move_limit, uint64_t *counters);
+
 /* ---- greedy supervised-data generator (data_generators.py:14-80; train_on_greedy.py:17-42) ---------------
  * Batched GreedyDataGenerator.generate_play: every game starts from state[.][i] (ccx_reset: start position or
  * randomised), optionally plays `random_plies` random legal plies (random_start), then both sides play
