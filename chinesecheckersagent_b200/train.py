@@ -1,0 +1,179 @@
+"""Training step on the gathered self-play buffer (§8f f1): the consumer of `all_gather_trajectories`.
+
+Mirrors the reference's `train.train` (train.py:109-148) and the compile settings of `ResidualCNN.build_model`
+(model.py:58-87): the same 9-block net, loss = softmax cross-entropy with logits on the policy head (loss.py:3-4,
+soft targets pi) + mean squared error on the value head (loss weights 1, 1; config.py:41), L2 kernel regularisation
+REG_CONST = 6e-3 on every conv / dense kernel (not on biases or BatchNorm), SGD with Nesterov momentum 0.9 at
+LEARNING_RATE = 1e-4, batch 32, 5 epochs, shuffled, the last 5 % of the (pre-shuffle) data held out for validation
+as Keras' `validation_split` does.  Per SURVEY §8f this step is plain PyTorch (autograd, cuDNN convs): it is a
+consumer of the hot path, not part of it.  Weights enter and leave in the Keras `save_weights` tensor layout
+('<layer>/<param>' arrays, kernels (kh,kw,cin,cout), dense (in,out)), i.e. exactly what model.ResidualCNN loads into the
+CUDA inference kernels, so a trained net goes straight back into self-play."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .config import BATCH_SIZE, EPOCHS, LEARNING_RATE, LOSS_WEIGHTS, NUM_ACTIONS, REG_CONST
+
+BN_EPS, BN_MOMENTUM = 1e-3, 0.99          # Keras BatchNormalization defaults (moving = 0.99 * moving + 0.01 * batch)
+
+
+class _ConvBN(nn.Module):
+    def __init__(self, cin, cout, k, padding):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=True)
+        self.bn = nn.BatchNorm2d(cout, eps=BN_EPS, momentum=1.0 - BN_MOMENTUM)
+
+    def forward(self, x):
+        return self.bn(self.conv(x))
+
+
+class TrainableResidualCNN(nn.Module):
+    """model.py:58-145 in PyTorch (NCHW inside, Flatten in Keras' (H, W, C) order so dense kernels map 1:1)."""
+
+    def __init__(self):
+        super().__init__()
+        self.layers = nn.ModuleDict()
+        self.layers["1"] = _ConvBN(7, 64, 3, 0)                                    # model.py:62
+        for b in range(9):                                                          # model.py:66-76, 120-145
+            self.layers[str(2 + 3 * b)] = _ConvBN(64, 32, 1, 0)
+            self.layers[str(3 + 3 * b)] = _ConvBN(32, 32, 3, 1)
+            self.layers[str(4 + 3 * b)] = _ConvBN(32, 64, 1, 0)
+        self.layers["29"] = _ConvBN(64, 16, 1, 0)                                   # policy conv, model.py:108
+        self.layers["30"] = _ConvBN(64, 1, 1, 0)                                    # value conv, model.py:91
+        self.policy_head = nn.Linear(400, NUM_ACTIONS)
+        self.dense_1 = nn.Linear(25, 32)
+        self.value_head = nn.Linear(32, 1)
+
+    def forward(self, board_x):
+        """board_x (B,7,7,7) channels-last (uint8 or float) -> (logits (B,294), value (B,))"""
+        x = board_x.to(self.policy_head.weight.dtype).permute(0, 3, 1, 2)
+        L = self.layers
+        x = F.relu(L["1"](x))
+        for b in range(9):
+            y = F.relu(L[str(2 + 3 * b)](x))
+            y = F.relu(L[str(3 + 3 * b)](y))
+            x = F.relu(L[str(4 + 3 * b)](y) + x)
+        p = F.relu(L["29"](x)).permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+        v = F.relu(L["30"](x)).permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+        return self.policy_head(p), torch.tanh(self.value_head(F.relu(self.dense_1(v))))[:, 0]
+
+    # -- Keras tensor layout <-> torch -----------------------------------------------------------------
+    def load_keras_weights(self, w):
+        """w: dict '<layer>/<param>' -> array (model.read_weight_file of a .h5 / .npz)"""
+        with torch.no_grad():
+            for i, m in self.layers.items():
+                m.conv.weight.copy_(torch.from_numpy(np.ascontiguousarray(np.transpose(w["conv2d_%s/kernel" % i], (3, 2, 0, 1)))))
+                m.conv.bias.copy_(torch.from_numpy(np.asarray(w["conv2d_%s/bias" % i])))
+                m.bn.weight.copy_(torch.from_numpy(np.asarray(w["batch_normalization_%s/gamma" % i])))
+                m.bn.bias.copy_(torch.from_numpy(np.asarray(w["batch_normalization_%s/beta" % i])))
+                m.bn.running_mean.copy_(torch.from_numpy(np.asarray(w["batch_normalization_%s/moving_mean" % i])))
+                m.bn.running_var.copy_(torch.from_numpy(np.asarray(w["batch_normalization_%s/moving_variance" % i])))
+            for name in ("policy_head", "dense_1", "value_head"):
+                lin = getattr(self, name)
+                lin.weight.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(w[name + "/kernel"]).T)))
+                lin.bias.copy_(torch.from_numpy(np.asarray(w[name + "/bias"])))
+        return self
+
+    def keras_weights(self):
+        out = {}
+        for i, m in self.layers.items():
+            out["conv2d_%s/kernel" % i] = m.conv.weight.detach().permute(2, 3, 1, 0).contiguous().cpu().numpy().astype(np.float32)
+            out["conv2d_%s/bias" % i] = m.conv.bias.detach().cpu().numpy().astype(np.float32)
+            out["batch_normalization_%s/gamma" % i] = m.bn.weight.detach().cpu().numpy().astype(np.float32)
+            out["batch_normalization_%s/beta" % i] = m.bn.bias.detach().cpu().numpy().astype(np.float32)
+            out["batch_normalization_%s/moving_mean" % i] = m.bn.running_mean.detach().cpu().numpy().astype(np.float32)
+            out["batch_normalization_%s/moving_variance" % i] = m.bn.running_var.detach().cpu().numpy().astype(np.float32)
+        for name in ("policy_head", "dense_1", "value_head"):
+            lin = getattr(self, name)
+            out[name + "/kernel"] = lin.weight.detach().t().contiguous().cpu().numpy().astype(np.float32)
+            out[name + "/bias"] = lin.bias.detach().cpu().numpy().astype(np.float32)
+        return out
+
+    def save_weights(self, path):
+        """`.npz` with the Keras tensor names (model.ResidualCNN.load_weights reads it); `.h5` needs h5py, which writes the
+        layout Keras' load_weights expects (model_weights-less `save_weights` file: one group per layer)."""
+        w = self.keras_weights()
+        if str(path).endswith(".npz"):
+            np.savez(path, **w)
+            return path
+        try:
+            import h5py
+        except ImportError as e:
+            raise RuntimeError("writing Keras .h5 weight files needs h5py (not installed here); save to .npz instead") from e
+        layers = sorted({k.split("/")[0] for k in w})
+        with h5py.File(path, "w") as f:
+            f.attrs["layer_names"] = [n.encode() for n in layers]
+            f.attrs["backend"], f.attrs["keras_version"] = b"tensorflow", b"2.1.6"
+            for n in layers:
+                g = f.create_group(n)
+                names = [k for k in w if k.split("/")[0] == n]
+                g.attrs["weight_names"] = [(k + ":0").encode() for k in names]
+                for k in names:
+                    g.create_dataset(k + ":0", data=w[k])
+        return path
+
+    def kernel_l2(self):
+        """sum of squares of every conv / dense kernel (Keras kernel_regularizer=l2(REG_CONST), model.py:60)"""
+        s = 0.0
+        for m in self.layers.values():
+            s = s + (m.conv.weight ** 2).sum()
+        for lin in (self.policy_head, self.dense_1, self.value_head):
+            s = s + (lin.weight ** 2).sum()
+        return s
+
+
+def loss_terms(model, board_x, pi_y, v_y):
+    """(total, policy CE, value MSE, L2) as Keras reports them for one batch"""
+    logits, value = model(board_x)
+    ce = -(pi_y * F.log_softmax(logits, dim=1)).sum(1).mean()                 # loss.py:3-4, soft targets
+    mse = F.mse_loss(value, v_y.to(value.dtype))
+    l2 = REG_CONST * model.kernel_l2()
+    return LOSS_WEIGHTS["policy_head"] * ce + LOSS_WEIGHTS["value_head"] * mse + l2, ce, mse, l2
+
+
+def make_optimizer(model, lr=LEARNING_RATE):
+    # model.py:83: SGD(lr, momentum=0.9, nesterov=True).  Keras: v = m v - lr g; w += m v - lr g  ==  torch's Nesterov form
+    return torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, nesterov=True)
+
+
+def train(model, board_x, pi_y, v_y, data_retention=1.0, epochs=EPOCHS, batch_size=BATCH_SIZE, validation_split=0.05,
+          seed=None, log=None):
+    """train.train (train.py:109-148) on device tensors: sample `data_retention` of the examples without replacement
+    (:130-133), hold out the LAST validation_split of the sampled set (Keras semantics), shuffle every epoch.
+    Returns the per-epoch history [{loss, policy, value, val_loss, ...}]."""
+    dev = next(model.parameters()).device
+    g = torch.Generator(device="cpu")
+    if seed is not None:
+        g.manual_seed(int(seed))
+    n_all = board_x.shape[0]
+    keep = torch.randperm(n_all, generator=g)[:int(data_retention * n_all)].to(dev)
+    bx, py, vy = board_x.to(dev)[keep], pi_y.to(dev)[keep].float(), v_y.to(dev)[keep].float()
+    n = bx.shape[0]
+    n_val = int(n * validation_split)
+    n_tr = n - n_val
+    opt = make_optimizer(model)
+    history = []
+    for ep in range(epochs):
+        model.train()
+        perm = torch.randperm(n_tr, generator=g).to(dev)
+        tot = np.zeros(4)
+        for s in range(0, n_tr, batch_size):
+            idx = perm[s:s + batch_size]
+            opt.zero_grad(set_to_none=True)
+            terms = loss_terms(model, bx[idx], py[idx], vy[idx])
+            terms[0].backward()
+            opt.step()
+            tot += np.array([float(t.detach()) for t in terms]) * idx.numel()
+        rec = dict(zip(("loss", "policy", "value", "l2"), (tot / max(n_tr, 1)).tolist()))
+        if n_val:
+            model.eval()
+            with torch.no_grad():
+                vt = loss_terms(model, bx[n_tr:], py[n_tr:], vy[n_tr:])
+            rec.update(val_loss=float(vt[0]), val_policy=float(vt[1]), val_value=float(vt[2]))
+        history.append(rec)
+        if log:
+            log("epoch %d/%d %s" % (ep + 1, epochs, rec))
+    model.eval()
+    return history
