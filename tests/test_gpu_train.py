@@ -29,12 +29,12 @@ def test_generate_train_reload_loop(tmp_path):
     # the trained weights in the CUDA inference kernels (BN folded, fp16 tensor-core path and fp32 path) vs torch eval mode
     infer = ResidualCNN(engine=eng).load_weights(path)
     x = data["board_x"][5000:5000 + 512] if n >= 5512 else data["board_x"][:512]
-    with torch.no_grad():
-        logits, value = net(x)
-    p_ref = torch.softmax(logits.double(), dim=1)
-    for kernel, bar in (("simt", 2e-5), ("tc", 1e-3)):
+    with torch.no_grad():                               # float64 reference (cuDNN's fp32 convs default to TF32)
+        logits, value = net.double()(x)
+    p_ref = torch.softmax(logits, dim=1)
+    for kernel, bar in (("simt", 2e-5), ("tc", 5e-3)):      # tc bar: tests/test_gpu_net.py (16-bit operands)
         infer.set_kernel(kernel)
         p, v = infer.predict_batch(x)
         assert (p - p_ref).abs().max().item() < bar, kernel
-        assert (v - value.double()).abs().max().item() < max(bar, 1e-4), kernel
+        assert (v - value).abs().max().item() < max(bar, 1e-4), kernel
     eng.close()
