@@ -197,7 +197,9 @@ k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32
 // per-game Philox counters), which the parity tests check.
 // Tried and dropped (r01): two lanes per game (three checkers each, redundant tails) to double the warp
 // count at 65,536 games — 3.90e9 steps/s against 4.35e9 for this kernel; the pair votes and waits cost more
-// than the extra latency hiding buys.
+// than the extra latency hiding buys.  Also tried and dropped (r01c): two checkers in flight per THREAD (streams of
+// checkers 0-2 and 3-5 expanded branch-free in the same iteration for instruction-level parallelism) — bit-identical,
+// 3.93e9 steps/s: the dummy expansions of a stream that has run dry outweigh the overlapped latencies.
 #define READY_THRESHOLD 8
 
 template <bool TRACE>
