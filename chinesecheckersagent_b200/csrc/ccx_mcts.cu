@@ -431,15 +431,9 @@ k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, c
 // phase A': select + utils.to_model_input of the leaf (utils.py:101-160) written straight into the net's uint8
 // input batch, one warp per tree (the leaf's 343 bytes are staged in shared memory: zero, scatter the 36
 // labels, copy out)
-__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
-k_mcts_select_encode(ccx_trees trees, int64_t n, double cpuct, uint8_t *__restrict__ planes)
+__device__ __forceinline__ void do_select_encode(const TreeView &tv, int lane, double cpuct, uint8_t *__restrict__ sp,
+                                                 uint8_t *__restrict__ dst)
 {
-    __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
-    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (tree >= n) return;
-    TreeView tv = tree_view(trees, tree);
-    uint8_t *sp = sP[threadIdx.x >> 5];
     Game g;
     if (tv.meta[META_OVERFLOW]) {
         // inactive / overflowed tree: hand the evaluator a well-formed dummy position (its output is ignored)
@@ -471,32 +465,33 @@ k_mcts_select_encode(ccx_trees trees, int64_t n, double cpuct, uint8_t *__restri
             for (int c = lane; c < 49; c += 32) sp[c * 7 + 6] = 1;                // utils.py:157-158
     }
     __syncwarp();
-    uint8_t *dst = planes + tree * 343;
     for (int i = lane; i < 343; i += 32) dst[i] = sp[i];
 }
 
-// phase B': float64 softmax over all 294 logits (model.py:21-24, utils.py:187-192; same arithmetic as
-// k_softmax_f64) + expand + backup, one warp per tree; the priors never touch global memory
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
-k_mcts_softmax_expand_backup(ccx_trees trees, int64_t n, const float *__restrict__ logits, const float *__restrict__ value,
-                             const double *__restrict__ noise, int noise_stride, int noise_normalize, const uint8_t *__restrict__ jt)
+k_mcts_select_encode(ccx_trees trees, int64_t n, double cpuct, uint8_t *__restrict__ planes)
 {
-    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
-    __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
-    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
-    __syncthreads();
+    __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
+    do_select_encode(tv, lane, cpuct, sP[threadIdx.x >> 5], planes + tree * 343);
+}
+
+// phase B': float64 softmax over all 294 logits (model.py:21-24, utils.py:187-192; same arithmetic as
+// k_softmax_f64) + expand + backup, one warp per tree; the priors never touch global memory
+__device__ __forceinline__ void do_softmax_expand_backup(const TreeView &tv, int lane, const float *__restrict__ lg, double v,
+                                                         const double *__restrict__ noise, int noise_normalize, double *__restrict__ pr,
+                                                         const uint8_t *__restrict__ sT)
+{
     if (tv.meta[META_LEAFKIND] != LEAF_EVAL) return;
-    double *pr = sPr[threadIdx.x >> 5];
     {
         double x[10], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 10; j++) {
             int i = lane + 32 * j;
-            x[j] = i < 294 ? (double)logits[tree * 294 + i] : -INFINITY;
+            x[j] = i < 294 ? (double)lg[i] : -INFINITY;
             mx = fmax(mx, x[j]);
         }
 #pragma unroll
@@ -513,8 +508,47 @@ k_mcts_softmax_expand_backup(ccx_trees trees, int64_t n, const float *__restrict
     int leaf = tv.meta[META_LEAF], path_len = tv.meta[META_PATHLEN];
     Game g = load_node_game(tv, leaf);
     TablePrior tp = {pr};
-    if (expand_node(tv, lane, leaf, g, tp, sT, path_len > 0 ? tv.path[path_len - 1] : -1)) backup(tv, lane, path_len, (double)value[tree], false);
-    if (noise && leaf == 0) mix_root_noise(tv, lane, noise + tree * noise_stride, noise_normalize != 0);
+    if (expand_node(tv, lane, leaf, g, tp, sT, path_len > 0 ? tv.path[path_len - 1] : -1)) backup(tv, lane, path_len, v, false);
+    if (noise && leaf == 0) mix_root_noise(tv, lane, noise, noise_normalize != 0);
+}
+
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_softmax_expand_backup(ccx_trees trees, int64_t n, const float *__restrict__ logits, const float *__restrict__ value,
+                             const double *__restrict__ noise, int noise_stride, int noise_normalize, const uint8_t *__restrict__ jt)
+{
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
+    __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
+    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
+    __syncthreads();
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    do_softmax_expand_backup(tv, lane, logits + tree * 294, (double)value[tree], noise ? noise + tree * noise_stride : nullptr,
+                             noise_normalize, sPr[threadIdx.x >> 5], sT);
+}
+
+// one launch per round in steady state: finish the previous round's leaf (softmax + expand + backup), then select and encode
+// the next one — the same warp owns the tree in both halves, so the halves need no grid-wide ordering between them
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+k_mcts_round(ccx_trees trees, int64_t n, double cpuct, const float *__restrict__ logits, const float *__restrict__ value,
+             const double *__restrict__ noise, int noise_stride, int noise_normalize, uint8_t *__restrict__ planes,
+             const uint8_t *__restrict__ jt)
+{
+    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
+    __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
+    __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
+    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
+    __syncthreads();
+    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (tree >= n) return;
+    TreeView tv = tree_view(trees, tree);
+    do_softmax_expand_backup(tv, lane, logits + tree * 294, (double)value[tree], noise ? noise + tree * noise_stride : nullptr,
+                             noise_normalize, sPr[threadIdx.x >> 5], sT);
+    __syncwarp();
+    __threadfence_block();
+    do_select_encode(tv, lane, cpuct, sP[threadIdx.x >> 5], planes + tree * 343);
 }
 
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
@@ -708,20 +742,24 @@ int ccx_mcts_run_net(ccx_handle *h, int64_t n, int32_t rounds, double cpuct, con
     static const bool timing = getenv("CCX_RUN_NET_TIMING") != nullptr;      // debug: per-kernel in-situ times of rounds 100..103
     cudaEvent_t ev[16];
     if (timing) for (auto &e : ev) cudaEventCreate(&e);
+    // round r: [r == 0: select+encode | r > 0: finish round r-1's leaf, then select+encode] -> net; one last finish at the end
     for (int r = 0; r < rounds; r++) {
         const bool tr = timing && r >= 100 && r < 104;
         if (tr) cudaEventRecord(ev[(r - 100) * 4 + 0], h->stream);
-        k_mcts_select_encode<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, planes);
+        if (r == 0)
+            k_mcts_select_encode<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, planes);
+        else
+            k_mcts_round<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, logits, value, r == 1 ? root_noise : nullptr,
+                                                                            noise_stride, noise_normalize, planes, h->jump_table);
         CCX_LAUNCHED(h);
         if (tr) cudaEventRecord(ev[(r - 100) * 4 + 1], h->stream);
         if ((rc = ccx_net_forward_active(h, n, planes, logits, value))) return rc;
-        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 2], h->stream);
-        k_mcts_softmax_expand_backup<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, logits, value,
-                                                                                        r == 0 ? root_noise : nullptr, noise_stride,
-                                                                                        noise_normalize, h->jump_table);
-        CCX_LAUNCHED(h);
-        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 3], h->stream);
+        if (tr) { cudaEventRecord(ev[(r - 100) * 4 + 2], h->stream); cudaEventRecord(ev[(r - 100) * 4 + 3], h->stream); }
     }
+    k_mcts_softmax_expand_backup<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, logits, value,
+                                                                                    rounds == 1 ? root_noise : nullptr, noise_stride,
+                                                                                    noise_normalize, h->jump_table);
+    CCX_LAUNCHED(h);
     if (timing && rounds >= 104) {
         cudaStreamSynchronize(h->stream);
         for (int i = 0; i + 1 < 16; i++) {
