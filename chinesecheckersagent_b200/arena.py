@@ -23,6 +23,8 @@ class BatchedArena:
         models = [p for p in (p1, p2) if p is not GREEDY and p != GREEDY]
         if not models:
             raise ValueError("at least one side must be a model (greedy-vs-greedy is BatchedEnv.play_greedy)")
+        if len(models) == 2 and models[0] is not models[1] and models[0].eng is models[1].eng:
+            raise ValueError("two different models need two Engines (one set of net weights per ccx handle)")
         self.players = {PLAYER_ONE: p1, PLAYER_TWO: p2}
         self.n, self.seed, self.uid0 = int(n), int(seed), int(game_id0)
         self.tau = float(tree_tau)
