@@ -86,6 +86,36 @@ class _File:
             pos += 16              # child pointer + next key
         return out
 
+    # -- attributes (message 0x0C, version 1): fixed-length string arrays and numeric arrays ---------------
+    def attributes(self, addr):
+        d = self.d
+        out = {}
+        for mtype, body, _ in self.messages(addr):
+            if mtype != 0x0C or d[body] != 1:
+                continue
+            nsz, tsz, ssz = struct.unpack_from("<HHH", d, body + 2)
+            pad = lambda x: (x + 7) & ~7
+            pos = body + 8
+            name = d[pos:pos + nsz].split(b"\x00")[0].decode()
+            pos += pad(nsz)
+            cls, size = d[pos] & 0x0F, struct.unpack_from("<I", d, pos + 4)[0]
+            big = d[pos + 1] & 1
+            tpos = pos
+            pos += pad(tsz)
+            ver, rank = d[pos], d[pos + 1]
+            dims = struct.unpack_from("<%dQ" % rank, d, pos + (8 if ver == 1 else 4)) if rank else ()
+            pos += pad(ssz)
+            n = int(np.prod(dims)) if dims else 1
+            if cls == 3:
+                vals = [d[pos + i * size:pos + (i + 1) * size].split(b"\x00")[0] for i in range(n)]
+                out[name] = vals if dims else vals[0]
+            elif cls in (0, 1):
+                kind = "f" if cls == 1 else ("i" if (d[tpos + 1] >> 3) & 1 else "u")
+                out[name] = np.frombuffer(d, dtype=np.dtype(("<", ">")[big] + kind + "%d" % size), count=n, offset=pos).reshape(dims).copy()
+            else:
+                out[name] = None                        # variable-length strings etc.: present, not decoded
+        return out
+
     # -- dataset --------------------------------------------------------------------------------------
     def dataset(self, addr):
         d = self.d
@@ -149,3 +179,177 @@ def read_weights(path):
     if not out:
         raise H5Error("no Keras weights found in %s" % path)
     return out
+
+
+# =====================================================================================================
+# Writer: the same subset, enough for Keras `save_weights` files (model.py:38-41) and the reference's training-data
+# files (utils.save_train_data, utils.py:48-56): superblock v0, old-style groups (one symbol-table node per group:
+# the superblock's group-leaf K is sized for the largest group), v1 object headers, contiguous little-endian
+# datasets, v1 attribute messages holding numeric arrays or fixed-length string arrays (what h5py writes for a list
+# of bytes — Keras' layer_names / weight_names).
+
+def _pad8(b):
+    return b + b"\x00" * (-len(b) % 8)
+
+
+def _msg(mtype, body, flags=0):
+    body = _pad8(body)
+    return struct.pack("<HHB3x", mtype, len(body), flags) + body
+
+
+def _dtype_msg(dt):
+    dt = np.dtype(dt)
+    if dt.kind == "S":
+        return struct.pack("<BBBBI", 0x13, 0x01, 0, 0, dt.itemsize)                       # string, null-padded, ASCII
+    if dt.kind == "f":
+        spec = {4: (31, 23, 8, 0, 23, 127), 8: (63, 52, 11, 0, 52, 1023)}[dt.itemsize]
+        sign, eloc, esz, mloc, msz, bias = spec
+        return (struct.pack("<BBBBI", 0x11, 0x20, sign, 0, dt.itemsize) +
+                struct.pack("<HHBBBBI", 0, dt.itemsize * 8, eloc, esz, mloc, msz, bias))
+    if dt.kind in "iu":
+        return struct.pack("<BBBBI", 0x10, 0x08 if dt.kind == "i" else 0x00, 0, 0, dt.itemsize) + struct.pack("<HH", 0, dt.itemsize * 8)
+    raise H5Error("unsupported dtype %s" % dt)
+
+
+def _space_msg(shape):
+    return struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", int(x)) for x in shape)
+
+
+def _attr_msg(name, value):
+    if isinstance(value, (list, tuple)) and (len(value) == 0 or isinstance(value[0], (bytes, str))):
+        vals = [v.encode() if isinstance(v, str) else v for v in value]
+        arr = np.array(vals, dtype="S%d" % max([len(v) for v in vals] + [1])) if vals else np.zeros((0,), dtype=np.float64)
+    elif isinstance(value, (bytes, str)):
+        arr = np.array(value.encode() if isinstance(value, str) else value)
+    else:
+        arr = np.asarray(value)
+    shape = arr.shape                              # (np.ascontiguousarray would promote a scalar to shape (1,))
+    arr = np.ascontiguousarray(arr)
+    if arr.dtype.byteorder == ">":
+        arr = arr.astype(arr.dtype.newbyteorder("<"))
+    nm = name.encode() + b"\x00"
+    t, sp = _dtype_msg(arr.dtype), _space_msg(shape)
+    body = struct.pack("<BBHHH", 1, 0, len(nm), len(t), len(sp)) + _pad8(nm) + _pad8(t) + _pad8(sp) + arr.tobytes()
+    return _msg(0x0C, body)
+
+
+class _Writer:
+    def __init__(self, leaf_k):
+        self.buf = bytearray(96)                  # superblock (56) + root symbol-table entry (40), filled in at the end
+        self.leaf_k = leaf_k
+
+    def alloc(self, data, align=8):
+        self.buf += b"\x00" * (-len(self.buf) % align)
+        addr = len(self.buf)
+        self.buf += data
+        return addr
+
+    def header(self, messages):
+        body = b"".join(messages)
+        return self.alloc(struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body)) + body)
+
+    def dataset(self, arr, attrs):
+        shape = np.shape(arr)
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype.byteorder == ">":
+            arr = arr.astype(arr.dtype.newbyteorder("<"))
+        data = self.alloc(arr.tobytes()) if arr.size else _UNDEF
+        msgs = [_msg(0x01, _space_msg(shape)), _msg(0x03, _dtype_msg(arr.dtype), flags=1),
+                _msg(0x05, struct.pack("<BBBB", 2, 2, 2, 0)),                              # fill value v2: not defined
+                _msg(0x08, struct.pack("<BBQQ", 3, 1, data, arr.nbytes))]                  # contiguous layout v3
+        return self.header(msgs + [_attr_msg(k, v) for k, v in attrs.items()])
+
+    def group(self, children, attrs):
+        """children: {name: object header address}; returns the group's object header address"""
+        names = sorted(children, key=lambda s: s.encode())
+        if len(names) > 2 * self.leaf_k:
+            raise H5Error("group too large for the symbol-table node size")
+        heap = bytearray(8)                                   # offset 0: the empty string
+        offs = {}
+        for nm in names:
+            offs[nm] = len(heap)
+            heap += _pad8(nm.encode() + b"\x00")
+        free = len(heap)
+        heap += struct.pack("<QQ", 1, 16)                     # one free block: next = 1 (end of list), size 16
+        heap_data = self.alloc(bytes(heap))
+        heap_addr = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free, heap_data))
+        snod = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(names)))
+        for nm in names:
+            snod += struct.pack("<QQII16x", offs[nm], children[nm], 0, 0)
+        snod += b"\x00" * (8 + 2 * self.leaf_k * 40 - len(snod))
+        snod_addr = self.alloc(bytes(snod))
+        last = offs[names[-1]] if names else 0
+        tree = (b"TREE" + struct.pack("<BBHQQ", 0, 0, 1 if names else 0, _UNDEF, _UNDEF) +
+                struct.pack("<QQQ", 0, snod_addr, last))
+        tree += b"\x00" * (24 + (2 * 16 + 1) * 8 + 2 * 16 * 8 - len(tree))        # full node for internal K = 16
+        tree_addr = self.alloc(tree)
+        hdr = self.header([_msg(0x11, struct.pack("<QQ", tree_addr, heap_addr))] + [_attr_msg(k, v) for k, v in attrs.items()])
+        return hdr, tree_addr, heap_addr
+
+    def finish(self, root_hdr, root_tree, root_heap):
+        eof = len(self.buf)
+        sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self.leaf_k, 16, 0)
+        sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
+        sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", root_tree, root_heap)     # root entry, cached btree/heap
+        self.buf[:len(sb)] = sb
+        return bytes(self.buf)
+
+
+def write_tree(path, tree, attrs=None):
+    """tree: nested dict {name: ndarray | dict}; attrs: {"/path/to/object": {attr name: value}} ("/" = root)."""
+    attrs = attrs or {}
+
+    def max_children(node):
+        return max([len(node)] + [max_children(v) for v in node.values() if isinstance(v, dict)])
+    w = _Writer(max(4, (max_children(tree) + 1) // 2))
+
+    def emit(node, prefix):
+        kids = {}
+        for name, v in node.items():
+            p = prefix + "/" + name
+            kids[name] = emit(v, p)[0] if isinstance(v, dict) else w.dataset(v, attrs.get(p, {}))
+        return w.group(kids, attrs.get(prefix or "/", {}))
+    data = w.finish(*emit(tree, ""))
+    with open(path, "wb") as f:
+        f.write(data)
+    return path
+
+
+# model.layers order of the reference's ResidualCNN (model.py:58-145) as Keras 2.1.6 names them: load_weights matches
+# weights to layers by this order (keras/engine/topology.py load_weights_from_hdf5_group)
+def keras_layer_order():
+    names = ["input_1", "conv2d_1", "batch_normalization_1", "activation_1"]
+    act = 1
+    for b in range(9):
+        for j in range(3):
+            i = 2 + 3 * b + j
+            names += ["conv2d_%d" % i, "batch_normalization_%d" % i]
+            if j == 2:
+                names.append("add_%d" % (b + 1))
+            act += 1
+            names.append("activation_%d" % act)
+    names += ["conv2d_30", "conv2d_29", "batch_normalization_30", "batch_normalization_29", "activation_30", "activation_29",
+              "flatten_2", "flatten_1", "dense_1", "policy_head", "value_head"]
+    return names
+
+
+_PARAM_ORDER = {"conv2d": ["kernel", "bias"], "batch_normalization": ["gamma", "beta", "moving_mean", "moving_variance"],
+                "dense": ["kernel", "bias"], "policy_head": ["kernel", "bias"], "value_head": ["kernel", "bias"]}
+
+
+def write_weights(path, weights, keras_version="2.1.6", backend="tensorflow"):
+    """{'<layer>/<param>': array} -> a Keras `save_weights` file: /<layer>/<layer>/<param>:0 float32 datasets, root attribute
+    layer_names (model.layers order), per-layer attribute weight_names."""
+    tree, attrs = {}, {"/": {"layer_names": [n.encode() for n in keras_layer_order()], "backend": backend.encode(),
+                             "keras_version": keras_version.encode()}}
+    have = {k.split("/")[0] for k in weights}
+    for layer in keras_layer_order():
+        if layer in have:
+            kind = next(k for k in _PARAM_ORDER if layer.startswith(k))
+            params = [p for p in _PARAM_ORDER[kind] if "%s/%s" % (layer, p) in weights]
+            tree[layer] = {layer: {p + ":0": np.asarray(weights["%s/%s" % (layer, p)], dtype=np.float32) for p in params}}
+            attrs["/" + layer] = {"weight_names": [("%s/%s:0" % (layer, p)).encode() for p in params]}
+        else:
+            tree[layer] = {}
+            attrs["/" + layer] = {"weight_names": []}
+    return write_tree(path, tree, attrs)

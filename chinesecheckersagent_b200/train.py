@@ -92,27 +92,15 @@ class TrainableResidualCNN(nn.Module):
         return out
 
     def save_weights(self, path):
-        """`.npz` with the Keras tensor names (model.ResidualCNN.load_weights reads it); `.h5` needs h5py, which writes the
-        layout Keras' load_weights expects (model_weights-less `save_weights` file: one group per layer)."""
+        """Model.save_weights (model.py:38-41): `.h5` = a Keras `save_weights` file (h5lite.write_weights: /<layer>/<layer>/<param>:0
+        datasets, layer_names / weight_names attributes in model.layers order), `.npz` = the same tensors by name; both are what
+        model.ResidualCNN.load_weights reads."""
         w = self.keras_weights()
         if str(path).endswith(".npz"):
             np.savez(path, **w)
             return path
-        try:
-            import h5py
-        except ImportError as e:
-            raise RuntimeError("writing Keras .h5 weight files needs h5py (not installed here); save to .npz instead") from e
-        layers = sorted({k.split("/")[0] for k in w})
-        with h5py.File(path, "w") as f:
-            f.attrs["layer_names"] = [n.encode() for n in layers]
-            f.attrs["backend"], f.attrs["keras_version"] = b"tensorflow", b"2.1.6"
-            for n in layers:
-                g = f.create_group(n)
-                names = [k for k in w if k.split("/")[0] == n]
-                g.attrs["weight_names"] = [(k + ":0").encode() for k in names]
-                for k in names:
-                    g.create_dataset(k + ":0", data=w[k])
-        return path
+        from . import h5lite
+        return h5lite.write_weights(path, w)
 
     def kernel_l2(self):
         """sum of squares of every conv / dense kernel (Keras kernel_regularizer=l2(REG_CONST), model.py:60)"""

@@ -50,3 +50,22 @@ def convert_to_train_data(self_play_games):
             reward = -reward
             curr_player = PLAYER_ONE + PLAYER_TWO - curr_player
     return board_x, pi_y, v_y
+
+
+def save_train_data(board_x, pi_y, v_y, version, directory="generated-training-data/", prefix="data-for-iter-"):
+    """utils.py:48-56 — `<dir>/data-for-iter-<version>.h5` with datasets board_x (N,7,7,7), pi_y (N,294), v_y (N,)
+    (written with the package's own HDF5 writer; no h5py needed)."""
+    import os
+
+    from . import h5lite
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, "%s%s.h5" % (prefix, version))
+    to_np = lambda t: t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+    return h5lite.write_tree(path, {"board_x": to_np(board_x), "pi_y": to_np(pi_y), "v_y": to_np(v_y)})
+
+
+def load_train_data(path):
+    """(board_x, pi_y, v_y) from a data-for-iter file (train.py:321-352 reads them back with h5py)."""
+    from . import h5lite
+    t = h5lite.read_tree(path)
+    return t["/board_x"], t["/pi_y"], t["/v_y"]
