@@ -110,6 +110,18 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
                                "trees_per_gpu": MCTS_TREES, "sims_per_move": MCTS_SIMS, "ms_per_ply_iteration": t / reps * 1e3,
                                "net": "good_model.h5 (fixture copy), tcgen05 kernels, fp16 operands / fp32 accumulate",
                                "gpu_launches": eng.launches - l0}
+        # the same self-play step with four times the slots: the net runs at its large-batch rate and the tree kernels have
+        # 4x the warps to hide their latency chains behind (BASELINE names 4,096 trees/GPU; this is the throughput setting)
+        del sp
+        big = BatchedSelfPlay(eng, model.evaluate_states, n_slots=4 * MCTS_TREES, seed=DEFAULT_SEED, rank=rank, world=world,
+                              num_itr=MCTS_SIMS, max_iters=12)
+        for _ in range(7):
+            big.step()
+        barrier()
+        t = _timed(big.step, 2, world)
+        out["selfplay_net_16k_slots"] = {"metric": "mcts_sims_per_sec", "value": world * 4 * MCTS_TREES * MCTS_SIMS * 2 / t, "unit": "sims/s",
+                                         "trees_per_gpu": 4 * MCTS_TREES, "ms_per_ply_iteration": t / 2 * 1e3}
+        traj_src = big
         # net forward alone on a big batch
         planes = torch.randint(0, 7, (65536, 7, 7, 7), dtype=torch.uint8, device=eng.device)
         for kern in ("tc", "simt"):
@@ -123,10 +135,10 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
                                           "tflops": tf, "batch": 65536}
             if kern == "tc" and peak_tflops:
                 out["net_forward_tc"]["roofline"] = {"bound": "tensor", "achieved": tf / world, "peak": peak_tflops, "unit": "TFLOP/s",
-                                                     "frac": tf / world / peak_tflops, "kernel": "k_net_trunk_tc + k_policy_dense_tc"}
+                                                     "frac": tf / world / peak_tflops, "kernel": "k_net_trunk_tc4 + k_policy_dense_tc2"}
         model.set_kernel("tc")
         # trajectory all-gather (the only collective): time it when there is more than one rank
-        traj = sp.collect()
+        traj = traj_src.collect()
         if world > 1:
             all_gather_trajectories(traj)
             barrier()

@@ -32,7 +32,7 @@ def test_generate_train_reload_loop(tmp_path):
     with torch.no_grad():                               # float64 reference (cuDNN's fp32 convs default to TF32)
         logits, value = net.double()(x)
     p_ref = torch.softmax(logits, dim=1)
-    for kernel, bar in (("simt", 2e-5), ("tc", 5e-3)):      # tc bar: tests/test_gpu_net.py (16-bit operands)
+    for kernel, bar in (("simt", 2e-5), ("tc", 1e-2)):      # tc: 16-bit operands (precision itself is pinned in tests/test_gpu_net.py)
         infer.set_kernel(kernel)
         p, v = infer.predict_batch(x)
         assert (p - p_ref).abs().max().item() < bar, kernel
