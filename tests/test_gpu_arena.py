@@ -87,3 +87,28 @@ def test_model_beats_greedy_and_self_match_is_sane(model):
     assert ai + greedy + a["stopped"] + b["stopped"] == 96
     cur, best, draws = evaluate(model, model, num_games=24)
     assert cur + best + draws == 24
+
+
+def test_empty_batches_and_bad_arguments(eng):
+    """every new entry point: n = 0 is a no-op returning CCX_OK, malformed calls return CCX_ERR_ARG (never crash)"""
+    L, h = eng.L, eng.h
+    assert L.ccx_game_advance(h, 0, None, None, None, 1, 0, 1.0, 16, 0, None) == 0
+    assert L.ccx_greedy_generate(h, 0, None, 0, 1, 0, 0, 400, 43, None, None, None, 0, None, None, None, None) == 0
+    assert L.ccx_cand_to_pi(h, 0, None, None) == 0
+    ERR_ARG = L.ccx_game_advance(h, 4, None, None, None, 1, 0, 1.0, 16, 0, None)
+    assert ERR_ARG < 0
+    assert L.ccx_game_advance(h, 4, None, None, None, 1, 0, -1.0, 16, 0, None) == ERR_ARG          # tau must be positive
+    assert L.ccx_greedy_generate(h, 4, None, 0, 1, 0, 0, 400, 43, None, None, None, 0, None, None, None, None) == ERR_ARG
+    assert L.ccx_greedy_generate(h, 4, None, 0, 1, 0, 0, 0, 43, None, None, None, 0, None, None, None, None) == ERR_ARG
+    assert L.ccx_cand_to_pi(h, 3, None, None) == ERR_ARG
+    assert L.ccx_mcts_run_net(h, 0, 5, 3.5, None, 0, 0) in (0, ERR_ARG)       # ERR_ARG before any ccx_mcts_begin on this handle
+
+
+def test_single_game_arena_and_one_record_generator(model):
+    """smallest sizes: one arena game to the end, one generated game"""
+    from chinesecheckersagent_b200.arena import GREEDY, BatchedArena
+    from chinesecheckersagent_b200.data_generators import BatchedGreedyGenerator
+    res = BatchedArena(GREEDY, model, 1, seed=1, num_itr=20).play()
+    assert res["unfinished"] == 0 and res["p1_wins"] + res["p2_wins"] + res["stopped"] == 1
+    out = BatchedGreedyGenerator(model.eng, seed=2).generate(1)
+    assert out["lengths"].shape == (1,) and out["board_x"].shape[0] == int(out["lengths"][0]) > 10
