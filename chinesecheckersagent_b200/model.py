@@ -65,25 +65,39 @@ def _op_layout(Wt, fp16=False):
     return out
 
 
+def _with_bias_columns(Wt, bias, fp16):
+    """[N][K] -> [N][K + 16]: columns K, K+1 = the bias split into two 16-bit terms (hi = round16(b), lo = round16(b - hi)),
+    multiplied inside the kernel by a constant ones operand (csrc/ccx_net_tc.cu, bias MMA)."""
+    dt = torch.float16 if fp16 else torch.bfloat16
+    b = torch.from_numpy(np.asarray(bias, dtype=np.float64))
+    hi = b.to(torch.float32).to(dt).to(torch.float64)
+    lo = (b - hi).to(torch.float32).to(dt).to(torch.float64)
+    ext = np.zeros((Wt.shape[0], Wt.shape[1] + 16), dtype=np.float64)
+    ext[:, :Wt.shape[1]] = Wt
+    ext[:, Wt.shape[1]] = hi.numpy()
+    ext[:, Wt.shape[1] + 1] = lo.numpy()
+    return ext
+
+
 def pack_weights_tc(w, fp16=False):
-    """Keras tensors -> (bf16 operand blob as int16 array, fp32 bias blob) for ccx_net_load_tc
-    (layout: csrc/ccx_net_tc.cu header).  Every weight matrix is stored transposed ([N][K]) and BN-folded."""
+    """Keras tensors -> (16-bit operand blob as int16 array, fp32 blob) for ccx_net_load_tc (layout: csrc/ccx_net_tc.cu
+    header).  Every weight matrix is stored transposed ([N][K + 16], bias columns appended) and BN-folded."""
     ops, fl = [], []
 
     def folded(i):
         m, b = _fold(w, i)                       # (K, N), (N,)
         return m, b
     m, b = folded(1)                             # conv1: K 63 -> 64
-    ops.append(_op_layout(np.pad(m, ((0, 1), (0, 0))).T, fp16)); fl.append(b)
+    ops.append(_op_layout(_with_bias_columns(np.pad(m, ((0, 1), (0, 0))).T, b, fp16), fp16)); fl.append(b)
     mp, bp = folded(29)                          # policy conv (64,16)
     mv, bv = folded(30)                          # value conv (64,1)
     heads = np.zeros((64, 32)); heads[:, :16] = mp; heads[:, 16] = mv[:, 0]
     hb = np.zeros(32); hb[:16] = bp; hb[16] = bv[0]
-    ops.append(_op_layout(heads.T, fp16)); fl.append(hb)
+    ops.append(_op_layout(_with_bias_columns(heads.T, hb, fp16), fp16)); fl.append(hb)
     for blk in range(9):
         for i in (2 + 3 * blk, 3 + 3 * blk, 4 + 3 * blk):
             m, b = folded(i)
-            ops.append(_op_layout(m.T, fp16)); fl.append(b)
+            ops.append(_op_layout(_with_bias_columns(m.T, b, fp16), fp16)); fl.append(b)
     Wd = np.zeros((400, 320)); Wd[:, :294] = w["policy_head/kernel"]
     bd = np.zeros(320); bd[:294] = w["policy_head/bias"]
     for half in range(2):
