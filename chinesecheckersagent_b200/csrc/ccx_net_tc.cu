@@ -228,6 +228,16 @@ template <bool FP16> __device__ __forceinline__ uint32_t pack2(float a, float b)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// ReLU after the 16-bit pack: round(max(x, 0)) == max(round(x), 0) bit for bit (rounding is monotonic and keeps the sign),
+// and one packed max handles two values
+template <bool FP16> __device__ __forceinline__ uint32_t relu_pack2(float a, float b)
+{
+    uint32_t p = pack2<FP16>(a, b), r;
+    if (FP16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(p), "r"(0u));
+    else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(p), "r"(0u));
+    return r;
+}
+
 // cooperative 16-byte-granular global -> shared copy as one cp.async group (an empty group if bytes == 0)
 __device__ __forceinline__ void refill(uint32_t dst, const uint8_t *src, int bytes, int t)
 {
@@ -453,9 +463,8 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
             {
                 float v[16];
                 umma::tmem_ld16(trow + T_AO + h * 16, v);
-#pragma unroll
-                for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q], 0.f);
-                const uint4 o0 = pack8(v), o1 = pack8(v + 8);
+                const uint4 o0 = make_uint4(relu_pack2<FP16>(v[0], v[1]), relu_pack2<FP16>(v[2], v[3]), relu_pack2<FP16>(v[4], v[5]), relu_pack2<FP16>(v[6], v[7]));
+                const uint4 o1 = make_uint4(relu_pack2<FP16>(v[8], v[9]), relu_pack2<FP16>(v[10], v[11]), relu_pack2<FP16>(v[12], v[13]), relu_pack2<FP16>(v[14], v[15]));
                 if (live) {
                     // copy d serves kernel row dy = d - 1: output cell (y - dy, x) reads this cell, so the value goes to row r - 6*dy
 #pragma unroll
@@ -496,7 +505,7 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
                 uint32_t pk[8];
 #pragma unroll
                 for (int q = 0; q < 8; q++)
-                    pk[q] = pack2<FP16>(fmaxf(v[2 * q], 0.f), fmaxf(v[2 * q + 1], 0.f));
+                    pk[q] = relu_pack2<FP16>(v[2 * q], v[2 * q + 1]);
                 umma::tmem_st8(trow + T_XB + h * 8, pk);         // M2B: 32 channels = 16 columns
             }
             // C: 1x1 conv 32 -> 64 accumulated onto the residual (model.py:137-144): X += M2B * Wc, then bias + ReLU in place
