@@ -742,7 +742,10 @@ int ccx_mcts_run_net(ccx_handle *h, int64_t n, int32_t rounds, double cpuct, con
     static const bool timing = getenv("CCX_RUN_NET_TIMING") != nullptr;      // debug: per-kernel in-situ times of rounds 100..103
     cudaEvent_t ev[16];
     if (timing) for (auto &e : ev) cudaEventCreate(&e);
-    // round r: [r == 0: select+encode | r > 0: finish round r-1's leaf, then select+encode] -> net; one last finish at the end
+    // round r: [r == 0: select+encode | r > 0: finish round r-1's leaf, then select+encode] -> net; one last finish at the end.
+    // Tried and dropped (r01c): programmatic dependent launch for the three kernels of a round (prologues before
+    // griddepcontrol.wait, launch_dependents at kernel start) — 23.8 ms per 4,096-slot ply against 21.3 ms without, and
+    // 94 ms against 73 ms at 16,384 slots: early-scheduled dependent CTAs take SM slots from the producer's later waves.
     for (int r = 0; r < rounds; r++) {
         const bool tr = timing && r >= 100 && r < 104;
         if (tr) cudaEventRecord(ev[(r - 100) * 4 + 0], h->stream);
