@@ -15,7 +15,7 @@
 #include <cstdlib>
 
 #define FULL 0xFFFFFFFFu
-#define MCTS_WARPS_PER_BLOCK 4
+#define MCTS_WARPS_PER_BLOCK 2
 #define NODE_WORDS 6            // 5 state words + info word
 
 // info word of a node: edge_begin (32) | n_edges (16) | winner (8) | expanded (8)
@@ -516,10 +516,8 @@ __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_softmax_expand_backup(ccx_trees trees, int64_t n, const float *__restrict__ logits, const float *__restrict__ value,
                              const double *__restrict__ noise, int noise_stride, int noise_normalize, const uint8_t *__restrict__ jt)
 {
-    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
     __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
-    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
-    __syncthreads();
+    const uint8_t *sT = jt;          // one expansion per launch: the 6 KB jump table is read through L1 instead of staged per block
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (tree >= n) return;
@@ -535,11 +533,9 @@ k_mcts_round(ccx_trees trees, int64_t n, double cpuct, const float *__restrict__
              const double *__restrict__ noise, int noise_stride, int noise_normalize, uint8_t *__restrict__ planes,
              const uint8_t *__restrict__ jt)
 {
-    __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
     __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
     __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
-    for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
-    __syncthreads();
+    const uint8_t *sT = jt;          // one expansion per launch: the 6 KB jump table is read through L1 instead of staged per block
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (tree >= n) return;
