@@ -18,11 +18,17 @@
 #define MCTS_WARPS_PER_BLOCK 2
 #define NODE_WORDS 6            // 5 state words + info word
 
-// info word of a node: edge_begin (32) | n_edges (16) | winner (8) | expanded (8)
+// info word of a node: edge_begin (32) | n_edges (8) | spare (16) | winner (4) | expanded (4).  The copy the descent reads lives
+// on the parent's edge (eInfo) for every node but the root.
+// (Tried and dropped, r01c: keeping N_sum in the spare bits, maintained by the backup, so that sqrt(N_sum) is ready before
+// the edge statistics arrive — self-play +0.8 %, stub search -3 %: the extra read-modify-write per level costs what it saves.)
 __device__ __forceinline__ u64 make_info(u32 eb, u32 ne, u32 winner, u32 expanded)
 {
-    return (u64)eb | ((u64)ne << 32) | ((u64)winner << 48) | ((u64)expanded << 56);
+    return (u64)eb | ((u64)(ne & 0xFF) << 32) | ((u64)(winner & 0xF) << 56) | ((u64)(expanded & 0xF) << 60);
 }
+__device__ __forceinline__ int info_ne(u64 info) { return (int)((info >> 32) & 0xFF); }
+__device__ __forceinline__ int info_eb(u64 info) { return (int)(u32)info; }
+__device__ __forceinline__ int info_winner(u64 info) { return (int)((info >> 56) & 0xF); }
 
 struct ccx_trees {
     int64_t cap_trees = 0;
@@ -147,11 +153,11 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
     int node = 0, depth = 0;
     u64 info = tv.node[5];
     for (;;) {
-        int winner = (int)((info >> 48) & 0xFF);
-        int ne = (int)((info >> 32) & 0xFFFF);
+        int winner = info_winner(info);
+        int ne = info_ne(info);
         if (winner) { leaf_kind = LEAF_TERMINAL; break; }
         if (ne == 0) { leaf_kind = LEAF_EVAL; break; }           // Node.isLeaf()
-        int eb = (int)(u32)info;
+        int eb = info_eb(info);
         // one pass over the edges: N, W, P of edges lane, lane+32, ... stay in registers (<= 126 legal moves)
         u32 Nr[4]; double Wr[4], Pr[4];
         u32 nsum = 0;
@@ -178,12 +184,15 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
                 if (QU > best) { best = QU; besti = j; }                                        // :65-67
             }
         }
-        // warp arg-max, ties to the smallest edge index (= first maximal edge in list order)
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            double ob = __shfl_xor_sync(FULL, best, off);
-            int oi = __shfl_xor_sync(FULL, besti, off);
-            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        // warp arg-max, ties to the smallest edge index (= first maximal edge in list order): order-preserving 64-bit key of
+        // the double (no NaNs here; + 0.0 folds a -0.0 into +0.0 so that equal values have equal keys), three warp reductions
+        {
+            u64 u = (u64)__double_as_longlong(best + 0.0);
+            u64 key = (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+            u32 hi = (u32)(key >> 32), lo = (u32)key;
+            u32 mhi = __reduce_max_sync(FULL, hi);
+            u32 mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+            besti = (int)__reduce_min_sync(FULL, (hi == mhi && lo == mlo) ? (u32)besti : 0x7FFFFFFFu);
         }
         int e = eb + besti;
         if (lane == 0 && depth < tv.path_max) tv.path[depth] = e;
@@ -317,7 +326,7 @@ __device__ __forceinline__ void eval_expand_backup(const TreeView &tv, int lane,
 __device__ __forceinline__ void mix_root_noise(const TreeView &tv, int lane, const double *noise, bool normalize = false)
 {
     u64 info = tv.node[5];
-    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    int ne = info_ne(info), eb = info_eb(info);
     double scale = 1.0;
     if (normalize) {                      // raw gamma draws -> Dirichlet sample over the ne root edges
         double sum = 0.0;
@@ -363,7 +372,7 @@ k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
     init_tree(tv, lane, roots, n, tree, -1);
-    if (pre_expand && ((tv.node[5] >> 48) & 0xFF) == 0) {                    // selfplay.py:117
+    if (pre_expand && info_winner(tv.node[5]) == 0) {                    // selfplay.py:117
         eval_expand_backup<EVAL>(tv, lane, 0, 0, sT);
         if (noise) mix_root_noise(tv, lane, noise + tree * noise_stride);
     }
@@ -572,7 +581,7 @@ k_mcts_finalize(ccx_trees trees, int64_t n, double inv_tau, u32 *__restrict__ vi
     }
     __syncwarp();
     u64 info = tv.node[5];
-    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    int ne = info_ne(info), eb = info_eb(info);
     double sum = 0.0;
     for (int j = lane; j < ne; j += 32) {
         u32 N = tv.eN[eb + j];
@@ -608,7 +617,7 @@ k_mcts_get_root(ccx_trees trees, int64_t n, int stride, int32_t *__restrict__ n_
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
     u64 info = tv.node[5];
-    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    int ne = info_ne(info), eb = info_eb(info);
     if (lane == 0) n_edges[tree] = ne;
     for (int j = lane; j < ne && j < stride; j += 32) {
         moves[tree * stride + j] = tv.eMove[eb + j];
@@ -626,7 +635,7 @@ k_mcts_set_root_priors(ccx_trees trees, int64_t n, int stride, const double *__r
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
     u64 info = tv.node[5];
-    int ne = (int)((info >> 32) & 0xFFFF), eb = (int)(u32)info;
+    int ne = info_ne(info), eb = info_eb(info);
     for (int j = lane; j < ne && j < stride; j += 32) tv.eP[eb + j] = P[tree * stride + j];
 }
 
