@@ -35,17 +35,19 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
     env = BatchedEnv(MCTS_TREES, engine=eng, seed=DEFAULT_SEED, game_id0=rank * MCTS_TREES)
     env.step_random(6)                                   # roots = start advanced by 6 random plies
     mcts = BatchedMCTS(eng, num_itr=MCTS_SIMS)
-    res = mcts.search(env.state)                         # warm-up + pool allocation
+    for _ in range(3):                                   # warm-up: pool allocation, and torch's caching allocator gets the
+        res = mcts.search(env.state)                     # output blocks a steady-state caller reuses (no cudaMalloc while timing)
+    stats = dict(overflowed=int((res["n_nodes"] < 0).sum().item()), mean_nodes=float(res["n_nodes"].float().mean().item()))
+    del res
     barrier()
     l0 = eng.launches
-    reps = 5
+    reps = 10
     t = _timed(lambda: mcts.search(env.state), reps, world)
     sims = world * MCTS_TREES * MCTS_SIMS * reps
     out["mcts_stub"] = {"metric": "mcts_sims_per_sec", "value": sims / t, "unit": "sims/s", "trees_per_gpu": MCTS_TREES,
                         "sims_per_move": MCTS_SIMS, "ms_per_search": t / reps * 1e3, "evaluator": "uniform prior 1/294, v=0",
                         "gpu_launches": eng.launches - l0,
-                        "overflowed_trees": int((res["n_nodes"] < 0).sum().item()),
-                        "mean_nodes_per_tree": float(res["n_nodes"].float().mean().item())}
+                        "overflowed_trees": stats["overflowed"], "mean_nodes_per_tree": stats["mean_nodes"]}
     if peak_gbs:
         ach = MCTS_BYTES_PER_SIM * MCTS_TREES * MCTS_SIMS / (t / reps) / 1e9
         out["mcts_stub"]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
@@ -69,14 +71,15 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
     # ---- §8f f3: greedy supervised-data generator (data_generators.py), records + pi + planes on the device ---------
     from .data_generators import BatchedGreedyGenerator
     gen = BatchedGreedyGenerator(eng, seed=DEFAULT_SEED, rank=rank, world=world)
-    gen.generate(GREEDY_GAMES)
+    n_rec = 0
+    for _ in range(2):                                   # warm-up (second call: the caching allocator already holds the output blocks)
+        n_rec = int(gen.generate(GREEDY_GAMES)["v_y"].shape[0])
     barrier()
-    made = {}
-    t = _timed(lambda: made.update(gen.generate(GREEDY_GAMES)), 2, world)
-    out["greedy_datagen"] = {"metric": "games_per_sec", "value": world * GREEDY_GAMES * 2 / t, "unit": "games/s",
-                             "records_per_sec": world * int(made["v_y"].shape[0]) * 2 / t, "games_per_gpu": GREEDY_GAMES,
+    t = _timed(lambda: gen.generate(GREEDY_GAMES), 3, world)
+    out["greedy_datagen"] = {"metric": "games_per_sec", "value": world * GREEDY_GAMES * 3 / t, "unit": "games/s",
+                             "records_per_sec_approx": world * n_rec * 3 / t, "games_per_gpu": GREEDY_GAMES,
                              "outputs": "board_x u8 (M,7,7,7), pi_y f32 (M,294), v_y i8 (M,)"}
-    del made, gen
+    del gen
     # ---- plane encoder (utils.to_model_input) straight into a bf16 NHWC tensor ----------------------------
     eenv = BatchedEnv(1 << 20, engine=eng, seed=DEFAULT_SEED)
     eenv.step_random(8)

@@ -9,9 +9,9 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_env.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_env.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4400 -c 1200 --csv --log-file gpurun_out/launches_sp.csv python scripts/selfplay_bench.py 1 > gpurun_out/ncu_sp.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3300 -c 900 --csv --log-file gpurun_out/launches_sp.csv python scripts/selfplay_bench.py 1 > gpurun_out/ncu_sp.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step_random -s 3 -c 1 -o gpurun_out/prof_step_random python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_p1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mcts_search -c 1 -o gpurun_out/prof_mcts_search python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_p2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_net_trunk|k_policy_dense" -s 6 -c 2 -o gpurun_out/prof_net python scripts/net_bench.py 1 > gpurun_out/ncu_p3.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_mcts_round" -s 1500 -c 1 -o gpurun_out/prof_tree python scripts/selfplay_bench.py 1 > gpurun_out/ncu_p4.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_mcts_round" -s 1320 -c 1 -o gpurun_out/prof_tree python scripts/selfplay_bench.py 1 > gpurun_out/ncu_p4.log 2>&1
 ls -la gpurun_out
