@@ -36,6 +36,7 @@ struct ccx_trees {
     u64 *node = nullptr;        // [T][NPT][NODE_WORDS]
     u32 *eN = nullptr;          // [T][EPT]
     double *eW = nullptr, *eP = nullptr;
+    double *eQ = nullptr;       // W / N as of the last backup (MCTS.py:89,118 store Q the same way): the descent divides once per edge, not twice
     int32_t *eChild = nullptr;  // node index inside the tree or -1
     u64 *eInfo = nullptr;       // [T][EPT] copy of the child node's info word (valid once eChild >= 0): the descent reads it
                                 // together with eChild, so a tree level costs two dependent memory round trips, not four
@@ -46,7 +47,7 @@ struct ccx_trees {
 };
 
 struct TreeView {
-    u64 *node; u32 *eN; double *eW; double *eP; int32_t *eChild; u64 *eInfo; uint16_t *eMove; int32_t *path; int32_t *meta;
+    u64 *node; u32 *eN; double *eW; double *eP; double *eQ; int32_t *eChild; u64 *eInfo; uint16_t *eMove; int32_t *path; int32_t *meta;
     int32_t npt, ept, path_max;
 };
 
@@ -57,6 +58,7 @@ __device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
     v.eN = t.eN + tree * t.edges_per_tree;
     v.eW = t.eW + tree * t.edges_per_tree;
     v.eP = t.eP + tree * t.edges_per_tree;
+    v.eQ = t.eQ + tree * t.edges_per_tree;
     v.eChild = t.eChild + tree * t.edges_per_tree;
     v.eInfo = t.eInfo + tree * t.edges_per_tree;
     v.eMove = t.eMove + tree * t.edges_per_tree;
@@ -148,6 +150,11 @@ __device__ __forceinline__ u64 leaf_hash(const Game &g, int lane)
 // ---- select (MCTS.moveToLeaf, MCTS.py:49-76) ---------------------------------------------------------
 // Returns the leaf node index (materialising it if this is its first visit) and leaves the path in
 // tv.path / path_len.  leaf_kind: LEAF_EVAL (needs evaluation + expansion), LEAF_TERMINAL (winner != 0).
+// PREFETCH: fetch the child index and child info word of EVERY edge together with the edge statistics, so that a tree level
+// is ONE dependent memory round trip (the chosen edge's pair comes out of a shuffle).  Pays off for the deep, narrow trees a
+// real net produces (round-based kernels: -1.9 % per self-play ply); costs bandwidth on the wide, shallow trees of the
+// uniform-prior stub (persistent kernel: -19 %), which therefore reads the pair after the arg-max.
+template <bool PREFETCH>
 __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double cpuct, int &path_len, int &leaf_kind)
 {
     int node = 0, depth = 0;
@@ -159,14 +166,18 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
         if (ne == 0) { leaf_kind = LEAF_EVAL; break; }           // Node.isLeaf()
         int eb = info_eb(info);
         // one pass over the edges: N, W, P of edges lane, lane+32, ... stay in registers (<= 126 legal moves)
-        u32 Nr[4]; double Wr[4], Pr[4];
+        u32 Nr[4]; double Wr[4], Pr[4]; int Cr[4]; u64 Ir[4];
         u32 nsum = 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             int j = lane + 32 * c;
             bool in = j < ne;
+            if (PREFETCH) {
+                Cr[c] = in ? tv.eChild[eb + j] : -1;
+                Ir[c] = in ? tv.eInfo[eb + j] : 0ULL;
+            }
             Nr[c] = in ? tv.eN[eb + j] : 0u;
-            Wr[c] = in ? tv.eW[eb + j] : 0.0;
+            Wr[c] = in ? tv.eQ[eb + j] : 0.0;                    // Q = W / N, stored by the backup
             Pr[c] = in ? tv.eP[eb + j] : 0.0;
             nsum += Nr[c];
         }
@@ -178,7 +189,7 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
             int j = lane + 32 * c;
             if (j < ne) {
                 u32 N = Nr[c];
-                double Q = N ? __ddiv_rn(Wr[c], (double)N) : 0.0;                                  // MCTS.py:89,118
+                double Q = Wr[c];                                                               // MCTS.py:89,118
                 double U = __ddiv_rn(__dmul_rn(__dmul_rn(cpuct, Pr[c]), sq), __dadd_rn(1.0, (double)N));   // :62
                 double QU = __dadd_rn(Q, U);                                                    // :63
                 if (QU > best) { best = QU; besti = j; }                                        // :65-67
@@ -197,8 +208,15 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
         int e = eb + besti;
         if (lane == 0 && depth < tv.path_max) tv.path[depth] = e;
         depth++;
-        int child = tv.eChild[e];
-        u64 cinfo = tv.eInfo[e];                                 // same round trip as eChild; meaningful iff child >= 0
+        int child; u64 cinfo;                                    // cinfo is meaningful iff child >= 0
+        if (PREFETCH) {
+            const int chunk = besti >> 5, src = besti & 31;
+            child = __shfl_sync(FULL, chunk == 0 ? Cr[0] : chunk == 1 ? Cr[1] : chunk == 2 ? Cr[2] : Cr[3], src);
+            cinfo = shfl64(chunk == 0 ? Ir[0] : chunk == 1 ? Ir[1] : chunk == 2 ? Ir[2] : Ir[3], src);
+        } else {
+            child = tv.eChild[e];
+            cinfo = tv.eInfo[e];
+        }
         if (child < 0) {
             // first visit: materialise the child state = Board.place on a copy (MCTS.py:104-105)
             int nn = tv.meta[META_NNODES];
@@ -236,8 +254,11 @@ __device__ __forceinline__ void backup(const TreeView &tv, int lane, int path_le
         bool same = ((path_len - d) & 1) == 0;                   // edge.currPlayer == leafNode.currPlayer
         double delta = terminal ? (same ? -1.0 : 1.0)            // REWARD['win'] * direction
                                 : __dmul_rn(v, same ? 1.0 : -1.0);
-        tv.eN[e] += 1;
-        tv.eW[e] = __dadd_rn(tv.eW[e], delta);
+        u32 N = tv.eN[e] + 1;
+        double W = __dadd_rn(tv.eW[e], delta);
+        tv.eN[e] = N;
+        tv.eW[e] = W;
+        tv.eQ[e] = __ddiv_rn(W, (double)N);                       // edge.stats['Q'] = W / N
     }
 }
 
@@ -278,7 +299,7 @@ __device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int no
         for (int q = 0; q < 6; q++) if (k == q) { m = dest[q]; base = pre[q]; }
         int to = select64(m, (u32)(j - base));
         int idx = k * 49 + (to >> 3) * 7 + (to & 7);             // utils.encode_checker_index
-        tv.eN[eb + j] = 0; tv.eW[eb + j] = 0.0; tv.eP[eb + j] = prior(idx);     // MCTS.py:32-37,108
+        tv.eN[eb + j] = 0; tv.eW[eb + j] = 0.0; tv.eQ[eb + j] = 0.0; tv.eP[eb + j] = prior(idx);     // MCTS.py:32-37,108
         tv.eChild[eb + j] = -1;
         tv.eMove[eb + j] = (uint16_t)((k << 8) | to);
     }
@@ -378,7 +399,7 @@ k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num
     }
     for (int it = 0; it < num_itr; it++) {                                   // MCTS.py:123-125
         int path_len, kind;
-        int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
+        int leaf = select_leaf<false>(tv, lane, cpuct, path_len, kind);
         __syncwarp();
         if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
         else if (kind == LEAF_EVAL) eval_expand_backup<EVAL>(tv, lane, leaf, path_len, sT);
@@ -408,7 +429,7 @@ k_mcts_select(ccx_trees trees, int64_t n, double cpuct, u64 *__restrict__ leaf_s
         return;
     }
     int path_len, kind;
-    int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
+    int leaf = select_leaf<true>(tv, lane, cpuct, path_len, kind);
     __syncwarp();
     if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
     if (lane < 5) leaf_state[lane * n + tree] = tv.node[(int64_t)leaf * NODE_WORDS + lane];
@@ -450,7 +471,7 @@ __device__ __forceinline__ void do_select_encode(const TreeView &tv, int lane, d
         reset_start(g);
     } else {
         int path_len, kind;
-        int leaf = select_leaf(tv, lane, cpuct, path_len, kind);
+        int leaf = select_leaf<true>(tv, lane, cpuct, path_len, kind);
         __syncwarp();
         if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
         if (lane == 0) { tv.meta[META_PATHLEN] = path_len; tv.meta[META_LEAF] = leaf; tv.meta[META_LEAFKIND] = kind; }
@@ -645,7 +666,7 @@ void ccx_trees_free(ccx_handle *h)
 {
     ccx_trees *t = h->trees;
     if (!t) return;
-    void *ptrs[] = {t->node, t->eN, t->eW, t->eP, t->eChild, t->eInfo, t->eMove, t->path, t->tree_meta};
+    void *ptrs[] = {t->node, t->eN, t->eW, t->eP, t->eQ, t->eChild, t->eInfo, t->eMove, t->path, t->tree_meta};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete t;
     h->trees = nullptr;
@@ -668,12 +689,13 @@ static int trees_reserve(ccx_handle *h, int64_t n, int32_t num_itr, int32_t edge
     CCX_CUDA(h, cudaMalloc(&t->eN, T * ept * 4));
     CCX_CUDA(h, cudaMalloc(&t->eW, T * ept * 8));
     CCX_CUDA(h, cudaMalloc(&t->eP, T * ept * 8));
+    CCX_CUDA(h, cudaMalloc(&t->eQ, T * ept * 8));
     CCX_CUDA(h, cudaMalloc(&t->eChild, T * ept * 4));
     CCX_CUDA(h, cudaMalloc(&t->eInfo, T * ept * 8));
     CCX_CUDA(h, cudaMalloc(&t->eMove, T * ept * 2));
     CCX_CUDA(h, cudaMalloc(&t->path, T * pm * 4));
     CCX_CUDA(h, cudaMalloc(&t->tree_meta, T * 8 * 4));
-    t->bytes = T * ((size_t)npt * NODE_WORDS * 8 + (size_t)ept * 34 + (size_t)pm * 4 + 32);
+    t->bytes = T * ((size_t)npt * NODE_WORDS * 8 + (size_t)ept * 42 + (size_t)pm * 4 + 32);
     return CCX_OK;
 }
 
