@@ -125,6 +125,23 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
         out["selfplay_net_16k_slots"] = {"metric": "mcts_sims_per_sec", "value": world * 4 * MCTS_TREES * MCTS_SIMS * 2 / t, "unit": "sims/s",
                                          "trees_per_gpu": 4 * MCTS_TREES, "ms_per_ply_iteration": t / 2 * 1e3}
         traj_src = big
+        # the reference-facing drop-in surface, one game at a time: AiPlayer.decide_move's MCTS(Node(Board()), model).search()
+        # (player.py:157-158) through the Python mirror -- what a user gets by only swapping the imports
+        from .board import Board
+        from .MCTS import MCTS, Node
+        import time
+        def one_decision():
+            return MCTS(Node(Board(engine=eng), 1), model, num_itr=MCTS_SIMS).search()
+        one_decision()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            one_decision()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        out["dropin_single_game_search"] = {"metric": "ms_per_move_decision", "value": dt * 1e3, "unit": "ms", "sims_per_sec": MCTS_SIMS / dt,
+                                            "api": "MCTS(Node(Board(), 1), ResidualCNN).search(), batch of one tree",
+                                            "reference_cpu": "~63 sims/s/core with a torch-CPU restatement of the net (BASELINE.md §2)"}
         # net forward alone on a big batch
         planes = torch.randint(0, 7, (65536, 7, 7, 7), dtype=torch.uint8, device=eng.device)
         for kern in ("tc", "simt"):
