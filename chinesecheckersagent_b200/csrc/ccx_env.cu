@@ -464,6 +464,9 @@ int ccx_destroy(ccx_handle *h)
     ccx_scratch *s[] = {&h->d_state, &h->d_aux0, &h->d_aux1, &h->d_aux2};
     for (auto *p : s) if (p->ptr) cudaFree(p->ptr);
     if (h->jump_table) cudaFree(h->jump_table);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
     return CCX_OK;
 }

@@ -28,6 +28,9 @@ struct ccx_handle {
     ccx_net_tc *net_tc = nullptr;
     uint8_t *jump_table = nullptr;   // CCX_JT_BYTES, device: ray-jump lookup table (ccx_device.cuh)
     int net_mode = 0;           // 0 = fp32 SIMT kernel, 1 = bf16 tcgen05 kernels (ccx_net_set_mode)
+    // second stream + fork/join events of the two-half round pipeline (ccx_mcts_run_net), created on first use
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 static inline int ccx_fail(ccx_handle *h, cudaError_t e)
@@ -64,6 +67,9 @@ static inline int ccx_reserve(ccx_handle *h, ccx_scratch &s, size_t bytes)
 // the active mode (ccx_net_set_mode) — used by ccx_net_eval and by the fused MCTS round loop (ccx_mcts_run_net)
 int ccx_net_scratch(ccx_handle *h, int64_t n, uint8_t **planes, float **logits, float **value);
 int ccx_net_forward_active(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value);
+// tensor-core forward on an explicit stream, rows [row0, row0 + n) of the evaluator scratch (capacity reserved by the caller)
+int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64_t row0, int64_t n, const uint8_t *planes, float *logits,
+                          float *value);
 
 // sub-module teardown hooks (defined where the sub-module lives)
 void ccx_net_free(ccx_handle *h);

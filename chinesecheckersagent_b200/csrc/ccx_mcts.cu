@@ -499,12 +499,12 @@ __device__ __forceinline__ void do_select_encode(const TreeView &tv, int lane, d
 }
 
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
-k_mcts_select_encode(ccx_trees trees, int64_t n, double cpuct, uint8_t *__restrict__ planes)
+k_mcts_select_encode(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, uint8_t *__restrict__ planes)
 {
     __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
-    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int64_t tree = tree0 + (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);      // trees [tree0, tree0 + n)
     int lane = threadIdx.x & 31;
-    if (tree >= n) return;
+    if (tree >= tree0 + n) return;
     TreeView tv = tree_view(trees, tree);
     do_select_encode(tv, lane, cpuct, sP[threadIdx.x >> 5], planes + tree * 343);
 }
@@ -543,14 +543,14 @@ __device__ __forceinline__ void do_softmax_expand_backup(const TreeView &tv, int
 }
 
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
-k_mcts_softmax_expand_backup(ccx_trees trees, int64_t n, const float *__restrict__ logits, const float *__restrict__ value,
+k_mcts_softmax_expand_backup(ccx_trees trees, int64_t tree0, int64_t n, const float *__restrict__ logits, const float *__restrict__ value,
                              const double *__restrict__ noise, int noise_stride, int noise_normalize, const uint8_t *__restrict__ jt)
 {
     __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
     const uint8_t *sT = jt;          // one expansion per launch: the 6 KB jump table is read through L1 instead of staged per block
-    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int64_t tree = tree0 + (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
-    if (tree >= n) return;
+    if (tree >= tree0 + n) return;
     TreeView tv = tree_view(trees, tree);
     do_softmax_expand_backup(tv, lane, logits + tree * 294, (double)value[tree], noise ? noise + tree * noise_stride : nullptr,
                              noise_normalize, sPr[threadIdx.x >> 5], sT);
@@ -559,16 +559,16 @@ k_mcts_softmax_expand_backup(ccx_trees trees, int64_t n, const float *__restrict
 // one launch per round in steady state: finish the previous round's leaf (softmax + expand + backup), then select and encode
 // the next one — the same warp owns the tree in both halves, so the halves need no grid-wide ordering between them
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
-k_mcts_round(ccx_trees trees, int64_t n, double cpuct, const float *__restrict__ logits, const float *__restrict__ value,
+k_mcts_round(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, const float *__restrict__ logits, const float *__restrict__ value,
              const double *__restrict__ noise, int noise_stride, int noise_normalize, uint8_t *__restrict__ planes,
              const uint8_t *__restrict__ jt)
 {
     __shared__ double sPr[MCTS_WARPS_PER_BLOCK][296];
     __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
     const uint8_t *sT = jt;          // one expansion per launch: the 6 KB jump table is read through L1 instead of staged per block
-    int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int64_t tree = tree0 + (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
-    if (tree >= n) return;
+    if (tree >= tree0 + n) return;
     TreeView tv = tree_view(trees, tree);
     do_softmax_expand_backup(tv, lane, logits + tree * 294, (double)value[tree], noise ? noise + tree * noise_stride : nullptr,
                              noise_normalize, sPr[threadIdx.x >> 5], sT);
@@ -765,40 +765,59 @@ int ccx_mcts_run_net(ccx_handle *h, int64_t n, int32_t rounds, double cpuct, con
     uint8_t *planes; float *logits, *value;
     int rc;
     if ((rc = ccx_net_scratch(h, n, &planes, &logits, &value))) return rc;
-    const unsigned grid = tree_blocks(n);
-    static const bool timing = getenv("CCX_RUN_NET_TIMING") != nullptr;      // debug: per-kernel in-situ times of rounds 100..103
-    cudaEvent_t ev[16];
-    if (timing) for (auto &e : ev) cudaEventCreate(&e);
+    // Two halves of the batch run as two independent round pipelines on two streams: trees are independent, and the
+    // low-occupancy stretches of one half (the tail of its tree kernel = the deepest trees, the last tile of its trunk kernel)
+    // are filled by the other half's kernels.  Same trees as the single-stream order, bit for bit.
+    static const bool no_split = getenv("CCX_NO_SPLIT") != nullptr;
+    const bool split = !no_split && h->net_mode == 1 && n >= 8192;     // measured: 16,384 slots 65.1 -> 62.2 ms per ply; no gain at 4,096
+    int64_t part_n[2] = {split ? (n / 2) & ~(int64_t)3 : n, 0};
+    part_n[1] = n - part_n[0];
+    cudaStream_t streams[2] = {h->stream, h->stream};
+    if (split) {
+        if (!h->stream2) {
+            CCX_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+            CCX_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            CCX_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        streams[1] = h->stream2;
+        CCX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        CCX_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    }
+    // make sure the evaluator's internal scratch covers the whole batch before two streams share it
+    if (h->net_mode == 1 && (rc = ccx_net_forward_tc_on(h, h->stream, n, 0, 0, planes, logits, value))) return rc;
+    const int parts = split ? 2 : 1;
     // round r: [r == 0: select+encode | r > 0: finish round r-1's leaf, then select+encode] -> net; one last finish at the end.
     // Tried and dropped (r01c): programmatic dependent launch for the three kernels of a round (prologues before
     // griddepcontrol.wait, launch_dependents at kernel start) — 23.8 ms per 4,096-slot ply against 21.3 ms without, and
     // 94 ms against 73 ms at 16,384 slots: early-scheduled dependent CTAs take SM slots from the producer's later waves.
-    for (int r = 0; r < rounds; r++) {
-        const bool tr = timing && r >= 100 && r < 104;
-        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 0], h->stream);
-        if (r == 0)
-            k_mcts_select_encode<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, planes);
-        else
-            k_mcts_round<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, logits, value, r == 1 ? root_noise : nullptr,
-                                                                            noise_stride, noise_normalize, planes, h->jump_table);
-        CCX_LAUNCHED(h);
-        if (tr) cudaEventRecord(ev[(r - 100) * 4 + 1], h->stream);
-        if ((rc = ccx_net_forward_active(h, n, planes, logits, value))) return rc;
-        if (tr) { cudaEventRecord(ev[(r - 100) * 4 + 2], h->stream); cudaEventRecord(ev[(r - 100) * 4 + 3], h->stream); }
-    }
-    k_mcts_softmax_expand_backup<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, logits, value,
-                                                                                    rounds == 1 ? root_noise : nullptr, noise_stride,
-                                                                                    noise_normalize, h->jump_table);
-    CCX_LAUNCHED(h);
-    if (timing && rounds >= 104) {
-        cudaStreamSynchronize(h->stream);
-        for (int i = 0; i + 1 < 16; i++) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-            fprintf(stderr, "run_net round %d seg %d: %.2f us\n", 100 + i / 4, i % 4, ms * 1e3f);
+    for (int r = 0; r <= rounds; r++) {
+        for (int q = 0; q < parts; q++) {
+            const int64_t t0 = q ? part_n[0] : 0, nq = part_n[q];
+            if (nq == 0) continue;
+            cudaStream_t st = streams[q];
+            const unsigned grid = tree_blocks(nq);
+            const double *nz = root_noise;
+            if (r == 0)
+                k_mcts_select_encode<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, planes);
+            else if (r < rounds)
+                k_mcts_round<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, logits, value, r == 1 ? nz : nullptr,
+                                                                         noise_stride, noise_normalize, planes, h->jump_table);
+            else
+                k_mcts_softmax_expand_backup<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, logits, value,
+                                                                                         rounds == 1 ? nz : nullptr, noise_stride,
+                                                                                         noise_normalize, h->jump_table);
+            CCX_LAUNCHED(h);
+            if (r < rounds) {
+                if (h->net_mode == 1) rc = ccx_net_forward_tc_on(h, st, n, t0, nq, planes + t0 * 343, logits + t0 * 294, value + t0);
+                else rc = ccx_net_forward_active(h, nq, planes + t0 * 343, logits + t0 * 294, value + t0);
+                if (rc) return rc;
+            }
         }
     }
-    if (timing) for (auto &e : ev) cudaEventDestroy(e);
+    if (split) {
+        CCX_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
+        CCX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    }
     return CCX_OK;
 }
 

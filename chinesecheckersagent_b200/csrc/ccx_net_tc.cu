@@ -708,29 +708,40 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
 int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value)
 {
     if (!h || n < 0 || (n && (!planes || !logits || !value))) return CCX_ERR_ARG;
+    if (n == 0) return tc_of(h, false) && tc_of(h, false)->wb ? CCX_OK : CCX_ERR_STATE;
+    return ccx_net_forward_tc_on(h, h->stream, n, 0, n, planes, logits, value);
+}
+
+}  // extern "C"
+
+// planes / logits / value point at the FIRST of the n rows to evaluate; row0 only selects the rows of the internal
+// policy-conv scratch (so two halves of a batch can be in flight on two streams)
+int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64_t row0, int64_t n, const uint8_t *planes, float *logits,
+                          float *value)
+{
     ccx_net_tc *tc = tc_of(h, false);
     if (!tc || !tc->wb) return CCX_ERR_STATE;
-    if (n == 0) return CCX_OK;
-    if (tc->cap < n) {
+    if (tc->cap < cap) {
+        CCX_CUDA(h, cudaDeviceSynchronize());          // another stream may still read the old scratch
         if (tc->polc) CCX_CUDA(h, cudaFree(tc->polc));
         tc->polc = nullptr; tc->cap = 0;
-        CCX_CUDA(h, cudaMalloc(&tc->polc, sizeof(__nv_bfloat16) * 400 * (size_t)n));
-        tc->cap = n;
+        CCX_CUDA(h, cudaMalloc(&tc->polc, sizeof(__nv_bfloat16) * 400 * (size_t)cap));
+        tc->cap = cap;
     }
+    if (n == 0) return CCX_OK;                         // (a call with n = 0 only reserves the scratch)
+    __nv_bfloat16 *polc = tc->polc + row0 * 400;
     {
         int64_t tiles = (n + tc4::POS - 1) / tc4::POS;
         unsigned grid = (unsigned)(tiles < 3 * h->num_sms ? tiles : 3 * h->num_sms);     // three resident CTAs per SM
-        if (tc->fp16) k_net_trunk_tc4<true><<<grid, tc4::THREADS, tc4::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
-        else k_net_trunk_tc4<false><<<grid, tc4::THREADS, tc4::S_TOTAL, h->stream>>>(tc->wb, tc->fb, planes, n, tc->polc, value);
+        if (tc->fp16) k_net_trunk_tc4<true><<<grid, tc4::THREADS, tc4::S_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
+        else k_net_trunk_tc4<false><<<grid, tc4::THREADS, tc4::S_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
     }
     CCX_LAUNCHED(h);
     {
         dim3 g2((unsigned)((n + 127) / 128), 4);
-        if (tc->fp16) k_policy_dense_tc2<true><<<g2, 128, pd2::S_TOTAL, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
-        else k_policy_dense_tc2<false><<<g2, 128, pd2::S_TOTAL, h->stream>>>(tc->wb, tc->fb, tc->polc, n, logits);
+        if (tc->fp16) k_policy_dense_tc2<true><<<g2, 128, pd2::S_TOTAL, stream>>>(tc->wb, tc->fb, polc, n, logits);
+        else k_policy_dense_tc2<false><<<g2, 128, pd2::S_TOTAL, stream>>>(tc->wb, tc->fb, polc, n, logits);
     }
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
-
-}  // extern "C"
