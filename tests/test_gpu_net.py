@@ -131,3 +131,19 @@ def test_fused_round_loop_equals_round_trips(model, kernel, pre_expand):
     assert torch.equal(a["q"].view(torch.int64), b["q"].view(torch.int64))
     assert torch.equal(a["n_nodes"], b["n_nodes"])
     model.set_kernel("tc")
+
+
+def test_fused_round_loop_two_stream_split_is_bit_identical(model):
+    """>= 8,192 trees: ccx_mcts_run_net runs the two halves of the batch as two pipelines on two streams (ragged halves here);
+    the trees must not depend on that"""
+    from chinesecheckersagent_b200.engine import BatchedMCTS
+    model.set_kernel("tc")
+    n = 8200 + 3
+    st, _, _ = orc.step_random(orc.start_states(n), 21, 0, 7, nthreads=8)
+    roots = torch.from_numpy(np.ascontiguousarray(st).view(np.int64)).cuda()
+    noise = torch.rand((n, 128), dtype=torch.float64, device="cuda")
+    m = BatchedMCTS(model.eng, num_itr=9)
+    a = m.search_with(roots, model.evaluate_states, pre_expand=True, root_noise=noise)
+    b = m.search_net(roots, pre_expand=True, root_noise=noise)
+    assert torch.equal(a["visits"], b["visits"]) and torch.equal(a["q"].view(torch.int64), b["q"].view(torch.int64))
+    assert torch.equal(a["n_nodes"], b["n_nodes"])
