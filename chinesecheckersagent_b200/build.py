@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    extra = os.environ.get("CCX_NVCC_EXTRA", "").split()          # experiments only (e.g. -DCCX_TRUNK_TIMING)
+    extra = os.environ.get("CCX_NVCC_EXTRA", "").split()          # experiments only (extra -D flags)
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     env = dict(os.environ)
     env.pop("CC", None)

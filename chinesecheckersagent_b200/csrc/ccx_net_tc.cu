@@ -1,4 +1,5 @@
-// ccx_net_tc.cu — bf16 tensor-core (tcgen05 + TMEM) path of the policy/value net (model.py:58-145).
+// ccx_net_tc.cu — tensor-core (tcgen05 + TMEM) path of the policy/value net (model.py:58-145): tcgen05 self-tests,
+// the trunk kernel (k_net_trunk_tc4), the policy dense kernel (k_policy_dense_tc2) and their C-ABI entry points.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "ccx_device.cuh"
@@ -238,12 +239,6 @@ template <bool FP16> __device__ __forceinline__ uint32_t relu_pack2(float a, flo
     return r;
 }
 
-// cooperative 16-byte-granular global -> shared copy as one cp.async group (an empty group if bytes == 0)
-__device__ __forceinline__ void refill(uint32_t dst, const uint8_t *src, int bytes, int t)
-{
-    for (int i = t; i < bytes / 16; i += 128) cp_async16(dst + i * 16, src + i * 16);
-    cp_async_commit();
-}
 
 // =====================================================================================================
 // Trunk kernel v4 = v3 with the 1x1 convs' A operands and the residual stream moved into TENSOR MEMORY:

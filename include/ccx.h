@@ -177,9 +177,11 @@ int ccx_net_load(ccx_handle *h, const float *packed_host, int64_t count);
 int ccx_net_forward(ccx_handle *h, int64_t n, const void *planes, int dtype, float *logits, float *value);
 int ccx_softmax_f64(ccx_handle *h, int64_t n, const float *logits, const float *value, double *p, double *v);
 int ccx_net_eval(ccx_handle *h, int64_t n, const uint64_t *leaf_state, double *p, double *v);
-/* bf16 tensor-core path (tcgen05.mma + TMEM, activations resident in shared memory): the weights arrive as
- * a bf16 blob already arranged in the UMMA operand layout plus an fp32 blob of biases (model.py
- * pack_weights_tc; sizes from ccx_net_tc_blob_bytes / ccx_net_tc_num_floats; HOST pointers).
+/* Tensor-core path (tcgen05.mma, accumulators / residual / 1x1-conv operands in TMEM, the 3x3 conv's operand in shared
+ * memory): the weights arrive as a 16-bit operand blob already arranged in the UMMA K-major operand layout — every
+ * trunk matrix transposed [N][K + 16] with the layer's bias split over two of the extra columns — plus an fp32 blob
+ * (biases again, for the policy dense kernel, and the value-head dense); model.py pack_weights_tc builds both, sizes
+ * from ccx_net_tc_blob_bytes / ccx_net_tc_num_floats; HOST pointers.
  * ccx_net_forward_tc takes uint8 planes (n,7,7,7).  ccx_net_set_mode(1) makes ccx_net_eval use it. */
 int ccx_net_tc_blob_bytes(void);
 int ccx_net_tc_num_floats(void);
