@@ -117,3 +117,24 @@ def test_generator_properties_at_size(eng):
     b2 = BatchedGreedyGenerator(eng, seed=SEED, rank=1, world=2).generate(256)
     assert torch.equal(a["lengths"], torch.cat([b1["lengths"], b2["lengths"]]))
     assert torch.equal(a["state"], torch.cat([b1["state"], b2["state"]], dim=1))
+
+
+def test_dropin_generate_play_matches_batched_records(eng):
+    """GreedyDataGenerator().generate_play() (data_generators.py:23-80 surface): [(Board, pi)], reward — and
+    utils.convert_to_train_data on it reproduces the batched generator's board_x / pi_y / v_y for the same games."""
+    from chinesecheckersagent_b200 import utils
+    from chinesecheckersagent_b200.data_generators import BatchedGreedyGenerator, GreedyDataGenerator
+    gen = GreedyDataGenerator(engine=eng, batch=8, seed=SEED)
+    games = [gen.generate_play() for _ in range(8)]
+    ref = BatchedGreedyGenerator(eng, seed=SEED).generate(8)
+    lengths = ref["lengths"].cpu().numpy()
+    assert [len(h) for h, _ in games] == list(lengths)
+    winners = ref["winners"].cpu().numpy()
+    assert [r for _, r in games] == [{0: 0, 1: 1, 2: -1}[int(w)] for w in winners]
+    bx, py, vy = utils.convert_to_train_data(games[:3])
+    m = int(lengths[:3].sum())
+    assert np.array_equal(np.stack(bx).astype(np.uint8), ref["board_x"][:m].cpu().numpy())
+    assert np.allclose(np.stack(py), ref["pi_y"][:m].cpu().numpy().astype(np.float64), atol=1e-7)
+    assert list(vy) == list(ref["v_y"][:m].cpu().numpy())
+    board, pi = games[0][0][0]
+    assert board.get_valid_moves(1) and abs(pi.sum() - 1.0) < 1e-6
