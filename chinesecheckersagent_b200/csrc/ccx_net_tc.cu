@@ -209,7 +209,7 @@ constexpr int F_D1W = F_POLD + 320, F_D1B = F_D1W + 800, F_VHW = F_D1B + 32, F_V
 struct ccx_net_tc {
     uint8_t *wb = nullptr;      // bf16 operand blob
     float *fb = nullptr;        // fp32 biases + value-head dense
-    __nv_bfloat16 *polc = nullptr;   // [cap][400] policy-conv activations between the two kernels (16-bit)
+    __nv_bfloat16 *polc = nullptr;   // policy-conv activations between the two kernels: 128-position tiles in the dense kernel's operand layout (pd3)
     int64_t cap = 0;
     int fp16 = 0;               // 0 = bf16 operands, 1 = IEEE half operands (same kernels, other instruction descriptor)
 };
@@ -239,6 +239,17 @@ template <bool FP16> __device__ __forceinline__ uint32_t relu_pack2(float a, flo
     return r;
 }
 
+
+// layout of the policy-conv activations handed from the trunk kernel to the policy dense kernel (see k_policy_dense_tc3)
+namespace pd3 {
+constexpr int NQ = 80;
+constexpr int A0_B = 128 * 208 * 2, A1_B = 128 * 192 * 2, TILE_B = A0_B + A1_B;        // 102,400 B per 128 positions
+constexpr int W0_B = NQ * 208 * 2, W1_B = NQ * 192 * 2;
+constexpr int S_A0 = 0, S_A1 = S_A0 + A0_B, S_W0 = S_A1 + A1_B, S_W1 = S_W0 + W0_B;
+constexpr int S_TOTAL = S_W1 + W1_B;                    // 166,400 B
+constexpr int OUT_LD = NQ + 1;                          // fp32 staging [128][81] over the A region once the MMAs are done
+static_assert(128 * OUT_LD * 4 <= S_W0, "staging fits in the A region");
+}  // namespace pd3
 
 // =====================================================================================================
 // Trunk kernel v4 = v3 with the 1x1 convs' A operands and the residual stream moved into TENSOR MEMORY:
@@ -540,8 +551,15 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
                 if (h == 0) {
 #pragma unroll
                     for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q], 0.f);
-                    uint4 *dst = reinterpret_cast<uint4 *>(polc + (pos0 + p_local) * 400 + cell * 16);      // Flatten in (y, x, c) order
-                    dst[0] = pack8(v); dst[1] = pack8(v + 8);
+                    // Flatten in (y, x, c) order = K index cell * 16 + c, stored straight in the policy dense kernel's A-operand
+                    // layout: 128-position tiles, each [K 0..207 | K 208..399] in the UMMA core-matrix layout, so that kernel
+                    // fetches a tile with two bulk copies
+                    const int64_t pos = pos0 + p_local;
+                    const int k = cell * 16, chunk = k >= 208, kk = k - chunk * 208;
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(polc) + (pos >> 7) * pd3::TILE_B + (chunk ? pd3::A0_B : 0) +
+                                   umma::op_offset((int)(pos & 127), kk, chunk ? 192 : 208);
+                    *reinterpret_cast<uint4 *>(dst) = pack8(v);
+                    *reinterpret_cast<uint4 *>(dst + 128) = pack8(v + 8);
                 } else {
                     reinterpret_cast<float *>(smem + S_VALC)[p_local * 25 + cell] = fmaxf(v[0], 0.f);
                 }
@@ -571,69 +589,50 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     if (warp == 0) umma::tmem_free(tmem, 128);
 }
 
-// Policy dense v2: 128 positions x 80 outputs per CTA (grid = row tiles x 4 column quarters: 128 CTAs at the
-// self-play batch of 4,096 instead of 64), both K chunks in flight at once (two cp.async groups, the first
-// chunk's MMAs run while the second lands), logits staged through shared memory for coalesced stores.
-namespace pd2 {
-constexpr int NQ = 80;
-constexpr int S_A0 = 0, S_A1 = S_A0 + 128 * 208 * 2, S_W0 = S_A1 + 128 * 192 * 2, S_W1 = S_W0 + NQ * 208 * 2;
-constexpr int S_TOTAL = S_W1 + NQ * 192 * 2;           // 166,400 B
-constexpr int OUT_LD = NQ + 1;                          // fp32 staging [128][81] over the A region once the MMAs are done
-static_assert(128 * OUT_LD * 4 <= S_W0, "staging fits in the A region");
-}  // namespace pd2
-
+// Policy dense v3: logits[B x 294] = flat(policy conv)[B x 400] * W + b as 128-position x 80-output tiles (grid = row tiles x
+// 4 column quarters: 128 CTAs at the self-play batch of 4,096).  Both operands of a tile arrive as FOUR bulk copies issued by
+// one thread (the trunk kernel already wrote the activations in the operand layout; the quarter's weight rows are a contiguous
+// slice of the blob) — v2 spent ~3 K instructions per thread on 16-byte cp.async address arithmetic, 12 us per launch.
+// The K chunks land on two mbarriers, so the first chunk's MMAs run while the second is in flight; logits are staged through
+// shared memory for coalesced stores.
 template <bool FP16>
 __global__ void __launch_bounds__(128, 1)
-k_policy_dense_tc2(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const __nv_bfloat16 *__restrict__ polc, int64_t n,
+k_policy_dense_tc3(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ polc, int64_t n,
                    float *__restrict__ logits)
 {
-    using namespace pd2;
+    using namespace pd3;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, barL[2];
     __shared__ uint32_t tmem_slot;
     const int t = threadIdx.x, warp = t >> 5;
     const int quarter = blockIdx.y, half = quarter >> 1, c0 = (quarter & 1) * NQ;
     const int64_t row0 = (int64_t)blockIdx.x * 128;
     const uint32_t sbase = umma::smem_u32(smem);
-    if (t == 0) umma::mbar_init(&bar, 1);
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
-#pragma unroll
-    for (int chunk = 0; chunk < 2; chunk++) {
-        const int k0 = chunk ? 208 : 0, Kc = chunk ? 192 : 208, pieces = Kc / 8;
-        const int sa = chunk ? S_A1 : S_A0, sw = chunk ? S_W1 : S_W0;
-        for (int i = t; i < 128 * pieces; i += 128) {
-            const int r = i / pieces, k8 = i % pieces;
-            const int64_t row = row0 + r;
-            if (row < n) cp_async16(sbase + sa + umma::op_offset(r, k8 * 8, Kc), polc + row * 400 + k0 + k8 * 8);
-            else *reinterpret_cast<uint4 *>(smem + sa + umma::op_offset(r, k8 * 8, Kc)) = make_uint4(0, 0, 0, 0);
-        }
+    if (t == 0) {
+        umma::mbar_init(&bar, 1); umma::mbar_init(&barL[0], 1); umma::mbar_init(&barL[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint8_t *a = polc + (int64_t)blockIdx.x * TILE_B;
         // this quarter's 80 weight rows are a contiguous slice of the half's [160 x Kc] operand
-        const uint8_t *wsrc = wb + tcl::W_POLD + half * tcl::POLD_HALF + (chunk ? tcl::POLD_C0 : 0) + (c0 / 8) * pieces * 128;
-        for (int i = t; i < NQ * Kc * 2 / 16; i += 128) cp_async16(sbase + sw + i * 16, wsrc + i * 16);
-        cp_async_commit();
+        const uint8_t *w0 = wb + tcl::W_POLD + half * tcl::POLD_HALF + (c0 / 8) * (208 / 8) * 128;
+        const uint8_t *w1 = wb + tcl::W_POLD + half * tcl::POLD_HALF + tcl::POLD_C0 + (c0 / 8) * (192 / 8) * 128;
+        umma::mbar_expect_tx(&barL[0], A0_B + W0_B);
+        umma::bulk_g2s(sbase + S_A0, a, A0_B, &barL[0]);
+        umma::bulk_g2s(sbase + S_W0, w0, W0_B, &barL[0]);
+        umma::mbar_expect_tx(&barL[1], A1_B + W1_B);
+        umma::bulk_g2s(sbase + S_A1, a + A0_B, A1_B, &barL[1]);
+        umma::bulk_g2s(sbase + S_W1, w1, W1_B, &barL[1]);
     }
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
     constexpr uint32_t ID = umma::make_idesc(NQ, FP16);
-    cp_async_wait<1>();
-    umma::fence_async_smem();
-    umma::fence_before_sync();
-    __syncthreads();
     if (warp == 0) {
-        umma::fence_after_sync();
-        if (umma::elect_one())
-            umma::gemm_issue_d<208>(tmem, umma::desc_base(sbase + S_A0, 128u, 208 / 8 * 128u), 0, umma::desc_base(sbase + S_W0, 128u, 208 / 8 * 128u), 0, ID, false);
-        __syncwarp();
-    }
-    cp_async_wait<0>();
-    umma::fence_async_smem();
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-        umma::fence_after_sync();
         if (umma::elect_one()) {
+            umma::mbar_wait(&barL[0], 0);
+            umma::gemm_issue_d<208>(tmem, umma::desc_base(sbase + S_A0, 128u, 208 / 8 * 128u), 0, umma::desc_base(sbase + S_W0, 128u, 208 / 8 * 128u), 0, ID, false);
+            umma::mbar_wait(&barL[1], 0);
             umma::gemm_issue_d<192>(tmem, umma::desc_base(sbase + S_A1, 128u, 192 / 8 * 128u), 0, umma::desc_base(sbase + S_W1, 128u, 192 / 8 * 128u), 0, ID, true);
             umma::commit(&bar);
         }
@@ -692,8 +691,8 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
     CCX_CUDA(h, cudaMemcpyAsync(tc->fb, f32_host, sizeof(float) * tcl::F_TOTAL, cudaMemcpyHostToDevice, h->stream));
     CCX_CUDA(h, cudaStreamSynchronize(h->stream));
     tc->fp16 = fp16;
-    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd2::S_TOTAL));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd2::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd3::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd3::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::S_TOTAL));
     return CCX_OK;
@@ -720,11 +719,14 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
         CCX_CUDA(h, cudaDeviceSynchronize());          // another stream may still read the old scratch
         if (tc->polc) CCX_CUDA(h, cudaFree(tc->polc));
         tc->polc = nullptr; tc->cap = 0;
-        CCX_CUDA(h, cudaMalloc(&tc->polc, sizeof(__nv_bfloat16) * 400 * (size_t)cap));
+        const size_t bytes = (size_t)((cap + 127) / 128) * pd3::TILE_B;         // whole 128-position tiles
+        CCX_CUDA(h, cudaMalloc(&tc->polc, bytes));
+        CCX_CUDA(h, cudaMemsetAsync(tc->polc, 0, bytes, stream));                  // rows past n of the last tile stay finite
         tc->cap = cap;
     }
     if (n == 0) return CCX_OK;                         // (a call with n = 0 only reserves the scratch)
-    __nv_bfloat16 *polc = tc->polc + row0 * 400;
+    if (row0 % 128) return CCX_ERR_ARG;
+    __nv_bfloat16 *polc = reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<uint8_t *>(tc->polc) + (row0 / 128) * pd3::TILE_B);
     {
         int64_t tiles = (n + tc4::POS - 1) / tc4::POS;
         unsigned grid = (unsigned)(tiles < 3 * h->num_sms ? tiles : 3 * h->num_sms);     // three resident CTAs per SM
@@ -734,8 +736,8 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
     CCX_LAUNCHED(h);
     {
         dim3 g2((unsigned)((n + 127) / 128), 4);
-        if (tc->fp16) k_policy_dense_tc2<true><<<g2, 128, pd2::S_TOTAL, stream>>>(tc->wb, tc->fb, polc, n, logits);
-        else k_policy_dense_tc2<false><<<g2, 128, pd2::S_TOTAL, stream>>>(tc->wb, tc->fb, polc, n, logits);
+        if (tc->fp16) k_policy_dense_tc3<true><<<g2, 128, pd3::S_TOTAL, stream>>>(tc->wb, tc->fb, (const uint8_t *)polc, n, logits);
+        else k_policy_dense_tc3<false><<<g2, 128, pd3::S_TOTAL, stream>>>(tc->wb, tc->fb, (const uint8_t *)polc, n, logits);
     }
     CCX_LAUNCHED(h);
     return CCX_OK;
