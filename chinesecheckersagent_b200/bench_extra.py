@@ -155,7 +155,7 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
                                           "tflops": tf, "batch": 65536}
             if kern == "tc" and peak_tflops:
                 out["net_forward_tc"]["roofline"] = {"bound": "tensor", "achieved": tf / world, "peak": peak_tflops, "unit": "TFLOP/s",
-                                                     "frac": tf / world / peak_tflops, "kernel": "k_net_trunk_tc4 + k_policy_dense_tc2"}
+                                                     "frac": tf / world / peak_tflops, "kernel": "k_net_trunk_tc4 + k_policy_dense_tc3"}
         model.set_kernel("tc")
         # trajectory all-gather (the only collective): time it when there is more than one rank
         traj = traj_src.collect()

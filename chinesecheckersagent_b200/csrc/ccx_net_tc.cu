@@ -1,5 +1,5 @@
 // ccx_net_tc.cu — tensor-core (tcgen05 + TMEM) path of the policy/value net (model.py:58-145): tcgen05 self-tests,
-// the trunk kernel (k_net_trunk_tc4), the policy dense kernel (k_policy_dense_tc2) and their C-ABI entry points.
+// the trunk kernel (k_net_trunk_tc4), the policy dense kernel (k_policy_dense_tc3) and their C-ABI entry points.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "ccx_device.cuh"
