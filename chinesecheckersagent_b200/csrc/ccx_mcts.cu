@@ -12,6 +12,7 @@
 #include "ccx_device.cuh"
 #include "ccx_internal.h"
 #include <new>
+#include <cmath>
 #include <cstdlib>
 
 #define FULL 0xFFFFFFFFu
@@ -71,6 +72,12 @@ __device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
 enum { META_NNODES = 0, META_NEDGES = 1, META_OVERFLOW = 2, META_PATHLEN = 3, META_LEAF = 4, META_LEAFKIND = 5 };
 enum { LEAF_EVAL = 0, LEAF_TERMINAL = 1, LEAF_DEAD = 2 };
 enum { EVAL_UNIFORM = 0, EVAL_HASH = 1, EVAL_NET = 2 };
+
+// sqrt of small integers, correctly rounded (filled on the host with IEEE sqrt, which is what the device's sqrt(double) returns
+// too): np.sqrt(N_sum) of the descent becomes one broadcast constant load instead of a ~150-cycle dependent sequence per level
+#define SQRT_TABLE 1024
+__constant__ double c_sqrt[SQRT_TABLE];
+__device__ __forceinline__ double sqrt_count(u32 n) { return n < SQRT_TABLE ? c_sqrt[n] : sqrt((double)n); }
 
 __device__ __forceinline__ u64 shfl64(u64 v, int src)
 {
@@ -182,7 +189,7 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
             nsum += Nr[c];
         }
         nsum = __reduce_add_sync(FULL, nsum);                    // N_sum (MCTS.py:58-59)
-        double sq = sqrt((double)nsum);                          // np.sqrt(N_sum)
+        double sq = sqrt_count(nsum);                            // np.sqrt(N_sum)
         double best = -INFINITY; int besti = 0x7FFFFFFF;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -674,6 +681,15 @@ void ccx_trees_free(ccx_handle *h)
 
 static int trees_reserve(ccx_handle *h, int64_t n, int32_t num_itr, int32_t edges_per_tree)
 {
+    {   // per device: the constant table lives in this module's image on the handle's device
+        static bool filled[64] = {false};
+        if (h->device >= 0 && h->device < 64 && !filled[h->device]) {
+            static double host_sqrt[SQRT_TABLE];
+            for (int i = 0; i < SQRT_TABLE; i++) host_sqrt[i] = sqrt((double)i);
+            CCX_CUDA(h, cudaMemcpyToSymbol(c_sqrt, host_sqrt, sizeof(host_sqrt)));
+            filled[h->device] = true;
+        }
+    }
     int32_t npt = num_itr + 2;
     int32_t ept = edges_per_tree > 0 ? edges_per_tree : 64 * (num_itr + 1);
     int32_t pm = num_itr + 2;
