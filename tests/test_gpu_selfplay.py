@@ -133,3 +133,29 @@ def test_selfplay_with_real_net_smoke(eng):
     assert st["plies"] == 64 * 10
     v = sp.visits.cpu().numpy()
     assert np.all(v.sum(1) == 16)                      # root pre-expanded: sum N = num_itr (selfplay.py:117,127)
+
+
+def test_full_selfplay_with_real_net_at_size(eng):
+    """cfg 5 at working size: 1,024 slots play whole games with the reference's settings (175 simulations, Dirichlet noise,
+    tau switch) through the fused net-MCTS rounds; the trajectory buffer must be consistent with the outcome counters."""
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    model = ResidualCNN(engine=eng).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+    sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=1024, max_iters=80, seed=2026)
+    assert sp.fused
+    st = sp.run(iters=80)
+    assert st["plies"] == 1024 * 80                      # every slot plays every iteration (finished slots restart at once)
+    finished = st["p1_wins"] + st["p2_wins"]
+    assert finished > 300 and st["discarded_overflow"] == 0
+    assert finished == st["games"]
+    assert 0.25 < st["p1_wins"] / finished < 0.75
+    traj = sp.collect()
+    m = traj["board_x"].shape[0]
+    assert m == st["records"] and traj["pi_y"].shape == (m, 294) and traj["v_y"].shape == (m,)
+    pi = traj["pi_y"]
+    assert torch.allclose(pi.sum(1), torch.ones(m, device=pi.device), atol=1e-4)
+    v = traj["v_y"].cpu().numpy()
+    assert set(np.unique(v)) <= {-1, 1} and 0.3 < (v == 1).mean() < 0.7
+    # records are positions after the six random opening plies: planes 0/1 hold six labelled checkers each
+    bx = traj["board_x"].cpu().numpy()
+    assert np.all((bx[..., 0] > 0).sum((1, 2)) == 6) and np.all((bx[..., 1] > 0).sum((1, 2)) == 6)
