@@ -1,0 +1,46 @@
+"""bench.py's output contract: the committed GPU line carries every key the driver reads, and the reference arm
+(`--impl reference`, CPU only: the oracle port on the host cores) runs here and prints the same shape."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def test_committed_gpu_line_has_the_contract_keys():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01d_bench_1gpu.json")))
+    assert BASE_KEYS <= set(d) and {"roofline", "cpu_baseline", "clocks"} <= set(d)
+    assert d["metric"] == "env_steps_per_sec" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True
+    assert "workload" in d["config"] and d["config"]["games_per_gpu"] == 65536 and "model" not in d["config"]
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(d["value"] - 65536 * 256 * d["steps"] / (d["ms_per_step"] * d["steps"] / 1e3)) / d["value"] < 1e-6
+    c = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference") and c["cores"] == 1
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    assert d["gpu_launches"] == d["steps"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def run_reference(env_extra):
+    env = dict(os.environ, **env_extra)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=300)
+    assert p.returncode == 0, p.stderr
+    return p.stdout.strip()
+
+
+def test_reference_arm_runs_on_cpu_and_only_rank0_prints():
+    out = run_reference({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    d = json.loads(out.splitlines()[-1])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["metric"] == "env_steps_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+    assert run_reference({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == ""
