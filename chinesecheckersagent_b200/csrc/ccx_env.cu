@@ -460,6 +460,7 @@ int ccx_destroy(ccx_handle *h)
     cudaSetDevice(h->device);
     ccx_net_free(h);
     ccx_net_tc_free(h);
+    ccx_net_acc_free(h);
     ccx_trees_free(h);
     ccx_scratch *s[] = {&h->d_state, &h->d_aux0, &h->d_aux1, &h->d_aux2};
     for (auto *p : s) if (p->ptr) cudaFree(p->ptr);

@@ -14,6 +14,7 @@ struct ccx_scratch {
 struct ccx_net;     // ccx_net.cu
 struct ccx_trees;   // ccx_mcts.cu
 struct ccx_net_tc;  // ccx_net_tc.cu
+struct ccx_net_acc; // ccx_net_tc.cu (accurate split-precision mode)
 
 struct ccx_handle {
     int device = 0;
@@ -26,8 +27,9 @@ struct ccx_handle {
     ccx_net *net = nullptr;
     ccx_trees *trees = nullptr;
     ccx_net_tc *net_tc = nullptr;
+    ccx_net_acc *net_acc = nullptr;
     uint8_t *jump_table = nullptr;   // CCX_JT_BYTES, device: ray-jump lookup table (ccx_device.cuh)
-    int net_mode = 0;           // 0 = fp32 SIMT kernel, 1 = bf16 tcgen05 kernels (ccx_net_set_mode)
+    int net_mode = 0;           // 0 = fp32 SIMT kernel, 1 = 16-bit tcgen05 kernels, 2 = split-precision tcgen05 kernels (ccx_net_set_mode)
     // second stream + fork/join events of the two-half round pipeline (ccx_mcts_run_net), created on first use
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -75,3 +77,6 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
 void ccx_net_free(ccx_handle *h);
 void ccx_trees_free(ccx_handle *h);
 void ccx_net_tc_free(ccx_handle *h);
+void ccx_net_acc_free(ccx_handle *h);
+extern "C" int ccx_net_forward_acc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value, const float *w_pold,
+                                   const float *b_pold);

@@ -317,8 +317,9 @@ int ccx_softmax_f64(ccx_handle *h, int64_t n, const float *logits, const float *
 
 int ccx_net_set_mode(ccx_handle *h, int32_t mode)
 {
-    if (!h || (mode != 0 && mode != 1)) return CCX_ERR_ARG;
+    if (!h || (mode != 0 && mode != 1 && mode != 2)) return CCX_ERR_ARG;
     if (mode == 1 && !h->net_tc) return CCX_ERR_STATE;
+    if (mode == 2 && (!h->net_tc || !h->net_acc || !h->net || !h->net->w)) return CCX_ERR_STATE;
     h->net_mode = mode;
     return CCX_OK;
 }
@@ -357,8 +358,16 @@ int ccx_net_scratch(ccx_handle *h, int64_t n, uint8_t **planes, float **logits, 
     return CCX_OK;
 }
 
+extern "C" int ccx_net_forward_u8(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value)
+{
+    if (!h || n < 0 || (n && (!planes || !logits || !value))) return CCX_ERR_ARG;
+    if (!h->net || !h->net->w) return CCX_ERR_STATE;
+    return ccx_net_forward_active(h, n, planes, logits, value);
+}
+
 int ccx_net_forward_active(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value)
 {
     if (h->net_mode == 1) return ccx_net_forward_tc(h, n, planes, logits, value);
+    if (h->net_mode == 2) return ccx_net_forward_acc(h, n, planes, logits, value, h->net->w + netl::POLD_W, h->net->w + netl::POLD_B);
     return ccx_net_forward(h, n, planes, CCX_DTYPE_U8, logits, value);
 }

@@ -742,3 +742,390 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
+
+// =====================================================================================================
+// Accurate tensor-core mode (ccx_net_set_mode(2)): same network, same tile geometry and phase structure as
+// k_net_trunk_tc4, but every product is evaluated in split precision — activations a = a_hi + a_lo and weights
+// w = w_hi + w_lo, each term an IEEE half — as  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  accumulated in fp32 by the tensor
+// core (the dropped a_lo*w_lo term is ~2^-22 relative).  A 16-bit-operand pass through the 29 layers leaves up to
+// 3.2e-3 on the largest probabilities (every layer group contributes: DESIGN.md §3); this mode brings the tensor-core
+// path to the fp32 restatement's ~1e-5 at three times the MMAs and twice the operand storage (one CTA per SM).
+// Operand blob (model.py pack_weights_acc): per matrix [hi: N x (K+16) with the bias columns][lo: N x K], UMMA layout:
+//   CONV1 | HEADS | 9 x [A | B | C].  The policy dense layer runs in fp32 on the fp32 copy of the weights (ccx_net_load).
+namespace acl {
+__host__ __device__ constexpr int hi_b(int N, int K) { return N * (K + 16) * 2; }
+__host__ __device__ constexpr int lo_b(int N, int K) { return N * K * 2; }
+constexpr int B_CONV1 = hi_b(64, 64) + lo_b(64, 64), B_HEADS = hi_b(32, 64) + lo_b(32, 64);
+constexpr int B_A = hi_b(32, 64) + lo_b(32, 64), B_B = hi_b(32, 288) + lo_b(32, 288), B_C = hi_b(64, 32) + lo_b(64, 32);
+constexpr int W_CONV1 = 0, W_HEADS = B_CONV1, W_BLOCK0 = W_HEADS + B_HEADS, W_BLOCK = B_A + B_B + B_C;
+constexpr int W_BA = 0, W_BB = B_A, W_BC = B_A + B_B;
+constexpr int W_TOTAL = W_BLOCK0 + 9 * W_BLOCK;
+constexpr int THREADS = 256, POS = 4, POS_ROWS = 30, LIVE_ROWS = 120;
+constexpr int YROWS = 130, Y_LBO = YROWS * 16, Y_COPY = 4 * Y_LBO;
+constexpr int T_X = 0, T_XH = 64, T_XL = 96, T_AO = 128;                   // TMEM columns (256 allocated)
+constexpr int S_YH = 0, S_YL = S_YH + 3 * Y_COPY;
+constexpr int S_WC1 = S_YL + 3 * Y_COPY;
+constexpr int S_WA = S_WC1 + B_CONV1, S_WB = S_WA + B_A, S_WC = S_WB + B_B;
+constexpr int S_ONES = S_WC + B_C;
+constexpr int S_F = S_ONES + 128 * 16 * 2;
+constexpr int S_PLANES = S_F + tc4::F_BYTES;
+constexpr int S_VALC = S_PLANES + 1376;
+constexpr int S_TOTAL = S_VALC + 512;
+static_assert(S_TOTAL <= 227 * 1024, "fits one CTA");
+static_assert(S_YL % 128 == 0 && S_WC1 % 128 == 0 && S_WA % 128 == 0 && S_WB % 128 == 0 && S_WC % 128 == 0 && S_ONES % 128 == 0 &&
+              S_F % 16 == 0 && S_PLANES % 16 == 0, "alignment");
+}  // namespace acl
+
+// (hi, lo) halves of two fp32 values: hi = round16(x), lo = round16(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    __half2 h = __floats2half2_rn(a, b);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    lo = *reinterpret_cast<uint32_t *>(&l);
+}
+
+__global__ void __launch_bounds__(acl::THREADS, 1)
+k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
+                float *__restrict__ polc, float *__restrict__ value)
+{
+    using namespace acl;
+    constexpr bool FP16 = true;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar, barW[4];
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int rg = warp & 3, h = warp >> 2;
+    const int r = rg * 32 + lane;
+    const int p_local = r / POS_ROWS, rem = r % POS_ROWS, cy = rem / 6, cx = rem % 6;
+    const bool live = r < LIVE_ROWS && cx < 5;
+    const int cell = cy * 5 + cx;
+    const uint32_t sbase = umma::smem_u32(smem);
+    const float *sF = reinterpret_cast<const float *>(smem + S_F);
+    const int64_t n_tiles = (n + POS - 1) / POS;
+
+    auto refill_slot = [&](int slot, int dst, const uint8_t *src, uint32_t bytes) {
+        umma::mbar_expect_tx(&barW[slot], bytes);
+        umma::bulk_g2s(sbase + dst, src, bytes, &barW[slot]);
+    };
+    auto stage_planes = [&](int64_t tile) {
+        const int bytes = (int)min((int64_t)POS, n - tile * POS) * 343;
+        const uint8_t *src = planes + tile * (POS * 343);
+        for (int i = t; i < POS * 343; i += THREADS) smem[S_PLANES + i] = i < bytes ? __ldg(src + i) : (uint8_t)0;
+    };
+
+    for (int i = t; i < S_WC1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows of both copy sets
+    for (int i = t; i < tc4::NF; i += THREADS) reinterpret_cast<float *>(smem + S_F)[i] = __ldg(fb + tcl::F_D1W + i);
+    for (int i = t; i < 128 * 2; i += THREADS) {
+        const int rr = i >> 1, chunk = i & 1;
+        *reinterpret_cast<uint4 *>(smem + S_ONES + umma::op_offset(rr, chunk * 8, 16)) = make_uint4(chunk == 0 ? pack2<FP16>(1.f, 1.f) : 0u, 0u, 0u, 0u);
+    }
+    if (t == 0) {
+        umma::mbar_init(&bar, 1);
+#pragma unroll
+        for (int q = 0; q < 4; q++) umma::mbar_init(&barW[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        refill_slot(3, S_WC1, wb + W_CONV1, B_CONV1);
+        refill_slot(0, S_WA, wb + W_BLOCK0 + W_BA, B_A);
+        refill_slot(1, S_WB, wb + W_BLOCK0 + W_BB, B_B);
+        refill_slot(2, S_WC, wb + W_BLOCK0 + W_BC, B_C);
+    }
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    uint32_t phW0 = 0, phW1 = 0, phW2 = 0;
+    bool conv1_ready = false;
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(rg * 32) << 16);
+    uint32_t phase = 0;
+    // operand descriptors: hi parts carry the 16 bias columns (K + 16 layout), lo parts follow them in the slot (K layout)
+    const umma::DescBase dYH = umma::desc_base(sbase + S_YH, Y_LBO, 128u), dYL = umma::desc_base(sbase + S_YL, Y_LBO, 128u);
+    const umma::DescBase dC1H = umma::desc_base(sbase + S_WC1, 128u, 80 / 8 * 128u), dC1L = umma::desc_base(sbase + S_WC1 + hi_b(64, 64), 128u, 64 / 8 * 128u);
+    const umma::DescBase dAH = umma::desc_base(sbase + S_WA, 128u, 80 / 8 * 128u), dAL = umma::desc_base(sbase + S_WA + hi_b(32, 64), 128u, 64 / 8 * 128u);
+    const umma::DescBase dBH = umma::desc_base(sbase + S_WB, 128u, 304 / 8 * 128u), dBL = umma::desc_base(sbase + S_WB + hi_b(32, 288), 128u, 288 / 8 * 128u);
+    const umma::DescBase dCH = umma::desc_base(sbase + S_WC, 128u, 48 / 8 * 128u), dCL = umma::desc_base(sbase + S_WC + hi_b(64, 32), 128u, 32 / 8 * 128u);
+    const umma::DescBase dONES = umma::desc_base(sbase + S_ONES, 128u, 16 / 8 * 128u);
+    constexpr uint32_t ID32 = umma::make_idesc(32, FP16), ID64 = umma::make_idesc(64, FP16);
+
+    auto tmem_sync = [&]() { umma::tmem_wait_st(); umma::fence_before_sync(); __syncthreads(); };
+    auto smem_sync = [&]() { umma::fence_async_smem(); umma::fence_before_sync(); __syncthreads(); };
+    auto wait_mma = [&]() { umma::mbar_wait(&bar, phase); phase ^= 1; umma::fence_after_sync(); };
+    auto bias_mma = [&](uint32_t tmem_d, umma::DescBase w, int K, uint32_t idesc, bool accumulate) {
+        umma::mma_bf16(tmem_d, umma::desc_at(dONES, 0u), umma::desc_at(w, (uint32_t)(K / 8) * 128u), idesc, accumulate);
+    };
+    // this thread's 32 residual columns: ReLU in place in TMEM X (fp32) and the split 16-bit copies XH / XL
+    auto finish_x = [&]() {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            float v[16];
+            umma::tmem_ld16(trow + T_X + h * 32 + half * 16, v);
+            uint32_t f[16], ph[8], pl[8];
+#pragma unroll
+            for (int j = 0; j < 16; j++) { v[j] = fmaxf(v[j], 0.f); f[j] = __float_as_uint(v[j]); }
+#pragma unroll
+            for (int j = 0; j < 8; j++) split2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+            umma::tmem_st16(trow + T_X + h * 32 + half * 16, f);
+            umma::tmem_st8(trow + T_XH + h * 16 + half * 8, ph);
+            umma::tmem_st8(trow + T_XL + h * 16 + half * 8, pl);
+        }
+    };
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t pos0 = tile * POS;
+        const int n_pos = (int)min((int64_t)POS, n - pos0);
+        stage_planes(tile);
+        __syncthreads();
+        // conv1 operand: the uint8 plane values are exact in half precision, so only the weights are split (a_lo = 0)
+        {
+            const uint8_t *pl = smem + S_PLANES + (live ? p_local * 343 : 0);
+#pragma unroll
+            for (int c8 = 0; c8 < 2; c8++) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    float v2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int kk = h * 32 + c8 * 16 + q * 2 + e;
+                        const int tap = kk / 7, ch = kk % 7, dy = tap / 3, dx = tap % 3;
+                        v2[e] = (live && kk < 63) ? (float)pl[((cy + dy) * 7 + (cx + dx)) * 7 + ch] : 0.f;
+                    }
+                    pk[q] = pack2<FP16>(v2[0], v2[1]);
+                }
+                umma::tmem_st8(trow + T_XH + h * 16 + c8 * 8, pk);
+            }
+        }
+        tmem_sync();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                if (!conv1_ready) { umma::mbar_wait(&barW[3], 0); conv1_ready = true; }
+                bias_mma(tmem + T_X, dC1H, 64, ID64, false);
+                umma::gemm_issue_ts<64>(tmem + T_X, tmem + T_XH, dC1H, 0, ID64, true);
+                umma::gemm_issue_ts<64>(tmem + T_X, tmem + T_XH, dC1L, 0, ID64, true);
+                umma::commit(&bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        finish_x();
+        for (int b = 0; b < 9; b++) {
+            const uint8_t *wnext = wb + W_BLOCK0 + ((b + 1) % 9) * W_BLOCK;
+            // A: 1x1 conv 64 -> 32
+            tmem_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[0], phW0); phW0 ^= 1;
+                    bias_mma(tmem + T_AO, dAH, 64, ID32, false);
+                    umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XH, dAH, 0, ID32, true);
+                    umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XL, dAH, 0, ID32, true);
+                    umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XH, dAL, 0, ID32, true);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            if (warp == 0 && umma::elect_one()) refill_slot(0, S_WA, b < 8 ? wnext + W_BA : wb + W_HEADS, B_A);
+            {
+                float v[16];
+                umma::tmem_ld16(trow + T_AO + h * 16, v);
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q], 0.f), fmaxf(v[2 * q + 1], 0.f), ph[q], pl[q]);
+                if (live) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const int oy = cy - (d - 1);
+                        if (oy >= 0 && oy <= 4) {
+                            const int off = d * Y_COPY + (2 * h) * Y_LBO + (1 + r - 6 * (d - 1)) * 16;
+                            *reinterpret_cast<uint4 *>(smem + S_YH + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                            *reinterpret_cast<uint4 *>(smem + S_YH + off + Y_LBO) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                            *reinterpret_cast<uint4 *>(smem + S_YL + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                            *reinterpret_cast<uint4 *>(smem + S_YL + off + Y_LBO) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                        }
+                    }
+                }
+            }
+            // B: 3x3 conv 32 -> 32: (hi, hi) + (lo, hi) + (hi, lo) over the nine row-shifted taps
+            smem_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
+                    bias_mma(tmem + T_AO, dBH, 288, ID32, false);
+#pragma unroll
+                    for (int term = 0; term < 3; term++)
+#pragma unroll
+                        for (int d = 0; d < 3; d++)
+#pragma unroll
+                            for (int dxi = 0; dxi < 3; dxi++)
+#pragma unroll
+                                for (int ks = 0; ks < 2; ks++)
+                                    umma::mma_bf16(tmem + T_AO, umma::desc_at(term == 1 ? dYL : dYH, (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO)),
+                                                   umma::desc_at(term == 2 ? dBL : dBH, (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128)), ID32, true);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            if (warp == 0 && umma::elect_one()) refill_slot(1, S_WB, wnext + W_BB, B_B);
+            {
+                float v[16];
+                umma::tmem_ld16(trow + T_AO + h * 16, v);
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q], 0.f), fmaxf(v[2 * q + 1], 0.f), ph[q], pl[q]);
+                umma::tmem_st8(trow + T_XH + h * 8, ph);         // conv C's operand: 32 channels = 16 columns, hi and lo
+                umma::tmem_st8(trow + T_XL + h * 8, pl);
+            }
+            // C: 1x1 conv 32 -> 64 accumulated onto the residual
+            tmem_sync();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[2], phW2); phW2 ^= 1;
+                    bias_mma(tmem + T_X, dCH, 32, ID64, true);
+                    umma::gemm_issue_ts<32>(tmem + T_X, tmem + T_XH, dCH, 0, ID64, true);
+                    umma::gemm_issue_ts<32>(tmem + T_X, tmem + T_XL, dCH, 0, ID64, true);
+                    umma::gemm_issue_ts<32>(tmem + T_X, tmem + T_XH, dCL, 0, ID64, true);
+                    umma::commit(&bar);
+                }
+                __syncwarp();
+            }
+            wait_mma();
+            if (warp == 0 && umma::elect_one()) refill_slot(2, S_WC, wnext + W_BC, B_C);
+            finish_x();
+        }
+        // heads
+        tmem_sync();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::mbar_wait(&barW[0], phW0); phW0 ^= 1;
+                bias_mma(tmem + T_AO, dAH, 64, ID32, false);
+                umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XH, dAH, 0, ID32, true);
+                umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XL, dAH, 0, ID32, true);
+                umma::gemm_issue_ts<64>(tmem + T_AO, tmem + T_XH, dAL, 0, ID32, true);
+                umma::commit(&bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        if (warp == 0 && umma::elect_one()) refill_slot(0, S_WA, wb + W_BLOCK0 + W_BA, B_A);
+        {
+            float v[16];
+            umma::tmem_ld16(trow + T_AO + h * 16, v);
+            if (live && p_local < n_pos) {
+                if (h == 0) {
+                    float4 *dst = reinterpret_cast<float4 *>(polc + (pos0 + p_local) * 400 + cell * 16);       // Flatten in (y, x, c) order, fp32
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        dst[q] = make_float4(fmaxf(v[4 * q], 0.f), fmaxf(v[4 * q + 1], 0.f), fmaxf(v[4 * q + 2], 0.f), fmaxf(v[4 * q + 3], 0.f));
+                } else {
+                    reinterpret_cast<float *>(smem + S_VALC)[p_local * 25 + cell] = fmaxf(v[0], 0.f);
+                }
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        if (warp < n_pos) {
+            const float *valc = reinterpret_cast<const float *>(smem + S_VALC) + warp * 25;
+            float acc = sF[tc4::FO_D1B + lane];
+            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], sF[tc4::FO_D1W + k * 32 + lane], acc);
+            float sv = fmaxf(acc, 0.f) * sF[tc4::FO_VHW + lane];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, off);
+            if (lane == 0) value[pos0 + warp] = tanhf(sv + sF[tc4::FO_VHB]);
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && umma::elect_one()) {
+        umma::mbar_wait(&barW[0], phW0); umma::mbar_wait(&barW[1], phW1); umma::mbar_wait(&barW[2], phW2);
+        if (!conv1_ready) umma::mbar_wait(&barW[3], 0);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tmem, 256);
+}
+
+// policy dense layer in fp32: logits[B x 294] = polc[B x 400] * W[400 x 294] + b.  30 positions per block (their activations
+// in shared memory, 48,000 B), one thread per output column holding 30 accumulators; W (fp32, row-major [400][294]) is read
+// once per block.
+#define PDF_POS 30
+__global__ void __launch_bounds__(320)
+k_policy_dense_f32(const float *__restrict__ W, const float *__restrict__ bias, const float *__restrict__ polc, int64_t n,
+                   float *__restrict__ logits)
+{
+    __shared__ float sA[PDF_POS][400];
+    const int64_t row0 = (int64_t)blockIdx.x * PDF_POS;
+    const int rows = (int)min((int64_t)PDF_POS, n - row0);
+    for (int i = threadIdx.x; i < PDF_POS * 400; i += blockDim.x) sA[i / 400][i % 400] = (i / 400) < rows ? polc[(row0 + i / 400) * 400 + i % 400] : 0.f;
+    __syncthreads();
+    const int col = threadIdx.x;
+    if (col >= CCX_NUM_ACTIONS) return;
+    float acc[PDF_POS];
+#pragma unroll
+    for (int p = 0; p < PDF_POS; p++) acc[p] = 0.f;
+    for (int k = 0; k < 400; k++) {
+        const float w = __ldg(W + k * CCX_NUM_ACTIONS + col);
+#pragma unroll
+        for (int p = 0; p < PDF_POS; p++) acc[p] = fmaf(sA[p][k], w, acc[p]);
+    }
+    const float b = __ldg(bias + col);
+    for (int p = 0; p < rows; p++) logits[(row0 + p) * CCX_NUM_ACTIONS + col] = acc[p] + b;
+}
+
+struct ccx_net_acc { uint8_t *wb = nullptr; float *polc = nullptr; int64_t cap = 0; };
+
+void ccx_net_acc_free(ccx_handle *h)
+{
+    if (!h->net_acc) return;
+    cudaFree(h->net_acc->wb); cudaFree(h->net_acc->polc);
+    delete h->net_acc;
+    h->net_acc = nullptr;
+}
+
+extern "C" {
+
+int ccx_net_acc_blob_bytes(void) { return acl::W_TOTAL; }
+
+int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
+{
+    if (!h || !blob_host || blob_bytes != acl::W_TOTAL) return CCX_ERR_ARG;
+    if (!h->net_acc) h->net_acc = new (std::nothrow) ccx_net_acc();
+    if (!h->net_acc) return CCX_ERR_NOMEM;
+    ccx_net_acc &a = *h->net_acc;
+    if (!a.wb) CCX_CUDA(h, cudaMalloc(&a.wb, acl::W_TOTAL));
+    CCX_CUDA(h, cudaMemcpyAsync(a.wb, blob_host, acl::W_TOTAL, cudaMemcpyHostToDevice, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, acl::S_TOTAL));
+    return CCX_OK;
+}
+
+// needs ccx_net_load (fp32 weights: policy dense), ccx_net_load_tc (fp32 blob: value head) and ccx_net_load_acc
+int ccx_net_forward_acc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value, const float *w_pold, const float *b_pold)
+{
+    if (!h || n < 0 || (n && (!planes || !logits || !value || !w_pold || !b_pold))) return CCX_ERR_ARG;
+    ccx_net_tc *tc = tc_of(h, false);
+    if (!h->net_acc || !h->net_acc->wb || !tc || !tc->fb) return CCX_ERR_STATE;
+    ccx_net_acc &a = *h->net_acc;
+    if (n == 0) return CCX_OK;
+    if (a.cap < n) {
+        if (a.polc) CCX_CUDA(h, cudaFree(a.polc));
+        a.polc = nullptr; a.cap = 0;
+        CCX_CUDA(h, cudaMalloc(&a.polc, sizeof(float) * 400 * (size_t)n));
+        a.cap = n;
+    }
+    int64_t tiles = (n + acl::POS - 1) / acl::POS;
+    unsigned grid = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, h->stream>>>(a.wb, tc->fb, planes, n, a.polc, value);
+    CCX_LAUNCHED(h);
+    k_policy_dense_f32<<<(unsigned)((n + PDF_POS - 1) / PDF_POS), 320, 0, h->stream>>>(w_pold, b_pold, a.polc, n, logits);
+    CCX_LAUNCHED(h);
+    return CCX_OK;
+}
+
+}  // extern "C"

@@ -110,6 +110,31 @@ def pack_weights_tc(w, fp16=False):
     return blob, floats
 
 
+def pack_weights_acc(w):
+    """Keras tensors -> operand blob of the accurate tensor-core mode (csrc/ccx_net_tc.cu, namespace acl): every BN-folded
+    matrix as [hi: N x (K+16) with the bias columns][lo: N x K], hi = round_half(W), lo = round_half(W - hi)."""
+    ops = []
+
+    def split(Wt, bias):
+        Wt = np.asarray(Wt, dtype=np.float64)
+        hi = torch.from_numpy(Wt).to(torch.float32).to(torch.float16).to(torch.float64).numpy()
+        lo = Wt - hi
+        ops.append(_op_layout(_with_bias_columns(hi, bias, True), True))
+        ops.append(_op_layout(lo, True))
+    m, b = _fold(w, 1)
+    split(np.pad(m, ((0, 1), (0, 0))).T, b)
+    mp, bp = _fold(w, 29)
+    mv, bv = _fold(w, 30)
+    heads = np.zeros((64, 32)); heads[:, :16] = mp; heads[:, 16] = mv[:, 0]
+    hb = np.zeros(32); hb[:16] = bp; hb[16] = bv[0]
+    split(heads.T, hb)
+    for blk in range(9):
+        for i in (2 + 3 * blk, 3 + 3 * blk, 4 + 3 * blk):
+            m, b = _fold(w, i)
+            split(m.T, b)
+    return np.ascontiguousarray(np.concatenate(ops))
+
+
 class Model:
     """model.py:15-47"""
 
@@ -141,6 +166,12 @@ class ResidualCNN(Model):
         self.set_kernel(self.kernel)
         return self
 
+    def _load_acc(self):
+        blob = pack_weights_acc(self._weights)
+        assert blob.nbytes == self.eng.L.ccx_net_acc_blob_bytes()
+        self.eng.call("ccx_net_load_acc", ctypes.c_void_p(blob.ctypes.data), blob.nbytes)
+        self._acc_loaded = True
+
     def _load_tc(self):
         blob, floats = pack_weights_tc(self._weights, fp16=self.tc_dtype == "fp16")
         assert blob.nbytes == self.eng.L.ccx_net_tc_blob_bytes() and floats.size == self.eng.L.ccx_net_tc_num_floats()
@@ -148,8 +179,9 @@ class ResidualCNN(Model):
                       floats.size, 1 if self.tc_dtype == "fp16" else 0)
 
     def set_kernel(self, kernel, tc_dtype=None):
-        """'tc' = tcgen05 tensor-core kernels (default; operands bf16 or fp16, fp32 accumulation), 'simt' = fp32 SIMT kernel."""
-        assert kernel in ("tc", "simt")
+        """'tc' = tcgen05 tensor-core kernels (default; operands bf16 or fp16, fp32 accumulation), 'tc_acc' = the same in split
+        precision (hi + lo halves of activations and weights: fp32-level accuracy at ~1/3 of the speed), 'simt' = fp32 SIMT kernel."""
+        assert kernel in ("tc", "simt", "tc_acc")
         self.kernel = kernel
         if tc_dtype is not None and tc_dtype != self.tc_dtype:
             assert tc_dtype in ("bf16", "fp16")
@@ -157,7 +189,9 @@ class ResidualCNN(Model):
             if self.loaded:
                 self._load_tc()
         if self.loaded:
-            self.eng.call("ccx_net_set_mode", 1 if kernel == "tc" else 0)
+            if kernel == "tc_acc" and not getattr(self, "_acc_loaded", False):
+                self._load_acc()
+            self.eng.call("ccx_net_set_mode", {"simt": 0, "tc": 1, "tc_acc": 2}[kernel])
         return self
 
     # -- batched inference ---------------------------------------------------------------------------
@@ -169,11 +203,11 @@ class ResidualCNN(Model):
         n = planes.shape[0]
         logits = self.eng.empty((n, NUM_ACTIONS), torch.float32)
         value = self.eng.empty((n,), torch.float32)
-        if self.kernel == "tc":
+        if self.kernel in ("tc", "tc_acc"):
             if planes.dtype != torch.uint8:
                 planes = planes.to(torch.uint8)          # plane values are the integers 0..6 (utils.py:123-128)
-            self.eng.call("ccx_net_forward_tc", n, ctypes.c_void_p(planes.data_ptr()), ctypes.c_void_p(logits.data_ptr()),
-                          ctypes.c_void_p(value.data_ptr()))
+            self.eng.call("ccx_net_forward_tc" if self.kernel == "tc" else "ccx_net_forward_u8", n, ctypes.c_void_p(planes.data_ptr()),
+                          ctypes.c_void_p(logits.data_ptr()), ctypes.c_void_p(value.data_ptr()))
             return logits, value
         self.eng.call("ccx_net_forward", n, ctypes.c_void_p(planes.data_ptr()), dt,
                       ctypes.c_void_p(logits.data_ptr()), ctypes.c_void_p(value.data_ptr()))

@@ -147,3 +147,22 @@ def test_fused_round_loop_two_stream_split_is_bit_identical(model):
     b = m.search_net(roots, pre_expand=True, root_noise=noise)
     assert torch.equal(a["visits"], b["visits"]) and torch.equal(a["q"].view(torch.int64), b["q"].view(torch.int64))
     assert torch.equal(a["n_nodes"], b["n_nodes"])
+
+
+def test_accurate_tensor_core_mode_meets_the_1e3_bar(model, gold):
+    """split-precision tcgen05 path (hi + lo halves of activations and weights, fp32 policy dense): the north_star's
+    |dp|, |dv| <= 1e-3 against the float64 restatement, with margin; argmax agreement 100 %"""
+    planes = torch.from_numpy(gold["planes"]).cuda()
+    model.set_kernel("tc_acc")
+    l, v = model.forward(planes)
+    p_ref = net_ref.softmax64(gold["logits"])
+    p = net_ref.softmax64(l.cpu().numpy())
+    dp = np.abs(p - p_ref).max()
+    dv = np.abs(v.cpu().numpy() - gold["v"]).max()
+    dl = np.abs(l.cpu().numpy() - gold["logits"]).max()
+    print("tc_acc: max|dlogit| %.4g max|dp| %.4g max|dv| %.4g" % (dl, dp, dv))
+    assert dp < 1e-4 and dv < 1e-4 and (p.argmax(1) == p_ref.argmax(1)).all()
+    for n in (1, 3, 4, 5, 130):                                      # ragged batches
+        l2, v2 = model.forward(planes[:n])
+        assert torch.equal(l2, l[:n]) and torch.equal(v2, v[:n])
+    model.set_kernel("tc")
