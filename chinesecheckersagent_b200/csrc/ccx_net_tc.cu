@@ -764,16 +764,14 @@ constexpr int THREADS = 256, POS = 4, POS_ROWS = 30, LIVE_ROWS = 120;
 constexpr int YROWS = 130, Y_LBO = YROWS * 16, Y_COPY = 4 * Y_LBO;
 constexpr int T_X = 0, T_XH = 64, T_XL = 96, T_AO = 128;                   // TMEM columns (256 allocated)
 constexpr int S_YH = 0, S_YL = S_YH + 3 * Y_COPY;
-constexpr int S_WC1 = S_YL + 3 * Y_COPY;
-constexpr int S_WA = S_WC1 + B_CONV1, S_WB = S_WA + B_A, S_WC = S_WB + B_B;
+constexpr int S_WA = S_YL + 3 * Y_COPY, S_WB = S_WA + B_A, S_WC = S_WB + B_B;     // slot B also carries conv1's weights at tile starts
 constexpr int S_ONES = S_WC + B_C;
-constexpr int S_F = S_ONES + 128 * 16 * 2;
-constexpr int S_PLANES = S_F + tc4::F_BYTES;
+constexpr int S_PLANES = S_ONES + 128 * 16 * 2;
 constexpr int S_VALC = S_PLANES + 1376;
 constexpr int S_TOTAL = S_VALC + 512;
-static_assert(S_TOTAL <= 227 * 1024, "fits one CTA");
-static_assert(S_YL % 128 == 0 && S_WC1 % 128 == 0 && S_WA % 128 == 0 && S_WB % 128 == 0 && S_WC % 128 == 0 && S_ONES % 128 == 0 &&
-              S_F % 16 == 0 && S_PLANES % 16 == 0, "alignment");
+static_assert(B_CONV1 <= B_B, "conv1's weights fit in slot B");
+static_assert(S_TOTAL <= 113 * 1024, "two CTAs per SM");
+static_assert(S_YL % 128 == 0 && S_WA % 128 == 0 && S_WB % 128 == 0 && S_WC % 128 == 0 && S_ONES % 128 == 0 && S_PLANES % 16 == 0, "alignment");
 }  // namespace acl
 
 // (hi, lo) halves of two fp32 values: hi = round16(x), lo = round16(x - hi)
@@ -786,7 +784,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     lo = *reinterpret_cast<uint32_t *>(&l);
 }
 
-__global__ void __launch_bounds__(acl::THREADS, 1)
+__global__ void __launch_bounds__(acl::THREADS, 2)
 k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
                 float *__restrict__ polc, float *__restrict__ value)
 {
@@ -802,7 +800,6 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     const bool live = r < LIVE_ROWS && cx < 5;
     const int cell = cy * 5 + cx;
     const uint32_t sbase = umma::smem_u32(smem);
-    const float *sF = reinterpret_cast<const float *>(smem + S_F);
     const int64_t n_tiles = (n + POS - 1) / POS;
 
     auto refill_slot = [&](int slot, int dst, const uint8_t *src, uint32_t bytes) {
@@ -815,8 +812,7 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         for (int i = t; i < POS * 343; i += THREADS) smem[S_PLANES + i] = i < bytes ? __ldg(src + i) : (uint8_t)0;
     };
 
-    for (int i = t; i < S_WC1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows of both copy sets
-    for (int i = t; i < tc4::NF; i += THREADS) reinterpret_cast<float *>(smem + S_F)[i] = __ldg(fb + tcl::F_D1W + i);
+    for (int i = t; i < S_WA / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows of both copy sets
     for (int i = t; i < 128 * 2; i += THREADS) {
         const int rr = i >> 1, chunk = i & 1;
         *reinterpret_cast<uint4 *>(smem + S_ONES + umma::op_offset(rr, chunk * 8, 16)) = make_uint4(chunk == 0 ? pack2<FP16>(1.f, 1.f) : 0u, 0u, 0u, 0u);
@@ -826,9 +822,8 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
 #pragma unroll
         for (int q = 0; q < 4; q++) umma::mbar_init(&barW[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        refill_slot(3, S_WC1, wb + W_CONV1, B_CONV1);
+        refill_slot(1, S_WB, wb + W_CONV1, B_CONV1);                     // slot B: conv1 first, conv B of block 0 right after it
         refill_slot(0, S_WA, wb + W_BLOCK0 + W_BA, B_A);
-        refill_slot(1, S_WB, wb + W_BLOCK0 + W_BB, B_B);
         refill_slot(2, S_WC, wb + W_BLOCK0 + W_BC, B_C);
     }
     if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
@@ -836,13 +831,12 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     __syncthreads();
     umma::fence_after_sync();
     uint32_t phW0 = 0, phW1 = 0, phW2 = 0;
-    bool conv1_ready = false;
     const uint32_t tmem = tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(rg * 32) << 16);
     uint32_t phase = 0;
     // operand descriptors: hi parts carry the 16 bias columns (K + 16 layout), lo parts follow them in the slot (K layout)
     const umma::DescBase dYH = umma::desc_base(sbase + S_YH, Y_LBO, 128u), dYL = umma::desc_base(sbase + S_YL, Y_LBO, 128u);
-    const umma::DescBase dC1H = umma::desc_base(sbase + S_WC1, 128u, 80 / 8 * 128u), dC1L = umma::desc_base(sbase + S_WC1 + hi_b(64, 64), 128u, 64 / 8 * 128u);
+    const umma::DescBase dC1H = umma::desc_base(sbase + S_WB, 128u, 80 / 8 * 128u), dC1L = umma::desc_base(sbase + S_WB + hi_b(64, 64), 128u, 64 / 8 * 128u);
     const umma::DescBase dAH = umma::desc_base(sbase + S_WA, 128u, 80 / 8 * 128u), dAL = umma::desc_base(sbase + S_WA + hi_b(32, 64), 128u, 64 / 8 * 128u);
     const umma::DescBase dBH = umma::desc_base(sbase + S_WB, 128u, 304 / 8 * 128u), dBL = umma::desc_base(sbase + S_WB + hi_b(32, 288), 128u, 288 / 8 * 128u);
     const umma::DescBase dCH = umma::desc_base(sbase + S_WC, 128u, 48 / 8 * 128u), dCL = umma::desc_base(sbase + S_WC + hi_b(64, 32), 128u, 32 / 8 * 128u);
@@ -901,7 +895,7 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         if (warp == 0) {
             umma::fence_after_sync();
             if (umma::elect_one()) {
-                if (!conv1_ready) { umma::mbar_wait(&barW[3], 0); conv1_ready = true; }
+                umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
                 bias_mma(tmem + T_X, dC1H, 64, ID64, false);
                 umma::gemm_issue_ts<64>(tmem + T_X, tmem + T_XH, dC1H, 0, ID64, true);
                 umma::gemm_issue_ts<64>(tmem + T_X, tmem + T_XH, dC1L, 0, ID64, true);
@@ -910,6 +904,7 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
             __syncwarp();
         }
         wait_mma();
+        if (warp == 0 && umma::elect_one()) refill_slot(1, S_WB, wb + W_BLOCK0 + W_BB, B_B);       // conv B of block 0 (needed two phases from now)
         finish_x();
         for (int b = 0; b < 9; b++) {
             const uint8_t *wnext = wb + W_BLOCK0 + ((b + 1) % 9) * W_BLOCK;
@@ -971,7 +966,10 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
                 __syncwarp();
             }
             wait_mma();
-            if (warp == 0 && umma::elect_one()) refill_slot(1, S_WB, wnext + W_BB, B_B);
+            if (warp == 0 && umma::elect_one()) {
+                if (b < 8) refill_slot(1, S_WB, wnext + W_BB, B_B);
+                else refill_slot(1, S_WB, wb + W_CONV1, B_CONV1);           // conv1 of the next tile
+            }
             {
                 float v[16];
                 umma::tmem_ld16(trow + T_AO + h * 16, v);
@@ -1033,18 +1031,17 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
         __syncthreads();
         if (warp < n_pos) {
             const float *valc = reinterpret_cast<const float *>(smem + S_VALC) + warp * 25;
-            float acc = sF[tc4::FO_D1B + lane];
-            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], sF[tc4::FO_D1W + k * 32 + lane], acc);
-            float sv = fmaxf(acc, 0.f) * sF[tc4::FO_VHW + lane];
+            float acc = __ldg(fb + tcl::F_D1B + lane);
+            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], __ldg(fb + tcl::F_D1W + k * 32 + lane), acc);
+            float sv = fmaxf(acc, 0.f) * __ldg(fb + tcl::F_VHW + lane);
 #pragma unroll
             for (int off = 16; off; off >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, off);
-            if (lane == 0) value[pos0 + warp] = tanhf(sv + sF[tc4::FO_VHB]);
+            if (lane == 0) value[pos0 + warp] = tanhf(sv + __ldg(fb + tcl::F_VHB));
         }
         __syncthreads();
     }
     if (warp == 0 && umma::elect_one()) {
         umma::mbar_wait(&barW[0], phW0); umma::mbar_wait(&barW[1], phW1); umma::mbar_wait(&barW[2], phW2);
-        if (!conv1_ready) umma::mbar_wait(&barW[3], 0);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -1120,7 +1117,7 @@ int ccx_net_forward_acc(ccx_handle *h, int64_t n, const uint8_t *planes, float *
         a.cap = n;
     }
     int64_t tiles = (n + acl::POS - 1) / acl::POS;
-    unsigned grid = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);
+    unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);       // two resident CTAs per SM
     k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, h->stream>>>(a.wb, tc->fb, planes, n, a.polc, value);
     CCX_LAUNCHED(h);
     k_policy_dense_f32<<<(unsigned)((n + PDF_POS - 1) / PDF_POS), 320, 0, h->stream>>>(w_pold, b_pold, a.polc, n, logits);

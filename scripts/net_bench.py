@@ -6,6 +6,8 @@ from chinesecheckersagent_b200.engine import Engine
 from chinesecheckersagent_b200.model import ResidualCNN
 m = ResidualCNN(engine=Engine(0)).load_weights(os.path.join(ROOT, 'tests', 'golden', 'good_model_weights.npz'))
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+kernel = sys.argv[2] if len(sys.argv) > 2 else 'tc'
+m.set_kernel(kernel)
 for n in (4096, 65536):
     x = torch.randint(0, 7, (n, 7, 7, 7), dtype=torch.uint8, device='cuda')
     for _ in range(3): m.forward(x)
@@ -15,4 +17,4 @@ for n in (4096, 65536):
     for _ in range(reps): m.forward(x)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
-    print('tc forward %d positions: %.4f ms -> %.4g positions/s, %.1f TFLOP/s' % (n, ms, n / ms * 1e3, 6.483264e6 * n / ms / 1e9))
+    print(kernel + ' forward %d positions: %.4f ms -> %.4g positions/s, %.1f TFLOP/s' % (n, ms, n / ms * 1e3, 6.483264e6 * n / ms / 1e9))
