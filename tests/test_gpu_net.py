@@ -166,3 +166,16 @@ def test_accurate_tensor_core_mode_meets_the_1e3_bar(model, gold):
         l2, v2 = model.forward(planes[:n])
         assert torch.equal(l2, l[:n]) and torch.equal(v2, v[:n])
     model.set_kernel("tc")
+
+
+def test_accurate_mode_in_the_fused_mcts_rounds(model):
+    """ccx_mcts_run_net with the accurate net = the select / ccx_net_eval / expand_backup round trips in the same mode"""
+    from chinesecheckersagent_b200.engine import BatchedMCTS
+    model.set_kernel("tc_acc")
+    st, _, _ = orc.step_random(orc.start_states(200), 31, 0, 8)
+    roots = torch.from_numpy(np.ascontiguousarray(st).view(np.int64)).cuda()
+    m = BatchedMCTS(model.eng, num_itr=30)
+    a = m.search_with(roots, model.evaluate_states)
+    b = m.search_net(roots)
+    assert torch.equal(a["visits"], b["visits"]) and torch.equal(a["q"].view(torch.int64), b["q"].view(torch.int64))
+    model.set_kernel("tc")
