@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(320)
 k_policy_dense_f32(const float *__restrict__ W, const float *__restrict__ bias, const float *__restrict__ polc, int64_t n,
                    float *__restrict__ logits)
 {
-    __shared__ float sA[PDF_POS][400];
+    __shared__ __align__(16) float sA[PDF_POS][400];
     const int64_t row0 = (int64_t)blockIdx.x * PDF_POS;
     const int rows = (int)min((int64_t)PDF_POS, n - row0);
     for (int i = threadIdx.x; i < PDF_POS * 400; i += blockDim.x) sA[i / 400][i % 400] = (i / 400) < rows ? polc[(row0 + i / 400) * 400 + i % 400] : 0.f;
@@ -1066,10 +1066,18 @@ k_policy_dense_f32(const float *__restrict__ W, const float *__restrict__ bias, 
     float acc[PDF_POS];
 #pragma unroll
     for (int p = 0; p < PDF_POS; p++) acc[p] = 0.f;
-    for (int k = 0; k < 400; k++) {
-        const float w = __ldg(W + k * CCX_NUM_ACTIONS + col);
+    for (int k = 0; k < 400; k += 8) {                       // eight independent weight loads in flight per thread
+        float w[8];
 #pragma unroll
-        for (int p = 0; p < PDF_POS; p++) acc[p] = fmaf(sA[p][k], w, acc[p]);
+        for (int q = 0; q < 8; q++) w[q] = __ldg(W + (k + q) * CCX_NUM_ACTIONS + col);
+#pragma unroll
+        for (int p = 0; p < PDF_POS; p++) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&sA[p][k]), a1 = *reinterpret_cast<const float4 *>(&sA[p][k + 4]);
+            float s = acc[p];
+            s = fmaf(a0.x, w[0], s); s = fmaf(a0.y, w[1], s); s = fmaf(a0.z, w[2], s); s = fmaf(a0.w, w[3], s);
+            s = fmaf(a1.x, w[4], s); s = fmaf(a1.y, w[5], s); s = fmaf(a1.z, w[6], s); s = fmaf(a1.w, w[7], s);
+            acc[p] = s;
+        }
     }
     const float b = __ldg(bias + col);
     for (int p = 0; p < rows; p++) logits[(row0 + p) * CCX_NUM_ACTIONS + col] = acc[p] + b;
