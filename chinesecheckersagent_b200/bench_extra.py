@@ -98,7 +98,7 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
     if os.path.exists(weights):
         from .model import ResidualCNN
         from .selfplay import BatchedSelfPlay, all_gather_trajectories
-        model = ResidualCNN(engine=eng).load_weights(weights)
+        model = ResidualCNN(engine=eng).load_weights(weights).set_kernel("tc")       # the throughput mode; the accurate default is timed below
         sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=MCTS_TREES, seed=DEFAULT_SEED, rank=rank, world=world,
                              num_itr=MCTS_SIMS, max_iters=16)
         for _ in range(7):                                # 6 opening plies + 1 searched ply as warm-up

@@ -15,7 +15,7 @@ BatchedMCTS(eng, num_itr=12).search(env.state)
 m = ResidualCNN(engine=eng).load_weights(os.path.join(ROOT, 'tests', 'golden', 'good_model_weights.npz'))
 for n in (3, 130):
     x = torch.randint(0, 7, (n, 7, 7, 7), dtype=torch.uint8, device='cuda')
-    m.set_kernel('tc'); m.forward(x); m.set_kernel('simt'); m.forward(x)
+    m.set_kernel('tc'); m.forward(x); m.set_kernel('tc_acc'); m.forward(x); m.set_kernel('simt'); m.forward(x)
 m.set_kernel('tc')
 BatchedMCTS(eng, num_itr=6).search_net(env.state[:, :70].contiguous())
 sp = BatchedSelfPlay(eng, m.evaluate_states, n_slots=33, num_itr=5, max_iters=10)
