@@ -759,7 +759,14 @@ constexpr int B_CONV1 = hi_b(64, 64) + lo_b(64, 64), B_HEADS = hi_b(32, 64) + lo
 constexpr int B_A = hi_b(32, 64) + lo_b(32, 64), B_B = hi_b(32, 288) + lo_b(32, 288), B_C = hi_b(64, 32) + lo_b(64, 32);
 constexpr int W_CONV1 = 0, W_HEADS = B_CONV1, W_BLOCK0 = W_HEADS + B_HEADS, W_BLOCK = B_A + B_B + B_C;
 constexpr int W_BA = 0, W_BB = B_A, W_BC = B_A + B_B;
-constexpr int W_TOTAL = W_BLOCK0 + 9 * W_BLOCK;
+constexpr int W_POLD = W_BLOCK0 + 9 * W_BLOCK;                 // policy dense: 2 N-halves x 4 K-chunks (112, 96, 96, 96) x [hi (N160, Kc) | lo (N160, Kc)]
+__host__ __device__ constexpr int pd_kc(int c) { return c == 0 ? 112 : 96; }          // multiples of 16 (one MMA = K 16)
+__host__ __device__ constexpr int pd_k0(int c) { return c == 0 ? 0 : c == 1 ? 112 : c == 2 ? 208 : 304; }
+constexpr int POLD_HALF = 2 * 160 * 400 * 2;
+__host__ __device__ constexpr int pd_w_off(int half, int c) { return W_POLD + half * POLD_HALF + 2 * 160 * pd_k0(c) * 2; }   // hi slice; lo follows at + 160*Kc*2
+constexpr int W_TOTAL = W_POLD + 2 * POLD_HALF;
+constexpr int PD_TILE_B = 128 * 400 * 2;                       // one 128-position tile of policy-conv activations (hi or lo), 4 K-chunks
+__host__ __device__ constexpr int pd_a_off(int c) { return 128 * pd_k0(c) * 2; }
 constexpr int THREADS = 256, POS = 4, POS_ROWS = 30, LIVE_ROWS = 120;
 constexpr int YROWS = 130, Y_LBO = YROWS * 16, Y_COPY = 4 * Y_LBO;
 constexpr int T_X = 0, T_XH = 64, T_XL = 96, T_AO = 128;                   // TMEM columns (256 allocated)
@@ -786,7 +793,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
 
 __global__ void __launch_bounds__(acl::THREADS, 2)
 k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
-                float *__restrict__ polc, float *__restrict__ value)
+                uint8_t *__restrict__ polc_h, uint8_t *__restrict__ polc_l, float *__restrict__ value)
 {
     using namespace acl;
     constexpr bool FP16 = true;
@@ -1018,10 +1025,20 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
             umma::tmem_ld16(trow + T_AO + h * 16, v);
             if (live && p_local < n_pos) {
                 if (h == 0) {
-                    float4 *dst = reinterpret_cast<float4 *>(polc + (pos0 + p_local) * 400 + cell * 16);       // Flatten in (y, x, c) order, fp32
+                    // Flatten in (y, x, c) order = K index cell * 16 + c, written as hi / lo halves straight in the accurate policy
+                    // dense kernel's A-operand layout (128-position tiles of four K-chunks)
+                    uint32_t ph[8], pl[8];
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        dst[q] = make_float4(fmaxf(v[4 * q], 0.f), fmaxf(v[4 * q + 1], 0.f), fmaxf(v[4 * q + 2], 0.f), fmaxf(v[4 * q + 3], 0.f));
+                    for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q], 0.f), fmaxf(v[2 * q + 1], 0.f), ph[q], pl[q]);
+                    const int64_t pos = pos0 + p_local;
+#pragma unroll
+                    for (int part = 0; part < 2; part++) {               // the cell's channels 0-7 and 8-15 may fall into different chunks
+                        const int k = cell * 16 + part * 8;
+                        const int c = k >= 304 ? 3 : k >= 208 ? 2 : k >= 112 ? 1 : 0;
+                        const int64_t off = (pos >> 7) * PD_TILE_B + pd_a_off(c) + umma::op_offset((int)(pos & 127), k - pd_k0(c), pd_kc(c));
+                        *reinterpret_cast<uint4 *>(polc_h + off) = make_uint4(ph[4 * part], ph[4 * part + 1], ph[4 * part + 2], ph[4 * part + 3]);
+                        *reinterpret_cast<uint4 *>(polc_l + off) = make_uint4(pl[4 * part], pl[4 * part + 1], pl[4 * part + 2], pl[4 * part + 3]);
+                    }
                 } else {
                     reinterpret_cast<float *>(smem + S_VALC)[p_local * 25 + cell] = fmaxf(v[0], 0.f);
                 }
@@ -1048,42 +1065,103 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     if (warp == 0) umma::tmem_free(tmem, 256);
 }
 
-// policy dense layer in fp32: logits[B x 294] = polc[B x 400] * W[400 x 294] + b.  30 positions per block (their activations
-// in shared memory, 48,000 B), one thread per output column holding 30 accumulators; W (fp32, row-major [400][294]) is read
-// once per block.
-#define PDF_POS 30
-__global__ void __launch_bounds__(320)
-k_policy_dense_f32(const float *__restrict__ W, const float *__restrict__ bias, const float *__restrict__ polc, int64_t n,
-                   float *__restrict__ logits)
+// Accurate policy dense: logits = flat(policy conv)[B x 400] * W + b in split precision, 128 positions x 80 outputs per CTA.
+// Four K-chunks (112, 96, 96, 96) stream through two shared-memory stages, each holding the chunk's hi and lo halves of the
+// activations (written in this layout by k_net_trunk_acc) and of the quarter's weight rows; per chunk the issuing lane fires
+// A_hi*W_hi + A_lo*W_hi + A_hi*W_lo and commits to the stage's "consumed" barrier so that the chunk after next can land.
+namespace pda {
+constexpr int NQ = 80;
+constexpr int A_B = 128 * 112 * 2, W_B = NQ * 112 * 2;                 // sized for the largest chunk
+constexpr int ST_AH = 0, ST_AL = A_B, ST_WH = 2 * A_B, ST_WL = 2 * A_B + W_B, STAGE_B = 2 * A_B + 2 * W_B;
+constexpr int S_TOTAL = 2 * STAGE_B;                                   // 186,368 B
+constexpr int OUT_LD = NQ + 1;
+static_assert(128 * OUT_LD * 4 <= STAGE_B, "fp32 staging fits in stage 0");
+}  // namespace pda
+
+__global__ void __launch_bounds__(128, 1)
+k_policy_dense_acc(const uint8_t *__restrict__ wb, const float *__restrict__ bias, const uint8_t *__restrict__ polc_h,
+                   const uint8_t *__restrict__ polc_l, int64_t n, float *__restrict__ logits)
 {
-    __shared__ __align__(16) float sA[PDF_POS][400];
-    const int64_t row0 = (int64_t)blockIdx.x * PDF_POS;
-    const int rows = (int)min((int64_t)PDF_POS, n - row0);
-    for (int i = threadIdx.x; i < PDF_POS * 400; i += blockDim.x) sA[i / 400][i % 400] = (i / 400) < rows ? polc[(row0 + i / 400) * 400 + i % 400] : 0.f;
-    __syncthreads();
-    const int col = threadIdx.x;
-    if (col >= CCX_NUM_ACTIONS) return;
-    float acc[PDF_POS];
+    using namespace pda;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar, full[2], empty[2];
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    const int quarter = blockIdx.y, half = quarter >> 1, c0 = (quarter & 1) * NQ;
+    const int64_t row0 = (int64_t)blockIdx.x * 128;
+    const uint32_t sbase = umma::smem_u32(smem);
+    if (t == 0) {
+        umma::mbar_init(&bar, 1);
 #pragma unroll
-    for (int p = 0; p < PDF_POS; p++) acc[p] = 0.f;
-    for (int k = 0; k < 400; k += 8) {                       // eight independent weight loads in flight per thread
-        float w[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) w[q] = __ldg(W + (k + q) * CCX_NUM_ACTIONS + col);
-#pragma unroll
-        for (int p = 0; p < PDF_POS; p++) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(&sA[p][k]), a1 = *reinterpret_cast<const float4 *>(&sA[p][k + 4]);
-            float s = acc[p];
-            s = fmaf(a0.x, w[0], s); s = fmaf(a0.y, w[1], s); s = fmaf(a0.z, w[2], s); s = fmaf(a0.w, w[3], s);
-            s = fmaf(a1.x, w[4], s); s = fmaf(a1.y, w[5], s); s = fmaf(a1.z, w[6], s); s = fmaf(a1.w, w[7], s);
-            acc[p] = s;
-        }
+        for (int q = 0; q < 2; q++) { umma::mbar_init(&full[q], 1); umma::mbar_init(&empty[q], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const float b = __ldg(bias + col);
-    for (int p = 0; p < rows; p++) logits[(row0 + p) * CCX_NUM_ACTIONS + col] = acc[p] + b;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    constexpr uint32_t ID = umma::make_idesc(NQ, true);
+    if (warp == 0) {
+        if (umma::elect_one()) {
+            auto load_chunk = [&](int c, int st) {
+                const int Kc = acl::pd_kc(c);
+                const uint32_t ab = 128 * Kc * 2, wbytes = NQ * Kc * 2;
+                const int64_t aoff = (int64_t)blockIdx.x * acl::PD_TILE_B + acl::pd_a_off(c);
+                const uint8_t *wh = wb + acl::pd_w_off(half, c) + (c0 / 8) * (Kc / 8) * 128;          // this quarter's 80 rows: a contiguous slice
+                const uint8_t *wl = wh + 160 * Kc * 2;
+                umma::mbar_expect_tx(&full[st], 2 * ab + 2 * wbytes);
+                umma::bulk_g2s(sbase + st * STAGE_B + ST_AH, polc_h + aoff, ab, &full[st]);
+                umma::bulk_g2s(sbase + st * STAGE_B + ST_AL, polc_l + aoff, ab, &full[st]);
+                umma::bulk_g2s(sbase + st * STAGE_B + ST_WH, wh, wbytes, &full[st]);
+                umma::bulk_g2s(sbase + st * STAGE_B + ST_WL, wl, wbytes, &full[st]);
+            };
+            load_chunk(0, 0);
+            load_chunk(1, 1);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int st = c & 1, Kc = acl::pd_kc(c);
+                umma::mbar_wait(&full[st], (uint32_t)(c >> 1) & 1u);
+                const uint32_t sb = sbase + st * STAGE_B;
+                const umma::DescBase dAH = umma::desc_base(sb + ST_AH, 128u, (uint32_t)(Kc / 8) * 128u), dAL = umma::desc_base(sb + ST_AL, 128u, (uint32_t)(Kc / 8) * 128u);
+                const umma::DescBase dWH = umma::desc_base(sb + ST_WH, 128u, (uint32_t)(Kc / 8) * 128u), dWL = umma::desc_base(sb + ST_WL, 128u, (uint32_t)(Kc / 8) * 128u);
+                for (int s = 0; s < Kc / 16; s++) {
+                    const uint32_t ko = (uint32_t)(2 * s) * 128u;
+                    umma::mma_bf16(tmem, umma::desc_at(dAH, ko), umma::desc_at(dWH, ko), ID, c > 0 || s > 0);
+                    umma::mma_bf16(tmem, umma::desc_at(dAL, ko), umma::desc_at(dWH, ko), ID, true);
+                    umma::mma_bf16(tmem, umma::desc_at(dAH, ko), umma::desc_at(dWL, ko), ID, true);
+                }
+                if (c + 2 < 4) {
+                    umma::commit(&empty[st]);                              // stage consumed -> the chunk after next may land
+                    umma::mbar_wait(&empty[st], 0);
+                    load_chunk(c + 2, st);
+                }
+            }
+            umma::commit(&bar);
+        }
+        __syncwarp();
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    float *stage = reinterpret_cast<float *>(smem);
+#pragma unroll
+    for (int c = 0; c < NQ; c += 16) {
+        float v[16];
+        umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 16; j++) stage[t * OUT_LD + c + j] = v[j];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    const int col_base = half * 160 + c0;
+    for (int i = t; i < 128 * NQ; i += 128) {
+        const int r = i / NQ, c = i % NQ, col = col_base + c;
+        if (row0 + r < n && col < CCX_NUM_ACTIONS) logits[(row0 + r) * CCX_NUM_ACTIONS + col] = stage[r * OUT_LD + c] + __ldg(bias + col);
+    }
+    if (warp == 0) umma::tmem_free(tmem, 128);
 }
 
-struct ccx_net_acc { uint8_t *wb = nullptr; float *polc = nullptr; int64_t cap = 0; };
+struct ccx_net_acc { uint8_t *wb = nullptr; uint8_t *polc = nullptr; int64_t cap = 0; };      // polc: hi tiles then lo tiles
 
 void ccx_net_acc_free(ccx_handle *h)
 {
@@ -1107,6 +1185,7 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
     CCX_CUDA(h, cudaMemcpyAsync(a.wb, blob_host, acl::W_TOTAL, cudaMemcpyHostToDevice, h->stream));
     CCX_CUDA(h, cudaStreamSynchronize(h->stream));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, acl::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, pda::S_TOTAL));
     return CCX_OK;
 }
 
@@ -1118,17 +1197,21 @@ int ccx_net_forward_acc(ccx_handle *h, int64_t n, const uint8_t *planes, float *
     if (!h->net_acc || !h->net_acc->wb || !tc || !tc->fb) return CCX_ERR_STATE;
     ccx_net_acc &a = *h->net_acc;
     if (n == 0) return CCX_OK;
+    const size_t tile_bytes = (size_t)((n + 127) / 128) * acl::PD_TILE_B;
     if (a.cap < n) {
         if (a.polc) CCX_CUDA(h, cudaFree(a.polc));
         a.polc = nullptr; a.cap = 0;
-        CCX_CUDA(h, cudaMalloc(&a.polc, sizeof(float) * 400 * (size_t)n));
+        CCX_CUDA(h, cudaMalloc(&a.polc, 2 * tile_bytes));
+        CCX_CUDA(h, cudaMemsetAsync(a.polc, 0, 2 * tile_bytes, h->stream));           // rows past n of the last tile stay finite
         a.cap = n;
     }
+    uint8_t *polc_h = a.polc, *polc_l = a.polc + (size_t)((a.cap + 127) / 128) * acl::PD_TILE_B;
     int64_t tiles = (n + acl::POS - 1) / acl::POS;
     unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);       // two resident CTAs per SM
-    k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, h->stream>>>(a.wb, tc->fb, planes, n, a.polc, value);
+    k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, h->stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
     CCX_LAUNCHED(h);
-    k_policy_dense_f32<<<(unsigned)((n + PDF_POS - 1) / PDF_POS), 320, 0, h->stream>>>(w_pold, b_pold, a.polc, n, logits);
+    (void)w_pold;
+    k_policy_dense_acc<<<dim3((unsigned)((n + 127) / 128), 4), 128, pda::S_TOTAL, h->stream>>>(a.wb, b_pold, polc_h, polc_l, n, logits);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

@@ -132,6 +132,15 @@ def pack_weights_acc(w):
         for i in (2 + 3 * blk, 3 + 3 * blk, 4 + 3 * blk):
             m, b = _fold(w, i)
             split(m.T, b)
+    # policy dense (400 -> 294, padded to 320): 2 N-halves x 4 K-chunks (112, 96, 96, 96) x [hi (N160, Kc) | lo (N160, Kc)]
+    Wd = np.zeros((400, 320)); Wd[:, :294] = np.asarray(w["policy_head/kernel"], dtype=np.float64)
+    for half in range(2):
+        Wh = Wd[:, half * 160:(half + 1) * 160]
+        for k0, kc in ((0, 112), (112, 96), (208, 96), (304, 96)):
+            Wt = Wh[k0:k0 + kc].T
+            hi = torch.from_numpy(np.ascontiguousarray(Wt)).to(torch.float32).to(torch.float16).to(torch.float64).numpy()
+            ops.append(_op_layout(hi, True))
+            ops.append(_op_layout(Wt - hi, True))
     return np.ascontiguousarray(np.concatenate(ops))
 
 
