@@ -751,7 +751,7 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
 // 3.2e-3 on the largest probabilities (every layer group contributes: DESIGN.md §3); this mode brings the tensor-core
 // path to the fp32 restatement's ~1e-5 at three times the MMAs and twice the operand storage (one CTA per SM).
 // Operand blob (model.py pack_weights_acc): per matrix [hi: N x (K+16) with the bias columns][lo: N x K], UMMA layout:
-//   CONV1 | HEADS | 9 x [A | B | C].  The policy dense layer runs in fp32 on the fp32 copy of the weights (ccx_net_load).
+//   CONV1 | HEADS | 9 x [A | B | C] | policy dense (see acl::W_POLD).  Biases of the policy dense come from the fp32 weights (ccx_net_load).
 namespace acl {
 __host__ __device__ constexpr int hi_b(int N, int K) { return N * (K + 16) * 2; }
 __host__ __device__ constexpr int lo_b(int N, int K) { return N * K * 2; }

@@ -191,8 +191,8 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
 int ccx_net_forward_tc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value);
 int ccx_net_set_mode(ccx_handle *h, int32_t mode);
 /* Accurate tensor-core mode (ccx_net_set_mode(h, 2); needs ccx_net_load, ccx_net_load_tc and ccx_net_load_acc): every product
- * in split precision, a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with IEEE-half terms and fp32 accumulation, the policy dense layer in
- * fp32 — the tensor-core path at the fp32 restatement's accuracy (|dp|, |dv| << 1e-3).  The blob (model.py pack_weights_acc):
+ * in split precision, a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with IEEE-half terms and fp32 accumulation, policy dense layer
+ * included — the tensor-core path at the fp32 restatement's accuracy (|dp|, |dv| << 1e-3).  The blob (model.py pack_weights_acc):
  * per matrix [hi: N x (K+16), bias columns][lo: N x K] in the UMMA operand layout; HOST pointer. */
 /* forward pass of uint8 planes (n,7,7,7) in the mode selected by ccx_net_set_mode (0 fp32 SIMT, 1 tensor core, 2 accurate) */
 int ccx_net_forward_u8(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value);
