@@ -178,20 +178,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// D[128 x N] (+)= A * B^T with the A operand in the ROW-CONTIGUOUS layout: element (r, k) at
-// (k/8)*lbo_a + r*16 + (k%8)*2 (SBO = 128).  a_start already includes the row shift (16 B per row), so a 3x3
-// conv tap is the same buffer addressed one or more rows further on.  B as in gemm_issue.
-__device__ __forceinline__ void gemm_issue_rows(uint32_t tmem_d, uint32_t a_start, uint32_t lbo_a, uint32_t b_base, int Kb, int kb0,
-                                                int K, int N, bool accumulate_first, bool fp16 = false)
-{
-    const uint32_t idesc = make_idesc(N, fp16);
-#pragma unroll
-    for (int s = 0; s < K / 16; s++) {
-        uint64_t ad = make_desc(a_start + (uint32_t)(2 * s) * lbo_a, lbo_a, 128u);
-        uint64_t bd = make_desc(b_base + (uint32_t)((kb0 >> 3) + 2 * s) * 128u, 128u, (uint32_t)(Kb >> 3) * 128u);
-        mma_bf16(tmem_d, ad, bd, idesc, accumulate_first || s > 0);
-    }
-}
+// (row-contiguous A operands — element (r, k) at (k/8)*LBO + r*16 + (k%8)*2, SBO = 128 — are addressed by the kernels through
+// desc_base / desc_at with a start address that already includes the row shift: see k_net_trunk_tc4's conv B)
 
 // ---- A operand from TMEM (tcgen05.mma "ts" form): row r of A lives in TMEM lane r, two consecutive K elements
 // per 32-bit column (element 2j in the low half of column j); one MMA consumes K = 16 = 8 columns.
