@@ -75,3 +75,12 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), "%s references the oracle" % f
+
+
+def test_sass_uses_the_blackwell_tensor_path(lib_path):
+    """SASS evidence (B200_PROFILING.md): tcgen05.mma -> UTCHMMA, tcgen05.ld/st -> LDTM/STTM, bulk async copies -> UBLKCP,
+    and no legacy HMMA (mma.sync / wmma) anywhere in the library."""
+    out = subprocess.run(["cuobjdump", "-sass", lib_path], stdout=subprocess.PIPE, text=True).stdout
+    counts = {m: len(re.findall(r"\b%s\b" % m, out)) for m in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR")}
+    assert all(v > 0 for v in counts.values()), counts
+    assert not re.search(r"\bHMMA\b", out)
