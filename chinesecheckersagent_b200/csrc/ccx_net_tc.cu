@@ -750,7 +750,8 @@ namespace acl {
 __host__ __device__ constexpr int hi_b(int N, int K) { return N * (K + 16) * 2; }
 __host__ __device__ constexpr int lo_b(int N, int K) { return N * K * 2; }
 constexpr int B_CONV1 = hi_b(64, 64) + lo_b(64, 64), B_HEADS = hi_b(32, 64) + lo_b(32, 64);
-constexpr int B_A = hi_b(32, 64) + lo_b(32, 64), B_B = hi_b(32, 288) + lo_b(32, 288), B_C = hi_b(64, 32) + lo_b(64, 32);
+constexpr int B_A = hi_b(32, 64) + lo_b(32, 64), B_C = hi_b(64, 32) + lo_b(64, 32);
+constexpr int B_B = hi_b(64, 288);       // conv B: ONE [64 x 304] operand, rows 0-31 = hi (+ bias columns), rows 32-63 = lo: a_hi * [w_hi | w_lo] is a single N = 64 MMA
 constexpr int W_CONV1 = 0, W_HEADS = B_CONV1, W_BLOCK0 = W_HEADS + B_HEADS, W_BLOCK = B_A + B_B + B_C;
 constexpr int W_BA = 0, W_BB = B_A, W_BC = B_A + B_B;
 constexpr int W_POLD = W_BLOCK0 + 9 * W_BLOCK;                 // policy dense: 2 N-halves x 4 K-chunks (112, 96, 96, 96) x [hi (N160, Kc) | lo (N160, Kc)]
@@ -763,7 +764,7 @@ constexpr int PD_TILE_B = 128 * 400 * 2;                       // one 128-positi
 __host__ __device__ constexpr int pd_a_off(int c) { return 128 * pd_k0(c) * 2; }
 constexpr int THREADS = 256, POS = 4, POS_ROWS = 30, LIVE_ROWS = 120;
 constexpr int YROWS = 130, Y_LBO = YROWS * 16, Y_COPY = 4 * Y_LBO;
-constexpr int T_X = 0, T_XH = 64, T_XL = 96, T_AO = 128;                   // TMEM columns (256 allocated)
+constexpr int T_X = 0, T_XH = 64, T_XL = 96, T_AO = 128;                   // TMEM columns (256 allocated); AO is 64 wide for conv B
 constexpr int S_YH = 0, S_YL = S_YH + 3 * Y_COPY;
 constexpr int S_WA = S_YL + 3 * Y_COPY, S_WB = S_WA + B_A, S_WC = S_WB + B_B;     // slot B also carries conv1's weights at tile starts
 constexpr int S_ONES = S_WC + B_C;
@@ -839,7 +840,7 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     const umma::DescBase dYH = umma::desc_base(sbase + S_YH, Y_LBO, 128u), dYL = umma::desc_base(sbase + S_YL, Y_LBO, 128u);
     const umma::DescBase dC1H = umma::desc_base(sbase + S_WB, 128u, 80 / 8 * 128u), dC1L = umma::desc_base(sbase + S_WB + hi_b(64, 64), 128u, 64 / 8 * 128u);
     const umma::DescBase dAH = umma::desc_base(sbase + S_WA, 128u, 80 / 8 * 128u), dAL = umma::desc_base(sbase + S_WA + hi_b(32, 64), 128u, 64 / 8 * 128u);
-    const umma::DescBase dBH = umma::desc_base(sbase + S_WB, 128u, 304 / 8 * 128u), dBL = umma::desc_base(sbase + S_WB + hi_b(32, 288), 128u, 288 / 8 * 128u);
+    const umma::DescBase dBH = umma::desc_base(sbase + S_WB, 128u, 304 / 8 * 128u);          // rows 0-31 hi, rows 32-63 lo
     const umma::DescBase dCH = umma::desc_base(sbase + S_WC, 128u, 48 / 8 * 128u), dCL = umma::desc_base(sbase + S_WC + hi_b(64, 32), 128u, 32 / 8 * 128u);
     const umma::DescBase dONES = umma::desc_base(sbase + S_ONES, 128u, 16 / 8 * 128u);
     constexpr uint32_t ID32 = umma::make_idesc(32, FP16), ID64 = umma::make_idesc(64, FP16);
@@ -951,17 +952,18 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
                     umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
-                    bias_mma(tmem + T_AO, dBH, 288, ID32, false);
+                    // columns [0,32) of AO: bias + a_hi*w_hi + a_lo*w_hi; columns [32,64): a_hi*w_lo (summed in the epilogue)
+                    bias_mma(tmem + T_AO, dBH, 288, ID64, false);
 #pragma unroll
-                    for (int term = 0; term < 3; term++)
+                    for (int d = 0; d < 3; d++)
 #pragma unroll
-                        for (int d = 0; d < 3; d++)
+                        for (int dxi = 0; dxi < 3; dxi++)
 #pragma unroll
-                            for (int dxi = 0; dxi < 3; dxi++)
-#pragma unroll
-                                for (int ks = 0; ks < 2; ks++)
-                                    umma::mma_bf16(tmem + T_AO, umma::desc_at(term == 1 ? dYL : dYH, (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO)),
-                                                   umma::desc_at(term == 2 ? dBL : dBH, (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128)), ID32, true);
+                            for (int ks = 0; ks < 2; ks++) {
+                                const uint32_t ao = (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO), wo = (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128);
+                                umma::mma_bf16(tmem + T_AO, umma::desc_at(dYH, ao), umma::desc_at(dBH, wo), ID64, true);
+                                umma::mma_bf16(tmem + T_AO, umma::desc_at(dYL, ao), umma::desc_at(dBH, wo), ID32, true);
+                            }
                     umma::commit(&bar);
                 }
                 __syncwarp();
@@ -972,11 +974,12 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
                 else refill_slot(1, S_WB, wb + W_CONV1, B_CONV1);           // conv1 of the next tile
             }
             {
-                float v[16];
+                float v[16], u[16];
                 umma::tmem_ld16(trow + T_AO + h * 16, v);
+                umma::tmem_ld16(trow + T_AO + 32 + h * 16, u);
                 uint32_t ph[8], pl[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q], 0.f), fmaxf(v[2 * q + 1], 0.f), ph[q], pl[q]);
+                for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q] + u[2 * q], 0.f), fmaxf(v[2 * q + 1] + u[2 * q + 1], 0.f), ph[q], pl[q]);
                 umma::tmem_st8(trow + T_XH + h * 8, ph);         // conv C's operand: 32 channels = 16 columns, hi and lo
                 umma::tmem_st8(trow + T_XL + h * 8, pl);
             }

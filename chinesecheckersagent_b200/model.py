@@ -129,9 +129,16 @@ def pack_weights_acc(w):
     hb = np.zeros(32); hb[:16] = bp; hb[16] = bv[0]
     split(heads.T, hb)
     for blk in range(9):
-        for i in (2 + 3 * blk, 3 + 3 * blk, 4 + 3 * blk):
+        for j, i in enumerate((2 + 3 * blk, 3 + 3 * blk, 4 + 3 * blk)):
             m, b = _fold(w, i)
-            split(m.T, b)
+            if j != 1:
+                split(m.T, b)
+                continue
+            # conv B: one [64 x (288 + 16)] operand, rows 0-31 = hi with the bias columns, rows 32-63 = lo (no bias)
+            Wt = np.asarray(m.T, dtype=np.float64)
+            hi = torch.from_numpy(Wt).to(torch.float32).to(torch.float16).to(torch.float64).numpy()
+            both = np.concatenate([_with_bias_columns(hi, b, True), _with_bias_columns(Wt - hi, np.zeros_like(b), True)], axis=0)
+            ops.append(_op_layout(both, True))
     # policy dense (400 -> 294, padded to 320): 2 N-halves x 4 K-chunks (112, 96, 96, 96) x [hi (N160, Kc) | lo (N160, Kc)]
     Wd = np.zeros((400, 320)); Wd[:, :294] = np.asarray(w["policy_head/kernel"], dtype=np.float64)
     for half in range(2):
