@@ -168,7 +168,7 @@ class ResidualCNN(Model):
         self.loaded = False
         self.fused_mcts = True      # engine.BatchedMCTS.search_net / BatchedSelfPlay may run the rounds inside libccx (ccx_mcts_run_net)
         # default = the accurate tensor-core mode: meets the <= 1e-3 output bar against the restated Keras graph (max |dp| 2e-5)
-        # at 19.6 M self-play sims/s; set_kernel("tc") trades that for 1.9x the speed (max |dp| 3.2e-3, same argmax)
+        # at 21.4 M self-play sims/s; set_kernel("tc") trades that for 1.7x the speed (max |dp| 3.2e-3, same argmax)
         self.kernel = "tc_acc"
         self.tc_dtype = "fp16"      # IEEE-half operands: 8x smaller error than bf16 at the same speed
 
