@@ -1,4 +1,5 @@
-"""Mirror of the reference's player.py: GreedyPlayer (player.py:67-129) and AiPlayer (player.py:133-166).
+"""Mirror of the reference's player.py: GreedyPlayer (player.py:67-129, both the deterministic-heuristic and the stochastic branch)
+and AiPlayer (player.py:133-166).
 HumanPlayer (interactive stdin) is out of scope."""
 import random
 
@@ -12,11 +13,34 @@ from .MCTS import MCTS, Node
 
 class GreedyPlayer:
     def __init__(self, player_num, stochastic=False):
-        if stochastic:
-            raise NotImplementedError("the stochastic greedy branch (player.py:77-97) is not on the hot path")
         self.player_num, self.stochastic = player_num, stochastic
 
+    def _decide_stochastic(self, board):
+        """player.py:77-97: forward moves sampled in proportion to the rows they advance, a uniform backward / sideways
+        move when nothing advances.  Move lists come from the device movegen; the sampling is host logic like the reference's."""
+        human = board_utils.convert_np_to_human_moves(board.get_valid_moves(self.player_num))
+        prior, forward, backward = [], [], []
+        for start in human:
+            for end in human[start]:
+                dist = end[0] - start[0]
+                if self.player_num == PLAYER_ONE:
+                    dist = -dist
+                if dist > 0:
+                    forward.append((start, end)); prior.append(dist)
+                else:
+                    backward.append((start, end))
+        if not forward:
+            return random.choice(backward)
+        p = np.array(prior) / sum(prior)
+        return forward[np.random.choice(len(forward), p=p)]
+
     def decide_move(self, board, verbose=False, training=False, total_moves=None):
+        if self.stochastic:
+            pick_start, pick_end = self._decide_stochastic(board)
+            if verbose:
+                board.visualise(cur_player=self.player_num)
+                print('GreedyPlayer moved from {} to {}\n'.format(pick_start, pick_end))
+            return board_utils.human_coord_to_np_index(pick_start), board_utils.human_coord_to_np_index(pick_end)
         env = _engine.BatchedEnv(1, engine=board._eng, state=board._pack(self.player_num - 1))
         masks = env.greedy_candidates().cpu().numpy().view(np.uint64)[:, 0]
         moves = []

@@ -69,3 +69,18 @@ def load_train_data(path):
     from . import h5lite
     t = h5lite.read_tree(path)
     return t["/board_x"], t["/pi_y"], t["/v_y"]
+
+
+def augment_train_data(board_x, pi_y, v_y, mirror_pi=True):
+    """utils.augment_train_data (utils.py:77-97): doubles the data with the board mirrored along the anti-diagonal
+    (np.fliplr(np.rot90(plane)) = cell (r, c) -> (6 - c, 6 - r), the game's mirror symmetry).  The reference mirrors the
+    boards but leaves pi untouched, which mislabels every mirrored example (SURVEY 8a quirk ii); here pi is mirrored with the
+    board (policy index id*49 + r*7 + c -> id*49 + (6-c)*7 + (6-r)) unless mirror_pi=False asks for the reference's behaviour.
+    Accepts lists / arrays (N,7,7,7), (N,294), (N,); returns arrays of twice the length."""
+    bx, py, vy = np.asarray(board_x), np.asarray(pi_y), np.asarray(v_y)
+    mb = bx[:, ::-1, ::-1, :].transpose(0, 2, 1, 3)               # out[r', c'] = in[6 - c', 6 - r']
+    mp = py
+    if mirror_pi:
+        p = py.reshape(len(py), 6, BOARD_HEIGHT, BOARD_WIDTH)
+        mp = p[:, :, ::-1, ::-1].transpose(0, 1, 3, 2).reshape(len(py), -1)
+    return np.concatenate([bx, mb]), np.concatenate([py, mp]), np.concatenate([vy, vy])

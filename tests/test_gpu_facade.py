@@ -132,3 +132,27 @@ def test_selfplay_function_contract():
         bx, py, vy = utils.convert_to_train_data(games)                      # train.py:269
         assert len(bx) == len(py) == len(vy) and bx[0].shape == (7, 7, 7)
         assert vy[0] == games[0][1] and (len(vy) < 2 or vy[1] == -vy[0])
+
+
+def test_stochastic_greedy_branch_samples_legal_forward_moves():
+    """GreedyPlayer(stochastic=True) (player.py:77-97): every pick is legal; forward moves are drawn in proportion to the rows
+    they advance, so the empirical mean advance from the start position sits at sum(d^2)/sum(d) over the forward moves."""
+    import random
+
+    from chinesecheckersagent_b200 import board_utils
+    from chinesecheckersagent_b200.board import Board
+    from chinesecheckersagent_b200.player import GreedyPlayer
+    random.seed(3); np.random.seed(3)
+    b = Board()
+    valid = b.get_valid_moves(1)
+    human = board_utils.convert_np_to_human_moves(valid)
+    dists = [s[0] - e[0] for s in human for e in human[s] if s[0] - e[0] > 0]
+    p = GreedyPlayer(1, stochastic=True)
+    adv = []
+    for _ in range(400):
+        s, e = p.decide_move(b)
+        assert e in valid[s]
+        adv.append(board_utils.np_index_to_human_coord(s)[0] - board_utils.np_index_to_human_coord(e)[0])
+    assert min(adv) > 0
+    want = sum(d * d for d in dists) / sum(dists)
+    assert abs(np.mean(adv) - want) < 0.15
