@@ -48,3 +48,48 @@ def test_agent_greedy_match_swaps_sides(arena):
     assert (a.p1, a.p2) == ("m", arena.GREEDY) and (b.p1, b.p2) == (arena.GREEDY, "m")
     FakeArena.script = [(1, 4), (4, 1)]
     assert arena.agent_greedy_match("m", 10) == arena.GREEDY
+
+
+def test_game_referee_matches_rule_statement():
+    """_Referee against a direct deque statement of game.py:70-92 on random destination streams."""
+    import random
+    from collections import deque
+    from chinesecheckersagent_b200.config import PROGRESS_MOVE_LIMIT, TOTAL_HIST_MOVES, UNIQUE_DEST_LIMIT
+    from chinesecheckersagent_b200.game import _Referee
+    rng = random.Random(5)
+    for trial in range(200):
+        capped = bool(trial & 1)
+        pool = [(rng.randrange(7), rng.randrange(7)) for _ in range(rng.choice([2, 3, 4, 6, 12]))]
+        ref, hist, plies = _Referee(capped), deque(maxlen=TOTAL_HIST_MOVES), 0
+        for _ in range(PROGRESS_MOVE_LIMIT + 5):
+            d = rng.choice(pool)
+            hist.append(d)
+            own = {hist[i] for i in range(len(hist) - 1, -1, -2)}
+            want = None
+            if len(hist) == TOTAL_HIST_MOVES and len(own) <= UNIQUE_DEST_LIMIT:
+                want = "rep"
+            else:
+                plies += 1
+                if capped and plies >= PROGRESS_MOVE_LIMIT:
+                    want = "cap"
+            got = ref.verdict(d)
+            assert (got is None) == (want is None)
+            if want:
+                assert ("Repetition" in got) == (want == "rep")
+                break
+
+
+def test_board_utils_round_trip_and_tips():
+    from chinesecheckersagent_b200 import board_utils as bu
+    seen = set()
+    for i in range(7):
+        for j in range(7):
+            h = bu.np_index_to_human_coord((i, j))
+            assert bu.human_coord_to_np_index(h) == (i, j)
+            assert 1 <= h[0] <= 13 and 1 <= h[1] <= 7 - abs(h[0] - 7)
+            seen.add(h)
+    assert len(seen) == 49
+    assert bu.np_index_to_human_coord((6, 0)) == (13, 1) and bu.np_index_to_human_coord((0, 6)) == (1, 1)
+    assert bu.np_index_to_human_coord((0, 0)) == (7, 1) and bu.np_index_to_human_coord((6, 6)) == (7, 7)
+    assert bu.is_valid_pos(6, 6) and not bu.is_valid_pos(7, 0) and not bu.is_valid_pos(0, -1)
+    assert bu.convert_np_to_human_moves({(6, 0): [(5, 0), (6, 1)]}) == {(13, 1): [(12, 1), (12, 2)]}
