@@ -14,7 +14,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .config import BATCH_SIZE, EPOCHS, LEARNING_RATE, LOSS_WEIGHTS, NUM_ACTIONS, REG_CONST
+from .config import (BATCH_SIZE, DEF_DATA_RETENTION_RATE, EPOCHS, EVAL_GAMES, LEARNING_RATE, LOSS_WEIGHTS, NUM_ACTIONS,
+                     NUM_SELF_PLAY, PAST_ITER_COUNT, REG_CONST)
 
 BN_EPS, BN_MOMENTUM = 1e-3, 0.99          # Keras BatchNormalization defaults (moving = 0.99 * moving + 0.01 * batch)
 
@@ -165,3 +166,80 @@ def train(model, board_x, pi_y, v_y, data_retention=1.0, epochs=EPOCHS, batch_si
             log("epoch %d/%d %s" % (ep + 1, epochs, rec))
     model.eval()
     return history
+
+
+# ---- the outer loop on one box (train.evolve, train.py:235-317), every stage on the batched kernels ----------------
+SAVE_TRAIN_DATA_DIR, SAVE_TRAIN_DATA_PREF = "generated-training-data", "data-for-iter-"
+SAVE_WEIGHTS_DIR, MODEL_PREFIX = "saved-weights", "version"
+
+
+def get_weights_path_from_version(version, directory=SAVE_WEIGHTS_DIR):
+    return "{}/{}{:0>4}-weights.h5".format(directory, MODEL_PREFIX, version)
+
+
+def combine_prev_iters_train_data(board_x, pi_y, v_y, iteration_count, save_dir=SAVE_TRAIN_DATA_DIR,
+                                  pref=SAVE_TRAIN_DATA_PREF):
+    """This iteration's examples pooled with the PAST_ITER_COUNT previous data files (train.py:321-352)."""
+    from .utils import combine_train_data
+    return combine_train_data(board_x, pi_y, v_y, iteration_count - PAST_ITER_COUNT, iteration_count - 1, save_dir, pref)
+
+
+def generate_self_play(model, num_games=NUM_SELF_PLAY, n_slots=None, seed=0, max_iters=512, **selfplay_kw):
+    """generate_self_play_in_parallel (train.py:73-86) without the process pool: `num_games` finished games out of one
+    BatchedSelfPlay batch, returned as (board_x, pi_y, v_y) NumPy arrays in convert_to_train_data's format (all-gathered
+    over the ranks when torch.distributed is initialised)."""
+    from .selfplay import BatchedSelfPlay, all_gather_trajectories
+    slots = int(n_slots or max(32, min(4096, num_games)))
+    sp = BatchedSelfPlay(model.eng, model.evaluate_states, n_slots=slots, seed=seed, max_iters=max_iters, **selfplay_kw)
+    sp.run(target_games=num_games)
+    traj = all_gather_trajectories(sp.collect())
+    return (traj["board_x"].cpu().numpy(), traj["pi_y"].cpu().numpy(), traj["v_y"].cpu().numpy().astype(np.float32)), sp.stats()
+
+
+def evolve(cur_model_path, other_opponent_for_selfplay=None, iteration_count=0, best_model=None, max_iterations=1,
+           num_self_play=NUM_SELF_PLAY, eval_games=EVAL_GAMES, data_dir=SAVE_TRAIN_DATA_DIR, weights_dir=SAVE_WEIGHTS_DIR,
+           seed=0, epochs=EPOCHS, log=print, **selfplay_kw):
+    """train.evolve (train.py:235-317) with a bound on the number of iterations: self-play with the best (else current)
+    model -> augment -> save data-for-iter-N.h5 -> pool with previous iterations -> train (retention min(1/iters, 0.5)) ->
+    save versionNNNN-weights.h5 -> arena against the best model, promote on more than int(0.55 * eval_games) wins.
+    Returns (cur_model_path, best_model, iteration_count) as they stand after the last iteration.
+    Self-play between two different nets (`other_opponent_for_selfplay`) is not built: the recorded search runs one net
+    per batch; the arena (arena.agent_match) is the two-net path."""
+    import os
+
+    from . import utils
+    from .arena import evaluate
+    from .model import ResidualCNN, read_weight_file
+    if other_opponent_for_selfplay is not None:
+        raise NotImplementedError("self-play against a second net is not part of this build; see arena.agent_match")
+    from .engine import Engine
+    engine = Engine(0)
+    for _ in range(int(max_iterations)):
+        generator_path = best_model if best_model is not None else cur_model_path
+        net = ResidualCNN(engine=engine).load_weights(generator_path)
+        (board_x, pi_y, v_y), stats = generate_self_play(net, num_self_play, seed=seed + iteration_count, **selfplay_kw)
+        log("iteration %d: self-play with %s: %s" % (iteration_count, generator_path, stats))
+        if len(board_x):
+            board_x, pi_y, v_y = utils.augment_train_data(board_x, pi_y, v_y)
+            utils.save_train_data(board_x, pi_y, v_y, version=iteration_count, directory=data_dir, prefix=SAVE_TRAIN_DATA_PREF)
+        board_x, pi_y, v_y, iters_used = combine_prev_iters_train_data(board_x, pi_y, v_y, iteration_count, data_dir)
+        if iters_used == 0:
+            log("No training data for iteration %d! Re-iterating..." % iteration_count)
+            continue
+        retention = min(1.0 / iters_used, DEF_DATA_RETENTION_RATE)
+        learner = TrainableResidualCNN().load_keras_weights(read_weight_file(cur_model_path)).to(net.eng.device)
+        history = train(learner, torch.from_numpy(board_x), torch.from_numpy(pi_y), torch.from_numpy(v_y), retention,
+                        epochs=epochs, seed=seed + iteration_count, log=log)
+        os.makedirs(weights_dir, exist_ok=True)
+        cur_model_path = learner.save_weights(get_weights_path_from_version(iteration_count, weights_dir))
+        log("iteration %d: trained on %d examples (retention %.2f), final %s -> %s"
+            % (iteration_count, len(board_x), retention, history[-1] if history else None, cur_model_path))
+        if best_model is not None:
+            cur_wins, best_wins, draws = evaluate(best_model, cur_model_path, eval_games, seed=seed + iteration_count)
+            if cur_wins > int(0.55 * eval_games):
+                best_model = cur_model_path
+                log("Now using {} as the best model".format(best_model))
+            else:
+                log("Output model of this iteration is not better; retaining {} as the best model".format(best_model))
+        iteration_count += 1
+    return cur_model_path, best_model, iteration_count

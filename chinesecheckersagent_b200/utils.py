@@ -84,3 +84,37 @@ def augment_train_data(board_x, pi_y, v_y, mirror_pi=True):
         p = py.reshape(len(py), 6, BOARD_HEIGHT, BOARD_WIDTH)
         mp = p[:, :, ::-1, ::-1].transpose(0, 1, 3, 2).reshape(len(py), -1)
     return np.concatenate([bx, mb]), np.concatenate([py, mp]), np.concatenate([vy, vy])
+
+
+# ---- data merge / label-count tools (combine_data.py, count_labels.py, train.py:321-352) ----
+def combine_train_data(board_x, pi_y, v_y, first_version, last_version, save_dir="generated-training-data",
+                       pref="data-for-iter-"):
+    """Pool the given examples (may be empty) with the saved files `<save_dir>/<pref><i>.h5` for every
+    i in [first_version, last_version] that is >= 0 and exists (missing files are reported and skipped, as
+    combine_data.py:13-25 does).  Returns (board_x, pi_y, v_y, number of sources pooled); ([], [], [], 0) when
+    there is nothing at all."""
+    import os
+    parts = []
+    if len(board_x) and len(pi_y) and len(v_y):
+        parts.append((np.asarray(board_x), np.asarray(pi_y), np.asarray(v_y)))
+    for version in range(max(int(first_version), 0), int(last_version) + 1):
+        path = "%s/%s%d.h5" % (save_dir, pref, version)
+        if os.path.exists(path):
+            parts.append(tuple(np.asarray(a) for a in load_train_data(path)))
+        else:
+            print("{} does not exist!".format(path))
+    if not parts:
+        return [], [], [], 0
+    boards, pis, vs = zip(*parts)
+    return np.concatenate(boards, axis=0), np.concatenate(pis, axis=0), np.concatenate([np.ravel(v) for v in vs]), len(parts)
+
+
+def count_items(v_y):
+    """count_labels.count_items: {label value: occurrences} of a v_y vector."""
+    values, counts = np.unique(np.asarray(v_y), return_counts=True)
+    return {v.item(): int(c) for v, c in zip(values, counts)}
+
+
+def get_train_label_count(path):
+    """count_labels.get_train_label_count: label histogram of one data-for-iter file."""
+    return count_items(load_train_data(path)[2])

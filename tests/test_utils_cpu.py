@@ -40,3 +40,30 @@ def test_coordinate_round_trips():
             row, col = board_utils.np_index_to_human_coord((i, j))
             assert row == i - j + 7 and col == min(i, j) + 1
             assert board_utils.human_coord_to_np_index((row, col)) == (i, j)
+
+
+def test_combine_train_data_and_label_counts(tmp_path):
+    """f4 tools (combine_data.py, count_labels.py, train.py:321-352): pool current examples with saved iterations,
+    skip missing files and negative versions, count labels."""
+    import numpy as np
+    from chinesecheckersagent_b200 import utils
+    from chinesecheckersagent_b200.train import combine_prev_iters_train_data
+    rng = np.random.default_rng(3)
+    def make(n, label):
+        return (rng.integers(0, 3, (n, 7, 7, 7)).astype(np.uint8), rng.random((n, 294)).astype(np.float32),
+                np.full((n,), label, np.float32))
+    d = str(tmp_path)
+    sets = {v: make(3 + v, (-1.0, 1.0)[v & 1]) for v in (0, 1, 3)}
+    for v, (bx, py, vy) in sets.items():
+        utils.save_train_data(bx, py, vy, version=v, directory=d)
+    cur = make(2, 1.0)
+    bx, py, vy, used = utils.combine_train_data(*cur, -2, 3, d)                     # versions -2, -1 ignored; 2 missing
+    assert used == 4 and bx.shape == (2 + 3 + 4 + 6, 7, 7, 7) and py.shape == (15, 294) and vy.shape == (15,)
+    assert np.array_equal(bx[:2], cur[0]) and np.array_equal(bx[2:5], sets[0][0]) and np.array_equal(py[9:], sets[3][1])
+    assert utils.count_items(vy) == {-1.0: 3, 1.0: 12}
+    assert utils.get_train_label_count("%s/data-for-iter-1.h5" % d) == {1.0: 4}
+    assert utils.combine_train_data([], [], [], 5, 6, d) == ([], [], [], 0)
+    bx2, _, vy2, used2 = combine_prev_iters_train_data(*cur, 1, save_dir=d)        # PAST_ITER_COUNT = 1 -> file 0 only
+    assert used2 == 2 and len(bx2) == 5 and utils.count_items(vy2) == {-1.0: 3, 1.0: 2}
+    _, _, _, used3 = combine_prev_iters_train_data([], [], [], 0, save_dir=d)       # nothing before iteration 0
+    assert used3 == 0
