@@ -179,3 +179,41 @@ def test_accurate_mode_in_the_fused_mcts_rounds(model):
     b = m.search_net(roots)
     assert torch.equal(a["visits"], b["visits"]) and torch.equal(a["q"].view(torch.int64), b["q"].view(torch.int64))
     model.set_kernel("tc")
+
+
+def test_net_bar_on_10k_positions_met_in_self_play(model):
+    """SURVEY 8d cfg 5: net parity on >= 10,000 positions ENCOUNTERED in self-play (searched plies of 1,024 games driven by
+    the net itself), against a float64 evaluation of the same Keras graph (train.TrainableResidualCNN in eval mode, which
+    tests/test_train_cpu.py pins to the NumPy restatement at 1e-9).  Bars: |dp|, |dv| <= 1e-3 (north_star) for the accurate
+    default mode and the fp32 kernel, argmax-move agreement reported and >= 99.9 %; the 16-bit throughput mode is reported."""
+    from chinesecheckersagent_b200.model import read_weight_file
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    from chinesecheckersagent_b200.train import TrainableResidualCNN
+    model.set_kernel("tc_acc")
+    sp = BatchedSelfPlay(model.eng, model.evaluate_states, n_slots=1024, num_itr=12, max_iters=24, seed=77)
+    for _ in range(6 + 12):
+        sp.step()
+    flags = sp.rec_flag & 0xF                                           # every searched ply, finished game or not
+    rows = torch.nonzero(flags != 0).flatten()
+    assert rows.numel() >= 10000
+    state = sp.rec_state[rows].t().contiguous()
+    planes = model.eng.empty((rows.numel(), 7, 7, 7), torch.uint8)
+    from chinesecheckersagent_b200.config import DTYPE_U8
+    from chinesecheckersagent_b200.engine import _p
+    model.eng.call("ccx_encode", rows.numel(), _p(state), _p(planes), DTYPE_U8)
+    assert len(torch.unique(state.t(), dim=0)) >= 9000                  # genuinely different positions
+    ref = TrainableResidualCNN().load_keras_weights(read_weight_file(WEIGHTS)).double().cuda().eval()
+    with torch.no_grad():
+        logits, v_ref = ref(planes)
+    p_ref = torch.softmax(logits, dim=1)
+    for kernel, bar in (("tc_acc", 1e-3), ("simt", 1e-3), ("tc", None)):
+        model.set_kernel(kernel)
+        p, v = model.predict_batch(planes)
+        dp, dv = (p - p_ref).abs().max().item(), (v - v_ref).abs().max().item()
+        agree = (p.argmax(1) == p_ref.argmax(1)).double().mean().item()
+        print("%s on %d self-play positions: max|dp| %.3g max|dv| %.3g argmax agreement %.5f" % (kernel, rows.numel(), dp, dv, agree))
+        if bar is not None:
+            assert dp <= bar and dv <= bar and agree >= 0.999, kernel
+        else:
+            assert dp < 2e-2 and dv < 2e-2 and agree >= 0.99
+    model.set_kernel("tc")
