@@ -200,6 +200,9 @@ k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32
 // than the extra latency hiding buys.  Also tried and dropped (r01c): two checkers in flight per THREAD (streams of
 // checkers 0-2 and 3-5 expanded branch-free in the same iteration for instruction-level parallelism) — bit-identical,
 // 3.93e9 steps/s: the dummy expansions of a stream that has run dry outweigh the overlapped latencies.
+// Tried and dropped (r01e): fewer games per warp (28 / 24 / 22 / 16 of 32 lanes, proportionally more warps, for latency
+// hiding and per-scheduler balance): 4.43e9 / 3.77e9 / 3.25e9 / 2.84e9 steps/s against 4.42e9 — the kernel's rate is set by
+// warp instructions issued, so the remaining lever is instructions per expansion, not occupancy.
 #ifndef READY_THRESHOLD
 #define READY_THRESHOLD 12        // sweep on B200 at 65,536 games (r01e): 4 -> 3.89e9, 6 -> 4.20e9, 8 -> 4.35e9, 10 -> 4.41e9, 12 -> 4.42e9, 16 -> 4.30e9 steps/s
 #endif
