@@ -19,6 +19,7 @@ SIGNATURES = {
     "ccx_set_stream": (i32, [vp, vp]),
     "ccx_synchronize": (i32, [vp]),
     "ccx_launch_count": (i64, [vp]),
+    "ccx_graph_replays": (i64, [vp]),
     "ccx_reset": (i32, [vp, i64, vp, i32, u64, i64]),
     "ccx_movegen": (i32, [vp, i64, vp, vp]),
     "ccx_apply": (i32, [vp, i64, vp, vp, vp, vp]),

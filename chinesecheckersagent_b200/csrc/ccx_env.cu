@@ -492,6 +492,7 @@ int ccx_synchronize(ccx_handle *h)
 }
 
 int64_t ccx_launch_count(const ccx_handle *h) { return h ? h->launches : 0; }
+int64_t ccx_graph_replays(const ccx_handle *h) { return h ? h->graph_replays : 0; }
 
 int ccx_reset(ccx_handle *h, int64_t n, uint64_t *state, int mode, uint64_t seed, int64_t game_id0)
 {

@@ -33,6 +33,13 @@ struct ccx_handle {
     // second stream + fork/join events of the two-half round pipeline (ccx_mcts_run_net), created on first use
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // CUDA-graph replay of the round loop (ccx_mcts_run_net): `epoch` changes whenever a device buffer the loop's kernels
+    // receive is (re)allocated or the evaluator changes, which invalidates the cached graph
+    uint64_t epoch = 0;
+    void *round_graph = nullptr;     // ccx_round_graph (ccx_mcts.cu)
+    cudaStream_t cap_stream = nullptr;
+    int graph_off = 0;
+    int64_t graph_replays = 0;
 };
 
 static inline int ccx_fail(ccx_handle *h, cudaError_t e)
@@ -76,6 +83,7 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
 // sub-module teardown hooks (defined where the sub-module lives)
 void ccx_net_free(ccx_handle *h);
 void ccx_trees_free(ccx_handle *h);
+void ccx_round_graph_free(ccx_handle *h);
 void ccx_net_tc_free(ccx_handle *h);
 void ccx_net_acc_free(ccx_handle *h);
 extern "C" int ccx_net_forward_acc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value, const float *w_pold,

@@ -274,6 +274,7 @@ int ccx_net_load(ccx_handle *h, const float *packed_host, int64_t count)
         h->net = new (std::nothrow) ccx_net();
         if (!h->net) return CCX_ERR_NOMEM;
     }
+    h->epoch++;
     if (!h->net->w) CCX_CUDA(h, cudaMalloc(&h->net->w, sizeof(float) * netl::TOTAL));
     CCX_CUDA(h, cudaMemcpyAsync(h->net->w, packed_host, sizeof(float) * netl::TOTAL, cudaMemcpyHostToDevice, h->stream));
     CCX_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -321,6 +322,7 @@ int ccx_net_set_mode(ccx_handle *h, int32_t mode)
     if (mode == 1 && !h->net_tc) return CCX_ERR_STATE;
     if (mode == 2 && (!h->net_tc || !h->net_acc || !h->net || !h->net->w)) return CCX_ERR_STATE;
     h->net_mode = mode;
+    h->epoch++;
     return CCX_OK;
 }
 
@@ -346,6 +348,7 @@ int ccx_net_scratch(ccx_handle *h, int64_t n, uint8_t **planes, float **logits, 
     if (!h->net || !h->net->w) return CCX_ERR_STATE;
     ccx_net *nt = h->net;
     if (nt->cap < n) {
+        h->epoch++;
         void *ptrs[] = {nt->logits, nt->value, nt->planes};
         for (void *q : ptrs) if (q) CCX_CUDA(h, cudaFree(q));
         nt->logits = nullptr; nt->value = nullptr; nt->planes = nullptr; nt->cap = 0;

@@ -679,6 +679,7 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
         return CCX_ERR_ARG;
     ccx_net_tc *tc = tc_of(h, true);
     if (!tc) return CCX_ERR_NOMEM;
+    h->epoch++;
     if (!tc->wb) CCX_CUDA(h, cudaMalloc(&tc->wb, tcl::W_TOTAL));
     if (!tc->fb) CCX_CUDA(h, cudaMalloc(&tc->fb, sizeof(float) * tcl::F_TOTAL));
     CCX_CUDA(h, cudaMemcpyAsync(tc->wb, bf16_blob_host, tcl::W_TOTAL, cudaMemcpyHostToDevice, h->stream));
@@ -710,6 +711,7 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
     ccx_net_tc *tc = tc_of(h, false);
     if (!tc || !tc->wb) return CCX_ERR_STATE;
     if (tc->cap < cap) {
+        h->epoch++;
         CCX_CUDA(h, cudaDeviceSynchronize());          // another stream may still read the old scratch
         if (tc->polc) CCX_CUDA(h, cudaFree(tc->polc));
         tc->polc = nullptr; tc->cap = 0;
@@ -1178,6 +1180,7 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
     if (!h->net_acc) h->net_acc = new (std::nothrow) ccx_net_acc();
     if (!h->net_acc) return CCX_ERR_NOMEM;
     ccx_net_acc &a = *h->net_acc;
+    h->epoch++;
     if (!a.wb) CCX_CUDA(h, cudaMalloc(&a.wb, acl::W_TOTAL));
     CCX_CUDA(h, cudaMemcpyAsync(a.wb, blob_host, acl::W_TOTAL, cudaMemcpyHostToDevice, h->stream));
     CCX_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1196,6 +1199,7 @@ int ccx_net_forward_acc(ccx_handle *h, int64_t n, const uint8_t *planes, float *
     if (n == 0) return CCX_OK;
     const size_t tile_bytes = (size_t)((n + 127) / 128) * acl::PD_TILE_B;
     if (a.cap < n) {
+        h->epoch++;
         if (a.polc) CCX_CUDA(h, cudaFree(a.polc));
         a.polc = nullptr; a.cap = 0;
         CCX_CUDA(h, cudaMalloc(&a.polc, 2 * tile_bytes));

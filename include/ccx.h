@@ -70,6 +70,8 @@ int ccx_set_stream(ccx_handle *h, void *cuda_stream);
 int ccx_synchronize(ccx_handle *h);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t ccx_launch_count(const ccx_handle *h);
+/* searches served by replaying the cached CUDA graph of the round loop (ccx_mcts_run_net); diagnostics */
+int64_t ccx_graph_replays(const ccx_handle *h);
 
 /* Board() / Board(randomised=True)  — board.py:10-57, 61-85.  RANDOMISED draws 12 distinct cells with
  * Philox4x32-10 keyed by (seed, game_id0 + i); the first six go to player 1 ids 0..5. */

@@ -217,3 +217,36 @@ def test_net_bar_on_10k_positions_met_in_self_play(model):
         else:
             assert dp < 2e-2 and dv < 2e-2 and agree >= 0.99
     model.set_kernel("tc")
+
+
+def test_round_loop_graph_replay_is_identical(model):
+    """ccx_mcts_run_net launches a cached CUDA graph of the round loop from the second call with the same arguments on; every
+    call (direct, captured, replayed) must equal the unfused select / evaluate / expand_backup round trips, and a change of
+    evaluator mode, batch size or weights must drop the cached graph."""
+    from chinesecheckersagent_b200.engine import BatchedMCTS
+    if os.environ.get("CCX_NO_GRAPH"):
+        pytest.skip("graph replay switched off")
+    L, h = model.eng.L, model.eng.h
+    st, _, _ = orc.step_random(orc.start_states(200), 31, 0, 8)
+    big = torch.from_numpy(np.ascontiguousarray(st).view(np.int64)).cuda()
+    small = big[:, :70].contiguous()
+    m = BatchedMCTS(model.eng, num_itr=20)
+    replays0 = L.ccx_graph_replays(h)
+    for kernel in ("tc", "tc_acc", "tc", "simt"):
+        model.set_kernel(kernel)
+        for roots in (big, small, big):
+            want = m.search_with(roots, model.evaluate_states)
+            before = L.ccx_graph_replays(h)
+            for rep in range(4):
+                got = m.search_net(roots)
+                assert torch.equal(want["visits"], got["visits"]), (kernel, roots.shape, rep)
+                assert torch.equal(want["q"].view(torch.int64), got["q"].view(torch.int64))
+            assert L.ccx_graph_replays(h) - before == 3                 # call 1 ran directly, call 2 captured + launched, 3 and 4 replayed
+    model.load_weights(WEIGHTS)                                         # reload: the graph of the old buffers is dropped
+    model.set_kernel("tc")
+    want = m.search_with(big, model.evaluate_states)
+    before = L.ccx_graph_replays(h)
+    for rep in range(3):
+        assert torch.equal(want["visits"], m.search_net(big)["visits"])
+    assert L.ccx_graph_replays(h) - before == 2
+    assert L.ccx_graph_replays(h) > replays0
