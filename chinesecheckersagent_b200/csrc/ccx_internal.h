@@ -80,6 +80,10 @@ int ccx_net_forward_active(ccx_handle *h, int64_t n, const uint8_t *planes, floa
 int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64_t row0, int64_t n, const uint8_t *planes, float *logits,
                           float *value);
 
+int ccx_net_forward_acc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64_t row0, int64_t n, const uint8_t *planes, float *logits,
+                           float *value, const float *b_pold);
+const float *ccx_net_pold_bias(const ccx_handle *h);     // fp32 policy-dense bias inside the SIMT weight blob (ccx_net.cu)
+
 // sub-module teardown hooks (defined where the sub-module lives)
 void ccx_net_free(ccx_handle *h);
 void ccx_trees_free(ccx_handle *h);

@@ -808,7 +808,7 @@ static int run_net_rounds(ccx_handle *h, int64_t n, int32_t rounds, double cpuct
     // low-occupancy stretches of one half (the tail of its tree kernel = the deepest trees, the last tile of its trunk kernel)
     // are filled by the other half's kernels.  Same trees as the single-stream order, bit for bit.
     static const bool no_split = getenv("CCX_NO_SPLIT") != nullptr;
-    const bool split = !no_split && h->net_mode == 1 && n >= 8192;     // measured: 16,384 slots 65.1 -> 62.2 ms per ply; no gain at 4,096
+    const bool split = !no_split && (h->net_mode == 1 || h->net_mode == 2) && n >= 8192;     // measured: 16,384 slots 65.1 -> 62.2 ms per ply; no gain at 4,096
     int64_t part_n[2] = {split ? (n / 2) & ~(int64_t)127 : n, 0};          // halves start on a 128-position tile of the net's scratch
     part_n[1] = n - part_n[0];
     cudaStream_t streams[2] = {h->stream, h->stream};
@@ -824,6 +824,7 @@ static int run_net_rounds(ccx_handle *h, int64_t n, int32_t rounds, double cpuct
     }
     // make sure the evaluator's internal scratch covers the whole batch before two streams share it
     if (h->net_mode == 1 && (rc = ccx_net_forward_tc_on(h, h->stream, n, 0, 0, planes, logits, value))) return rc;
+    if (h->net_mode == 2 && (rc = ccx_net_forward_acc_on(h, h->stream, n, 0, 0, planes, logits, value, ccx_net_pold_bias(h)))) return rc;
     const int parts = split ? 2 : 1;
     // round r: [r == 0: select+encode | r > 0: finish round r-1's leaf, then select+encode] -> net; one last finish at the end.
     // Tried and dropped (r01c): programmatic dependent launch for the three kernels of a round (prologues before
@@ -848,6 +849,7 @@ static int run_net_rounds(ccx_handle *h, int64_t n, int32_t rounds, double cpuct
             CCX_LAUNCHED(h);
             if (r < rounds) {
                 if (h->net_mode == 1) rc = ccx_net_forward_tc_on(h, st, n, t0, nq, planes + t0 * 343, logits + t0 * 294, value + t0);
+                else if (h->net_mode == 2) rc = ccx_net_forward_acc_on(h, st, n, t0, nq, planes + t0 * 343, logits + t0 * 294, value + t0, ccx_net_pold_bias(h));
                 else rc = ccx_net_forward_active(h, nq, planes + t0 * 343, logits + t0 * 294, value + t0);
                 if (rc) return rc;
             }

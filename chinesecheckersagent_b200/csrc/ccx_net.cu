@@ -368,6 +368,8 @@ extern "C" int ccx_net_forward_u8(ccx_handle *h, int64_t n, const uint8_t *plane
     return ccx_net_forward_active(h, n, planes, logits, value);
 }
 
+const float *ccx_net_pold_bias(const ccx_handle *h) { return (h && h->net && h->net->w) ? h->net->w + netl::POLD_B : nullptr; }
+
 int ccx_net_forward_active(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value)
 {
     if (h->net_mode == 1) return ccx_net_forward_tc(h, n, planes, logits, value);

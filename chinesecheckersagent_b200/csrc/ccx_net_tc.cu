@@ -1193,28 +1193,40 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
 int ccx_net_forward_acc(ccx_handle *h, int64_t n, const uint8_t *planes, float *logits, float *value, const float *w_pold, const float *b_pold)
 {
     if (!h || n < 0 || (n && (!planes || !logits || !value || !w_pold || !b_pold))) return CCX_ERR_ARG;
+    (void)w_pold;
+    return ccx_net_forward_acc_on(h, h->stream, n, 0, n, planes, logits, value, b_pold);
+}
+
+}  // extern "C"
+
+// rows [row0, row0 + n) of a batch whose internal policy-conv scratch holds `cap` positions, on an explicit stream (the two
+// halves of a split batch are in flight on two streams, ccx_mcts_run_net); planes / logits / value point at the first of the n rows
+int ccx_net_forward_acc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64_t row0, int64_t n, const uint8_t *planes, float *logits,
+                           float *value, const float *b_pold)
+{
     ccx_net_tc *tc = tc_of(h, false);
     if (!h->net_acc || !h->net_acc->wb || !tc || !tc->fb) return CCX_ERR_STATE;
     ccx_net_acc &a = *h->net_acc;
-    if (n == 0) return CCX_OK;
-    const size_t tile_bytes = (size_t)((n + 127) / 128) * acl::PD_TILE_B;
-    if (a.cap < n) {
+    if (a.cap < cap) {
         h->epoch++;
+        CCX_CUDA(h, cudaDeviceSynchronize());          // another stream may still read the old scratch
         if (a.polc) CCX_CUDA(h, cudaFree(a.polc));
         a.polc = nullptr; a.cap = 0;
+        const size_t tile_bytes = (size_t)((cap + 127) / 128) * acl::PD_TILE_B;
         CCX_CUDA(h, cudaMalloc(&a.polc, 2 * tile_bytes));
-        CCX_CUDA(h, cudaMemsetAsync(a.polc, 0, 2 * tile_bytes, h->stream));           // rows past n of the last tile stay finite
-        a.cap = n;
+        CCX_CUDA(h, cudaMemsetAsync(a.polc, 0, 2 * tile_bytes, stream));               // rows past n of the last tile stay finite
+        a.cap = cap;
     }
-    uint8_t *polc_h = a.polc, *polc_l = a.polc + (size_t)((a.cap + 127) / 128) * acl::PD_TILE_B;
+    if (n == 0) return CCX_OK;                         // (a call with n = 0 only reserves the scratch)
+    if (row0 % 128) return CCX_ERR_ARG;
+    const size_t off = (size_t)(row0 / 128) * acl::PD_TILE_B;
+    uint8_t *polc_h = a.polc + off, *polc_l = a.polc + (size_t)((a.cap + 127) / 128) * acl::PD_TILE_B + off;
     int64_t tiles = (n + acl::POS - 1) / acl::POS;
     unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);       // two resident CTAs per SM
-    k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, h->stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+    k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
     CCX_LAUNCHED(h);
-    (void)w_pold;
-    k_policy_dense_acc<<<dim3((unsigned)((n + 127) / 128), 4), 128, pda::S_TOTAL, h->stream>>>(a.wb, b_pold, polc_h, polc_l, n, logits);
+    k_policy_dense_acc<<<dim3((unsigned)((n + 127) / 128), 4), 128, pda::S_TOTAL, stream>>>(a.wb, b_pold, polc_h, polc_l, n, logits);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
 
-}  // extern "C"

@@ -14,4 +14,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_st
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_mcts_search -c 1 -o gpurun_out/prof_mcts_search python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_p2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_net_trunk|k_policy_dense" -s 6 -c 2 -o gpurun_out/prof_net python scripts/net_bench.py 1 > gpurun_out/ncu_p3.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_mcts_round" -s 1320 -c 1 -o gpurun_out/prof_tree python scripts/selfplay_bench.py 1 > gpurun_out/ncu_p4.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_net_trunk_acc|k_policy_dense_acc" -s 6 -c 2 -o gpurun_out/prof_net_acc python scripts/net_bench.py 1 tc_acc > gpurun_out/ncu_p5.log 2>&1
+{ python scripts/selfplay_bench.py 3 4096 tc; python scripts/selfplay_bench.py 3 4096 tc_acc; python scripts/selfplay_bench.py 2 16384 tc; python scripts/selfplay_bench.py 2 16384 tc_acc;
+  python scripts/net_bench.py 10 tc; python scripts/net_bench.py 10 tc_acc; python scripts/mcts_stub_bench.py; } > gpurun_out/side_benches.log 2>&1
+cat gpurun_out/side_benches.log
 ls -la gpurun_out

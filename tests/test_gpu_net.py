@@ -133,11 +133,13 @@ def test_fused_round_loop_equals_round_trips(model, kernel, pre_expand):
     model.set_kernel("tc")
 
 
-def test_fused_round_loop_two_stream_split_is_bit_identical(model):
+@pytest.mark.parametrize("kernel", ["tc", "tc_acc"])
+def test_fused_round_loop_two_stream_split_is_bit_identical(model, kernel):
     """>= 8,192 trees: ccx_mcts_run_net runs the two halves of the batch as two pipelines on two streams (ragged halves here);
-    the trees must not depend on that"""
+    the trees must not depend on that (16-bit and accurate tensor-core modes; rounds 10 >= 8, so the third call also
+    replays the two-branch CUDA graph)"""
     from chinesecheckersagent_b200.engine import BatchedMCTS
-    model.set_kernel("tc")
+    model.set_kernel(kernel)
     n = 8200 + 3
     st, _, _ = orc.step_random(orc.start_states(n), 21, 0, 7, nthreads=8)
     roots = torch.from_numpy(np.ascontiguousarray(st).view(np.int64)).cuda()
@@ -147,6 +149,10 @@ def test_fused_round_loop_two_stream_split_is_bit_identical(model):
     b = m.search_net(roots, pre_expand=True, root_noise=noise)
     assert torch.equal(a["visits"], b["visits"]) and torch.equal(a["q"].view(torch.int64), b["q"].view(torch.int64))
     assert torch.equal(a["n_nodes"], b["n_nodes"])
+    for _ in range(2):                                                   # captured, then replayed
+        c = m.search_net(roots, pre_expand=True, root_noise=noise)
+        assert torch.equal(a["visits"], c["visits"]) and torch.equal(a["n_nodes"], c["n_nodes"])
+    model.set_kernel("tc")
 
 
 def test_accurate_tensor_core_mode_meets_the_1e3_bar(model, gold):
