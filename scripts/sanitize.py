@@ -18,6 +18,11 @@ for n in (3, 130):
     m.set_kernel('tc'); m.forward(x); m.set_kernel('tc_acc'); m.forward(x); m.set_kernel('simt'); m.forward(x)
 m.set_kernel('tc')
 BatchedMCTS(eng, num_itr=6).search_net(env.state[:, :70].contiguous())
+g9 = BatchedMCTS(eng, num_itr=9); r9 = env.state[:, :70].contiguous()
+for _ in range(3): g9.search_net(r9)          # direct, captured, replayed (CUDA graph of the round loop)
+m.set_kernel('tc_acc')
+for _ in range(3): g9.search_net(r9)
+m.set_kernel('tc')
 sp = BatchedSelfPlay(eng, m.evaluate_states, n_slots=33, num_itr=5, max_iters=10)
 for _ in range(8): sp.step()
 sp.collect()
