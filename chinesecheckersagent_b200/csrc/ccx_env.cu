@@ -219,20 +219,21 @@ k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1
     if (tid < 64) sNB[tid] = ((CCX_VALID >> tid) & 1) ? (neighbours(1ULL << tid) & CCX_VALID) : 0ULL;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
-    unsigned mask = __ballot_sync(0xFFFFFFFFu, i < n);
-    if (i >= n) return;
-    Game g = load_game(st, n, i);
+    // every lane stays in the loop until its whole warp is done (id == 7 marks a lane without a game or past its last ply), so
+    // the per-iteration vote runs on the constant full mask
+    const bool act = i < n;
+    unsigned alive = __ballot_sync(0xFFFFFFFFu, act);
+    Game g = load_game(st, n, act ? i : 0);
     const u64 gid = (u64)(gid0 + i);
     u32 w1 = 0, w2 = 0;
-    int t = 0, id = 0;
+    int t = 0, id = act ? 0 : 7;
     u64 occ_all = g.occ_me | g.occ_op;
     int cell = (int)(g.cells_me & 0xFF);
-    u64 o = 1ULL << cell, occ = occ_all & ~o, todo = o, reach = 0;
-    bool leave = false;
+    u64 o = 1ULL << cell, occ = occ_all & ~o, todo = act ? o : 0ULL, reach = 0;
     for (;;) {
         if (todo) {                                         // expand one cell (ray formulation, ccx_device.cuh)
-            int c = __ffsll((long long)todo) - 1;
-            todo &= todo - 1;
+            int c = 63 - __clzll((long long)todo);          // any order gives the same closure; the top bit is the cheapest to find
+            todo ^= 1ULL << c;
             u64 nw = expand_cell(c, occ, sT) & ~(reach | o);
             reach |= nw;
             todo |= nw;
@@ -247,8 +248,8 @@ k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1
         // every lane now either has a cell to expand or is ready (id == 6); one vote per iteration is the
         // warp-convergent point that keeps the compiler from re-nesting the loop
         const bool ready = id == 6;
-        const unsigned r = __ballot_sync(mask, ready);
-        if (!(__popc(r) >= READY_THRESHOLD || r == mask)) continue;
+        const unsigned r = __ballot_sync(0xFFFFFFFFu, ready);
+        if (!(__popc(r) >= READY_THRESHOLD || r == alive)) continue;
         if (ready) {
             u64 dest[6];
 #pragma unroll
@@ -276,7 +277,7 @@ k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1
                 if (TRACE && row) row[11] = (u64)from | ((u64)to << 8) | ((u64)win << 16) | ((u64)pid << 24);
                 if (win) { w1 += win == 1; w2 += win == 2; reset_start(g); }
             }
-            if (++t == plies) leave = true;
+            if (++t == plies) id = 7;
             else {
                 occ_all = g.occ_me | g.occ_op;
                 id = 0;
@@ -284,9 +285,10 @@ k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1
                 o = 1ULL << cell; occ = occ_all & ~o; todo = o; reach = 0;
             }
         }
-        mask = __ballot_sync(mask, !leave);     // only reached on iterations that ran a tail (uniform branch above)
-        if (leave) break;
+        alive = __ballot_sync(0xFFFFFFFFu, id != 7);     // only reached on iterations that ran a tail (uniform branch above)
+        if (alive == 0) break;
     }
+    if (!act) return;
     store_game(st, n, i, g);
     if (w1) atomicAdd(&wins[0], (u64)w1);
     if (w2) atomicAdd(&wins[1], (u64)w2);
