@@ -208,7 +208,7 @@ k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32
 #endif
 
 template <bool TRACE>
-__global__ void __launch_bounds__(ENV_THREADS)
+__global__ void __launch_bounds__(ENV_THREADS, 1, 1)     // cluster rank bound 1: the shared-window base stays in a uniform register across the loop
 k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies,
                    u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games, const uint8_t *__restrict__ jt)
 {
