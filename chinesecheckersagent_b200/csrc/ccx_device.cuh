@@ -177,6 +177,35 @@ CCX_HD u64 expand_cell(int i, u64 occ, const uint8_t *__restrict__ T)
     return L;
 }
 
+// per-cell constants of the diagonal through cell i for expand_cell_lut: shift in bits 0-7, table offset of (len, pos) above
+CCX_HD u32 cell_diag_info(int i)
+{
+    const int r = i >> 3, c = i & 7, k = c - r;
+    const int sh = k >= 0 ? k : -8 * k;
+    const int len = 7 - (k >= 0 ? k : -k);
+    const int pos = k >= 0 ? r : c;
+    return (u32)sh | ((u32)((len - 1) * 896 + pos * 128) << 8);
+}
+
+// expand_cell with the diagonal's shift / table row looked up (CI[i] = cell_diag_info(i)) instead of computed
+CCX_HD u64 expand_cell_lut(int i, u64 occ, const uint8_t *__restrict__ T, const u32 *__restrict__ CI)
+{
+    const u32 ci = CI[i];
+    const int r = i >> 3, c = i & 7;
+    u32 row7 = (u32)(occ >> (8 * r)) & 0x7Fu;
+    u64 L = (u64)T[6 * 896 + c * 128 + row7] << (8 * r);
+    u64 colx = (occ >> c) & 0x0001010101010101ULL;
+    u32 col7 = (u32)((colx * 0x0000040810204081ULL) >> 42) & 0x7Fu;
+    u64 colr = ((u64)T[6 * 896 + r * 128 + col7] * 0x0002040810204081ULL) & 0x0001010101010101ULL;
+    L |= colr << c;
+    const int sh = (int)(ci & 0xFFu);
+    u64 diax = (occ >> sh) & 0x0040201008040201ULL;
+    u32 dia7 = (u32)((diax * 0x0001010101010101ULL) >> 48) & 0x7Fu;
+    u64 diar = ((u64)T[(ci >> 8) + dia7] * 0x0001010101010101ULL) & 0x0040201008040201ULL;
+    L |= diar << sh;
+    return L;
+}
+
 // Board.get_valid_moves (board.py:215-222) with the ray formulation.  Same single-loop structure as movegen():
 // the loop body expands ONE cell of the thread's current checker (origin first, then every newly reached
 // landing cell), and a thread that exhausts a checker moves on to its next one inside the same loop.

@@ -216,7 +216,9 @@ k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1
     __shared__ u64 sD[6][ENV_THREADS];          // destination masks of the current ply, per checker
     __shared__ u64 sNB[64];                     // on-board neighbours of every cell
     const int tid = threadIdx.x;
+    __shared__ u32 sCI[64];                     // per-cell diagonal constants (expand_cell_lut)
     if (tid < 64) sNB[tid] = ((CCX_VALID >> tid) & 1) ? (neighbours(1ULL << tid) & CCX_VALID) : 0ULL;
+    if (tid < 64) sCI[tid] = cell_diag_info(tid);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
     // every lane stays in the loop until its whole warp is done (id == 7 marks a lane without a game or past its last ply), so
@@ -234,7 +236,7 @@ k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1
         if (todo) {                                         // expand one cell (ray formulation, ccx_device.cuh)
             int c = 63 - __clzll((long long)todo);          // any order gives the same closure; the top bit is the cheapest to find
             todo ^= 1ULL << c;
-            u64 nw = expand_cell(c, occ, sT) & ~(reach | o);
+            u64 nw = expand_cell_lut(c, occ, sT, sCI) & ~(reach | o);
             reach |= nw;
             todo |= nw;
         }
