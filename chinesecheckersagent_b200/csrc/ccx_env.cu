@@ -204,7 +204,7 @@ k_step_random(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32
 // hiding and per-scheduler balance): 4.43e9 / 3.77e9 / 3.25e9 / 2.84e9 steps/s against 4.42e9 — the kernel's rate is set by
 // warp instructions issued, so the remaining lever is instructions per expansion, not occupancy.
 #ifndef READY_THRESHOLD
-#define READY_THRESHOLD 12        // sweep on B200 at 65,536 games (r01e): 4 -> 3.89e9, 6 -> 4.20e9, 8 -> 4.35e9, 10 -> 4.41e9, 12 -> 4.42e9, 16 -> 4.30e9 steps/s
+#define READY_THRESHOLD 12        // sweep on B200 at 65,536 games (r01e): 4 -> 3.89e9, 6 -> 4.20e9, 8 -> 4.35e9, 10 -> 4.41e9, 12 -> 4.42e9, 16 -> 4.30e9 steps/s; re-swept after the r01f instruction-count pass: 10 -> 4.92e9, 12 -> 4.93e9, 14 -> 4.91e9, 16 -> 4.82e9
 #endif
 
 template <bool TRACE>
