@@ -260,6 +260,15 @@ static_assert(128 * OUT_LD * 4 <= S_W0, "staging fits in the A region");
 //    each layer issues one more MMA against a constant [128 x 16] "ones" operand, so the epilogues are ReLU + pack only.
 // TMEM columns: X fp32 [0,64) | XB: 16-bit x [64,96), reused as M2B: 16-bit conv-B output [64,80) |
 //               AO: conv A / conv B / heads accumulator [96,128).
+// Tried and dropped (r01f, both bit-identical to v4; the code is in the history, commit "Experiment: trunk v5 ... v6"):
+//  * v5: two tiles in flight per CTA, the same 256 threads running one tile's epilogue while the other's MMAs execute
+//    (256 TMEM columns, 101 KB, two CTAs = four tiles per SM): 1.27 ms per 65,536 positions against 1.00 ms — the epilogues of
+//    the two tiles serialise on the same threads, and the MMA latency they were meant to hide is only ~0.2 of an epilogue;
+//  * v6: the same with two independent 256-thread contexts per CTA (named barriers, weight slots shared and refilled by the
+//    second context to finish a layer, 64 registers): 0.971 ms per 65,536 (+2.7 %), 90.0 us against 85.6 us per 4,096 and
+//    19.2 ms against 18.3 ms per self-play ply.  Four tiles per SM instead of three buy nothing: the tile rate is not set by
+//    per-tile latency with idle resources but by what the tiles share on the SM (shared-memory operand traffic of the N = 32
+//    MMAs and the epilogues' TMEM / shared-memory round trips).
 namespace tc4 {
 constexpr int THREADS = 256, POS = 4, POS_ROWS = 30, LIVE_ROWS = 120;
 constexpr int YROWS = 130, Y_LBO = YROWS * 16, Y_COPY = 4 * Y_LBO;        // 1 guard row + 128 + 1 guard row
@@ -583,583 +592,6 @@ k_net_trunk_tc4(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     if (warp == 0) umma::tmem_free(tmem, 128);
 }
 
-// =====================================================================================================
-// Trunk kernel v5 = v4 with TWO tiles in flight per CTA (contexts 0 and 1, consecutive tiles of a pair): the same 256 threads run
-// the epilogue of one context while the tensor core works on the other one's MMAs, so tensor and SIMT work overlap inside the
-// CTA instead of only across CTAs.  Each context has its own 128 TMEM columns, its own three row-shifted 3x3 operand copies,
-// its own MMA barrier and plane / value staging; the streamed weight slots, the ones operand and the value-head floats are
-// shared, so the two contexts walk the layers in lockstep (a slot is refilled once context 1's MMAs of the layer are done).
-// 101 KB shared memory, 256 TMEM columns -> two CTAs = four tiles per SM (v4: three).  Arithmetic per tile is v4's, bit for bit.
-namespace tc5 {
-using namespace tc4;                       // tile geometry, TMEM column map (per context), FO_* offsets
-constexpr int S_Y0 = 0, S_YCTX = 3 * Y_COPY;
-constexpr int S5_WC1 = 2 * S_YCTX;
-constexpr int S5_WA = S5_WC1 + tcl::B_CONV1, S5_WB = S5_WA + tcl::B_A, S5_WC = S5_WB + tcl::B_B;
-constexpr int S5_ONES = S5_WC + tcl::B_C;
-constexpr int S5_F = S5_ONES + 128 * 16 * 2;
-constexpr int S5_PLANES = S5_F + F_BYTES, PLANES_CTX = 1376;
-constexpr int S5_VALC = S5_PLANES + 2 * PLANES_CTX, VALC_CTX = 512;
-constexpr int S5_TOTAL = S5_VALC + 2 * VALC_CTX;
-static_assert(S5_TOTAL <= 112 * 1024, "two CTAs per SM");
-static_assert(S5_WC1 % 128 == 0 && S5_WA % 128 == 0 && S5_WB % 128 == 0 && S5_WC % 128 == 0 && S5_ONES % 128 == 0 && S5_F % 16 == 0 &&
-              S5_PLANES % 16 == 0, "alignment");
-}  // namespace tc5
-
-template <bool FP16>
-__global__ void __launch_bounds__(tc4::THREADS, 2)
-k_net_trunk_tc5(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
-                __nv_bfloat16 *__restrict__ polc, float *__restrict__ value)
-{
-    using namespace tc5;
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar[2], barW[4];             // per context: MMAs of a phase done; weight slots A, B, C and conv1 landed
-    __shared__ uint32_t tmem_slot;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int rg = warp & 3, h = warp >> 2;
-    const int r = rg * 32 + lane;
-    const int p_local = r / POS_ROWS, rem = r % POS_ROWS, cy = rem / 6, cx = rem % 6;
-    const bool live = r < LIVE_ROWS && cx < 5;
-    const int cell = cy * 5 + cx;
-    const uint32_t sbase = umma::smem_u32(smem);
-    const float *sF = reinterpret_cast<const float *>(smem + S5_F);
-    const int64_t n_tiles = (n + POS - 1) / POS;
-    const int64_t n_pairs = (n_tiles + 1) / 2;
-    const bool planes_aligned = (reinterpret_cast<uintptr_t>(planes) & 3) == 0;
-
-    auto refill_slot = [&](int slot, int dst, const uint8_t *src, uint32_t bytes) {
-        umma::mbar_expect_tx(&barW[slot], bytes);
-        umma::bulk_g2s(sbase + dst, src, bytes, &barW[slot]);
-    };
-    auto load_planes = [&](int64_t tile, uint32_t (&w)[2]) {
-        w[0] = 0u; w[1] = 0u;
-        if (tile >= n_tiles) return;
-        const int bytes = (int)min((int64_t)POS, n - tile * POS) * 343;
-        const uint8_t *src = planes + tile * (POS * 343);
-        if (bytes == POS * 343 && planes_aligned) {
-            w[0] = __ldg(reinterpret_cast<const uint32_t *>(src) + t);
-            if (t < 343 - THREADS) w[1] = __ldg(reinterpret_cast<const uint32_t *>(src) + THREADS + t);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-                for (int k = 0; k < 4; k++) {
-                    const int byte = (q * THREADS + t) * 4 + k;
-                    if (byte < bytes) w[q] |= (uint32_t)__ldg(src + byte) << (8 * k);
-                }
-        }
-    };
-    auto store_planes = [&](int ctx, const uint32_t (&w)[2]) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int idx = q * THREADS + t;
-            if (idx < 344) reinterpret_cast<uint32_t *>(smem + S5_PLANES + ctx * PLANES_CTX)[idx] = w[q];
-        }
-    };
-
-    for (int i = t; i < S5_WC1 / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows stay zero
-    for (int i = t; i < NF; i += THREADS) reinterpret_cast<float *>(smem + S5_F)[i] = __ldg(fb + tcl::F_D1W + i);
-    for (int i = t; i < 128 * 2; i += THREADS) {
-        const int rr = i >> 1, chunk = i & 1;
-        *reinterpret_cast<uint4 *>(smem + S5_ONES + umma::op_offset(rr, chunk * 8, 16)) = make_uint4(chunk == 0 ? pack2<FP16>(1.f, 1.f) : 0u, 0u, 0u, 0u);
-    }
-    {
-        uint32_t w0[2];
-        load_planes(2 * (int64_t)blockIdx.x, w0); store_planes(0, w0);
-        load_planes(2 * (int64_t)blockIdx.x + 1, w0); store_planes(1, w0);
-    }
-    if (t == 0) {
-        umma::mbar_init(&bar[0], 1); umma::mbar_init(&bar[1], 1);
-#pragma unroll
-        for (int q = 0; q < 4; q++) umma::mbar_init(&barW[q], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        refill_slot(3, S5_WC1, wb + tcl::W_CONV1, tcl::B_CONV1);
-        refill_slot(0, S5_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, tcl::B_A);
-        refill_slot(1, S5_WB, wb + tcl::W_BLOCK0 + tcl::W_BB, tcl::B_B);
-        refill_slot(2, S5_WC, wb + tcl::W_BLOCK0 + tcl::W_BC, tcl::B_C);
-    }
-    if (warp == 0) umma::tmem_alloc(&tmem_slot, 256);
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    uint32_t phW0 = 0, phW1 = 0, phW2 = 0;
-    bool conv1_ready = false;
-    const uint32_t tmem0 = tmem_slot;
-    uint32_t phase0 = 0, phase1 = 0;
-    const umma::DescBase dWC1 = umma::desc_base(sbase + S5_WC1, 128u, (64 + tcl::KB) / 8 * 128u), dWA = umma::desc_base(sbase + S5_WA, 128u, (64 + tcl::KB) / 8 * 128u);
-    const umma::DescBase dWB = umma::desc_base(sbase + S5_WB, 128u, (288 + tcl::KB) / 8 * 128u), dWC = umma::desc_base(sbase + S5_WC, 128u, (32 + tcl::KB) / 8 * 128u);
-    const umma::DescBase dONES = umma::desc_base(sbase + S5_ONES, 128u, 16 / 8 * 128u);
-    const umma::DescBase dY0 = umma::desc_base(sbase + S_Y0, Y_LBO, 128u), dY1 = umma::desc_base(sbase + S_Y0 + S_YCTX, Y_LBO, 128u);
-    constexpr uint32_t ID32 = umma::make_idesc(32, FP16), ID64 = umma::make_idesc(64, FP16);
-
-    auto tmem_sync = [&]() { umma::tmem_wait_st(); umma::fence_before_sync(); __syncthreads(); };
-    auto smem_sync = [&]() { umma::fence_async_smem(); umma::fence_before_sync(); __syncthreads(); };
-    auto wait_mma = [&](int ctx) {
-        if (ctx == 0) { umma::mbar_wait(&bar[0], phase0); phase0 ^= 1; }
-        else { umma::mbar_wait(&bar[1], phase1); phase1 ^= 1; }
-        umma::fence_after_sync();
-    };
-    auto pack8 = [&](const float *rr) {
-        return make_uint4(pack2<FP16>(rr[0], rr[1]), pack2<FP16>(rr[2], rr[3]), pack2<FP16>(rr[4], rr[5]), pack2<FP16>(rr[6], rr[7]));
-    };
-    auto tm = [&](int ctx) { return tmem0 + (uint32_t)(ctx * 128); };
-    auto trow_of = [&](int ctx) { return tmem0 + (uint32_t)(ctx * 128) + ((uint32_t)(rg * 32) << 16); };
-    auto finish_x = [&](int ctx) {
-        const uint32_t trow = trow_of(ctx);
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            float v[16];
-            umma::tmem_ld16(trow + T_X + h * 32 + half * 16, v);
-            uint32_t f[16], pk[8];
-#pragma unroll
-            for (int j = 0; j < 16; j++) { v[j] = fmaxf(v[j], 0.f); f[j] = __float_as_uint(v[j]); }
-#pragma unroll
-            for (int j = 0; j < 8; j++) pk[j] = pack2<FP16>(v[2 * j], v[2 * j + 1]);
-            umma::tmem_st16(trow + T_X + h * 32 + half * 16, f);
-            umma::tmem_st8(trow + T_XB + h * 16 + half * 8, pk);
-        }
-    };
-    auto bias_mma = [&](uint32_t tmem_d, umma::DescBase w, int K, uint32_t idesc, bool accumulate) {
-        umma::mma_bf16(tmem_d, umma::desc_at(dONES, 0u), umma::desc_at(w, (uint32_t)(K / 8) * 128u), idesc, accumulate);
-    };
-    // --- per-context operand builders / epilogues (v4's code with the context's TMEM base and shared-memory regions) ---
-    auto build_conv1 = [&](int ctx) {
-        const uint8_t *pl = smem + S5_PLANES + ctx * PLANES_CTX + (live ? p_local * 343 : 0);
-        const uint32_t trow = trow_of(ctx);
-#pragma unroll
-        for (int c8 = 0; c8 < 2; c8++) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float v2[2];
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int kk = h * 32 + c8 * 16 + q * 2 + e;
-                    const int tap = kk / 7, ch = kk % 7, dy = tap / 3, dx = tap % 3;
-                    v2[e] = (live && kk < 63) ? (float)pl[((cy + dy) * 7 + (cx + dx)) * 7 + ch] : 0.f;
-                }
-                pk[q] = pack2<FP16>(v2[0], v2[1]);
-            }
-            umma::tmem_st8(trow + T_XB + h * 16 + c8 * 8, pk);
-        }
-    };
-    auto epi_a = [&](int ctx) {                       // conv A output -> ReLU -> the three row-shifted copies of the 3x3 operand
-        float v[16];
-        umma::tmem_ld16(trow_of(ctx) + T_AO + h * 16, v);
-        const uint4 o0 = make_uint4(relu_pack2<FP16>(v[0], v[1]), relu_pack2<FP16>(v[2], v[3]), relu_pack2<FP16>(v[4], v[5]), relu_pack2<FP16>(v[6], v[7]));
-        const uint4 o1 = make_uint4(relu_pack2<FP16>(v[8], v[9]), relu_pack2<FP16>(v[10], v[11]), relu_pack2<FP16>(v[12], v[13]), relu_pack2<FP16>(v[14], v[15]));
-        if (live) {
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                const int oy = cy - (d - 1);
-                if (oy >= 0 && oy <= 4) {
-                    uint8_t *dst = smem + S_Y0 + ctx * S_YCTX + d * Y_COPY + (2 * h) * Y_LBO + (1 + r - 6 * (d - 1)) * 16;
-                    *reinterpret_cast<uint4 *>(dst) = o0;
-                    *reinterpret_cast<uint4 *>(dst + Y_LBO) = o1;
-                }
-            }
-        }
-    };
-    auto epi_b = [&](int ctx) {                       // conv B output -> ReLU -> M2B in TMEM
-        float v[16];
-        umma::tmem_ld16(trow_of(ctx) + T_AO + h * 16, v);
-        uint32_t pk[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) pk[q] = relu_pack2<FP16>(v[2 * q], v[2 * q + 1]);
-        umma::tmem_st8(trow_of(ctx) + T_XB + h * 8, pk);
-    };
-    // --- MMA issue of a layer for one context (one elected lane of warp 0); `first` = the weight slot has to be waited for ---
-    auto issue = [&](int ctx, int layer, bool first) {        // layer: 0 conv1, 1 conv A / heads, 2 conv B, 3 conv C
-        if (warp == 0) {
-            umma::fence_after_sync();
-            if (umma::elect_one()) {
-                const uint32_t tb = tm(ctx);
-                if (layer == 0) {
-                    if (!conv1_ready) { umma::mbar_wait(&barW[3], 0); conv1_ready = true; }
-                    bias_mma(tb + T_X, dWC1, 64, ID64, false);
-                    umma::gemm_issue_ts<64>(tb + T_X, tb + T_XB, dWC1, 0, ID64, true);
-                } else if (layer == 1) {
-                    if (first) { umma::mbar_wait(&barW[0], phW0); phW0 ^= 1; }
-                    bias_mma(tb + T_AO, dWA, 64, ID32, false);
-                    umma::gemm_issue_ts<64>(tb + T_AO, tb + T_XB, dWA, 0, ID32, true);
-                } else if (layer == 2) {
-                    if (first) { umma::mbar_wait(&barW[1], phW1); phW1 ^= 1; }
-                    const umma::DescBase dY = ctx ? dY1 : dY0;
-                    bias_mma(tb + T_AO, dWB, 288, ID32, false);
-#pragma unroll
-                    for (int d = 0; d < 3; d++)
-#pragma unroll
-                        for (int dxi = 0; dxi < 3; dxi++)
-#pragma unroll
-                            for (int ks = 0; ks < 2; ks++)
-                                umma::mma_bf16(tb + T_AO, umma::desc_at(dY, (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO)),
-                                               umma::desc_at(dWB, (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128)), ID32, true);
-                } else {
-                    if (first) { umma::mbar_wait(&barW[2], phW2); phW2 ^= 1; }
-                    bias_mma(tb + T_X, dWC, 32, ID64, true);
-                    umma::gemm_issue_ts<32>(tb + T_X, tb + T_XB, dWC, 0, ID64, true);
-                }
-                umma::commit(&bar[ctx]);
-            }
-            __syncwarp();
-        }
-    };
-
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const int64_t tile0 = 2 * pair;
-        const bool two = tile0 + 1 < n_tiles;              // the last pair of an odd tile count has no second context
-        const int nctx = two ? 2 : 1;
-        uint32_t pw0[2], pw1[2];
-        load_planes(2 * (pair + gridDim.x), pw0);            // next pair's planes land while this pair computes
-        load_planes(2 * (pair + gridDim.x) + 1, pw1);
-        // conv1 of both contexts
-        for (int c = 0; c < nctx; c++) { build_conv1(c); tmem_sync(); issue(c, 0, true); }
-        for (int c = 0; c < nctx; c++) { wait_mma(c); finish_x(c); tmem_sync(); issue(c, 1, c == 0); }
-        for (int b = 0; b < 9; b++) {
-            const uint8_t *wnext = wb + tcl::W_BLOCK0 + ((b + 1) % 9) * tcl::W_BLOCK;
-            for (int c = 0; c < nctx; c++) {               // conv A done -> 3x3 operand -> conv B
-                wait_mma(c);
-                if (c == nctx - 1 && warp == 0 && umma::elect_one()) refill_slot(0, S5_WA, b < 8 ? wnext + tcl::W_BA : wb + tcl::W_HEADS, tcl::B_A);
-                epi_a(c); smem_sync(); issue(c, 2, c == 0);
-            }
-            for (int c = 0; c < nctx; c++) {               // conv B done -> M2B -> conv C onto the residual
-                wait_mma(c);
-                if (c == nctx - 1 && warp == 0 && umma::elect_one()) refill_slot(1, S5_WB, wnext + tcl::W_BB, tcl::B_B);
-                epi_b(c); tmem_sync(); issue(c, 3, c == 0);
-            }
-            for (int c = 0; c < nctx; c++) {               // conv C done -> ReLU in place -> conv A of the next block / heads
-                wait_mma(c);
-                if (c == nctx - 1 && warp == 0 && umma::elect_one()) refill_slot(2, S5_WC, wnext + tcl::W_BC, tcl::B_C);
-                finish_x(c); tmem_sync(); issue(c, 1, c == 0);
-            }
-        }
-        // heads epilogue of both contexts
-        for (int c = 0; c < nctx; c++) {
-            wait_mma(c);
-            if (c == nctx - 1 && warp == 0 && umma::elect_one()) refill_slot(0, S5_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, tcl::B_A);
-            const int64_t pos0 = (tile0 + c) * POS;
-            const int n_pos = (int)min((int64_t)POS, n - pos0);
-            float v[16];
-            umma::tmem_ld16(trow_of(c) + T_AO + h * 16, v);
-            if (live && p_local < n_pos) {
-                if (h == 0) {
-#pragma unroll
-                    for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q], 0.f);
-                    const int64_t pos = pos0 + p_local;
-                    const int k = cell * 16, chunk = k >= 208, kk = k - chunk * 208;
-                    uint8_t *dst = reinterpret_cast<uint8_t *>(polc) + (pos >> 7) * pd3::TILE_B + (chunk ? pd3::A0_B : 0) +
-                                   umma::op_offset((int)(pos & 127), kk, chunk ? 192 : 208);
-                    *reinterpret_cast<uint4 *>(dst) = pack8(v);
-                    *reinterpret_cast<uint4 *>(dst + 128) = pack8(v + 8);
-                } else {
-                    reinterpret_cast<float *>(smem + S5_VALC + c * VALC_CTX)[p_local * 25 + cell] = fmaxf(v[0], 0.f);
-                }
-            }
-        }
-        store_planes(0, pw0); store_planes(1, pw1);
-        umma::fence_before_sync();
-        __syncthreads();
-        // value head: warps 0-3 take context 0's positions, warps 4-7 context 1's
-        {
-            const int c = warp >> 2, wp = warp & 3;
-            const int64_t pos0 = (tile0 + c) * POS;
-            const int n_pos = c < nctx ? (int)min((int64_t)POS, n - pos0) : 0;
-            if (wp < n_pos) {
-                const float *valc = reinterpret_cast<const float *>(smem + S5_VALC + c * VALC_CTX) + wp * 25;
-                float acc = sF[FO_D1B + lane];
-                for (int k = 0; k < 25; k++) acc = fmaf(valc[k], sF[FO_D1W + k * 32 + lane], acc);
-                float sv = fmaxf(acc, 0.f) * sF[FO_VHW + lane];
-#pragma unroll
-                for (int off = 16; off; off >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, off);
-                if (lane == 0) value[pos0 + wp] = tanhf(sv + sF[FO_VHB]);
-            }
-        }
-        __syncthreads();                                   // the value staging is rewritten by the next pair's heads epilogue
-    }
-    if (warp == 0 && umma::elect_one()) {
-        umma::mbar_wait(&barW[0], phW0); umma::mbar_wait(&barW[1], phW1); umma::mbar_wait(&barW[2], phW2);
-        if (!conv1_ready) umma::mbar_wait(&barW[3], 0);
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_free(tmem0, 256);
-}
-
-template <bool FP16>
-__global__ void __launch_bounds__(2 * tc4::THREADS, 2)
-k_net_trunk_tc6(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
-                __nv_bfloat16 *__restrict__ polc, float *__restrict__ value)
-{
-    using namespace tc5;
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar[2], barW[4];             // per context: MMAs of a phase done; weight slots A, B, C and conv1 landed
-    __shared__ uint32_t tmem_slot;
-    __shared__ unsigned slot_done[3];                // contexts that finished the current layer of a weight slot (the second one refills it)
-    const int ctx = threadIdx.x >> 8;                // two independent 256-thread contexts, one tile each
-    const int t = threadIdx.x & 255, warp = t >> 5, lane = t & 31;
-    const int rg = warp & 3, h = warp >> 2;
-    const int r = rg * 32 + lane;
-    const int p_local = r / POS_ROWS, rem = r % POS_ROWS, cy = rem / 6, cx = rem % 6;
-    const bool live = r < LIVE_ROWS && cx < 5;
-    const int cell = cy * 5 + cx;
-    const uint32_t sbase = umma::smem_u32(smem);
-    const float *sF = reinterpret_cast<const float *>(smem + S5_F);
-    const int64_t n_tiles = (n + POS - 1) / POS;
-    const int64_t n_pairs = (n_tiles + 1) / 2;
-    const bool planes_aligned = (reinterpret_cast<uintptr_t>(planes) & 3) == 0;
-
-    auto refill_slot = [&](int slot, int dst, const uint8_t *src, uint32_t bytes) {
-        umma::mbar_expect_tx(&barW[slot], bytes);
-        umma::bulk_g2s(sbase + dst, src, bytes, &barW[slot]);
-    };
-    auto load_planes = [&](int64_t tile, uint32_t (&w)[2]) {
-        w[0] = 0u; w[1] = 0u;
-        if (tile >= n_tiles) return;
-        const int bytes = (int)min((int64_t)POS, n - tile * POS) * 343;
-        const uint8_t *src = planes + tile * (POS * 343);
-        if (bytes == POS * 343 && planes_aligned) {
-            w[0] = __ldg(reinterpret_cast<const uint32_t *>(src) + t);
-            if (t < 343 - THREADS) w[1] = __ldg(reinterpret_cast<const uint32_t *>(src) + THREADS + t);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-                for (int k = 0; k < 4; k++) {
-                    const int byte = (q * THREADS + t) * 4 + k;
-                    if (byte < bytes) w[q] |= (uint32_t)__ldg(src + byte) << (8 * k);
-                }
-        }
-    };
-    auto store_planes = [&](int ctx, const uint32_t (&w)[2]) {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int idx = q * THREADS + t;
-            if (idx < 344) reinterpret_cast<uint32_t *>(smem + S5_PLANES + ctx * PLANES_CTX)[idx] = w[q];
-        }
-    };
-
-    for (int i = threadIdx.x; i < S5_WC1 / 16; i += 2 * THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows stay zero
-    for (int i = threadIdx.x; i < NF; i += 2 * THREADS) reinterpret_cast<float *>(smem + S5_F)[i] = __ldg(fb + tcl::F_D1W + i);
-    for (int i = threadIdx.x; i < 128 * 2; i += 2 * THREADS) {
-        const int rr = i >> 1, chunk = i & 1;
-        *reinterpret_cast<uint4 *>(smem + S5_ONES + umma::op_offset(rr, chunk * 8, 16)) = make_uint4(chunk == 0 ? pack2<FP16>(1.f, 1.f) : 0u, 0u, 0u, 0u);
-    }
-    {
-        uint32_t w0[2];
-        load_planes(2 * (int64_t)blockIdx.x + ctx, w0); store_planes(ctx, w0);
-    }
-    if (threadIdx.x == 0) {
-        slot_done[0] = 0u; slot_done[1] = 0u; slot_done[2] = 0u;
-        umma::mbar_init(&bar[0], 1); umma::mbar_init(&bar[1], 1);
-#pragma unroll
-        for (int q = 0; q < 4; q++) umma::mbar_init(&barW[q], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        refill_slot(3, S5_WC1, wb + tcl::W_CONV1, tcl::B_CONV1);
-        refill_slot(0, S5_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, tcl::B_A);
-        refill_slot(1, S5_WB, wb + tcl::W_BLOCK0 + tcl::W_BB, tcl::B_B);
-        refill_slot(2, S5_WC, wb + tcl::W_BLOCK0 + tcl::W_BC, tcl::B_C);
-    }
-    if (threadIdx.x < 32) umma::tmem_alloc(&tmem_slot, 256);
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    uint32_t phW0 = 0, phW1 = 0, phW2 = 0;
-    bool conv1_ready = false;
-    const uint32_t tmem0 = tmem_slot;
-    uint32_t phase = 0;
-    const umma::DescBase dWC1 = umma::desc_base(sbase + S5_WC1, 128u, (64 + tcl::KB) / 8 * 128u), dWA = umma::desc_base(sbase + S5_WA, 128u, (64 + tcl::KB) / 8 * 128u);
-    const umma::DescBase dWB = umma::desc_base(sbase + S5_WB, 128u, (288 + tcl::KB) / 8 * 128u), dWC = umma::desc_base(sbase + S5_WC, 128u, (32 + tcl::KB) / 8 * 128u);
-    const umma::DescBase dONES = umma::desc_base(sbase + S5_ONES, 128u, 16 / 8 * 128u);
-    const umma::DescBase dY0 = umma::desc_base(sbase + S_Y0, Y_LBO, 128u), dY1 = umma::desc_base(sbase + S_Y0 + S_YCTX, Y_LBO, 128u);
-    constexpr uint32_t ID32 = umma::make_idesc(32, FP16), ID64 = umma::make_idesc(64, FP16);
-
-    auto ctx_barrier = [&]() { asm volatile("bar.sync %0, 256;" :: "r"(1 + ctx) : "memory"); };       // this context's 8 warps only
-    auto tmem_sync = [&]() { umma::tmem_wait_st(); umma::fence_before_sync(); ctx_barrier(); };
-    auto smem_sync = [&]() { umma::fence_async_smem(); umma::fence_before_sync(); ctx_barrier(); };
-    auto wait_mma = [&](int) {
-        umma::mbar_wait(&bar[ctx], phase); phase ^= 1;
-        umma::fence_after_sync();
-    };
-    // a context is done with the current layer of weight slot `slot`; the second one to say so streams the next layer in
-    auto slot_release = [&](int slot, int dst, const uint8_t *src, uint32_t bytes, bool alone) {
-        if (warp == 0 && umma::elect_one()) {
-            const unsigned inc = alone ? 2u : 1u;
-            if (((atomicAdd(&slot_done[slot], inc) + inc) & 1u) == 0u) refill_slot(slot, dst, src, bytes);
-        }
-    };
-    auto pack8 = [&](const float *rr) {
-        return make_uint4(pack2<FP16>(rr[0], rr[1]), pack2<FP16>(rr[2], rr[3]), pack2<FP16>(rr[4], rr[5]), pack2<FP16>(rr[6], rr[7]));
-    };
-    auto tm = [&](int ctx) { return tmem0 + (uint32_t)(ctx * 128); };
-    auto trow_of = [&](int ctx) { return tmem0 + (uint32_t)(ctx * 128) + ((uint32_t)(rg * 32) << 16); };
-    auto finish_x = [&](int ctx) {
-        const uint32_t trow = trow_of(ctx);
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            float v[16];
-            umma::tmem_ld16(trow + T_X + h * 32 + half * 16, v);
-            uint32_t f[16], pk[8];
-#pragma unroll
-            for (int j = 0; j < 16; j++) { v[j] = fmaxf(v[j], 0.f); f[j] = __float_as_uint(v[j]); }
-#pragma unroll
-            for (int j = 0; j < 8; j++) pk[j] = pack2<FP16>(v[2 * j], v[2 * j + 1]);
-            umma::tmem_st16(trow + T_X + h * 32 + half * 16, f);
-            umma::tmem_st8(trow + T_XB + h * 16 + half * 8, pk);
-        }
-    };
-    auto bias_mma = [&](uint32_t tmem_d, umma::DescBase w, int K, uint32_t idesc, bool accumulate) {
-        umma::mma_bf16(tmem_d, umma::desc_at(dONES, 0u), umma::desc_at(w, (uint32_t)(K / 8) * 128u), idesc, accumulate);
-    };
-    // --- per-context operand builders / epilogues (v4's code with the context's TMEM base and shared-memory regions) ---
-    auto build_conv1 = [&](int ctx) {
-        const uint8_t *pl = smem + S5_PLANES + ctx * PLANES_CTX + (live ? p_local * 343 : 0);
-        const uint32_t trow = trow_of(ctx);
-#pragma unroll
-        for (int c8 = 0; c8 < 2; c8++) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                float v2[2];
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int kk = h * 32 + c8 * 16 + q * 2 + e;
-                    const int tap = kk / 7, ch = kk % 7, dy = tap / 3, dx = tap % 3;
-                    v2[e] = (live && kk < 63) ? (float)pl[((cy + dy) * 7 + (cx + dx)) * 7 + ch] : 0.f;
-                }
-                pk[q] = pack2<FP16>(v2[0], v2[1]);
-            }
-            umma::tmem_st8(trow + T_XB + h * 16 + c8 * 8, pk);
-        }
-    };
-    auto epi_a = [&](int ctx) {                       // conv A output -> ReLU -> the three row-shifted copies of the 3x3 operand
-        float v[16];
-        umma::tmem_ld16(trow_of(ctx) + T_AO + h * 16, v);
-        const uint4 o0 = make_uint4(relu_pack2<FP16>(v[0], v[1]), relu_pack2<FP16>(v[2], v[3]), relu_pack2<FP16>(v[4], v[5]), relu_pack2<FP16>(v[6], v[7]));
-        const uint4 o1 = make_uint4(relu_pack2<FP16>(v[8], v[9]), relu_pack2<FP16>(v[10], v[11]), relu_pack2<FP16>(v[12], v[13]), relu_pack2<FP16>(v[14], v[15]));
-        if (live) {
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                const int oy = cy - (d - 1);
-                if (oy >= 0 && oy <= 4) {
-                    uint8_t *dst = smem + S_Y0 + ctx * S_YCTX + d * Y_COPY + (2 * h) * Y_LBO + (1 + r - 6 * (d - 1)) * 16;
-                    *reinterpret_cast<uint4 *>(dst) = o0;
-                    *reinterpret_cast<uint4 *>(dst + Y_LBO) = o1;
-                }
-            }
-        }
-    };
-    auto epi_b = [&](int ctx) {                       // conv B output -> ReLU -> M2B in TMEM
-        float v[16];
-        umma::tmem_ld16(trow_of(ctx) + T_AO + h * 16, v);
-        uint32_t pk[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) pk[q] = relu_pack2<FP16>(v[2 * q], v[2 * q + 1]);
-        umma::tmem_st8(trow_of(ctx) + T_XB + h * 8, pk);
-    };
-    // --- MMA issue of a layer for one context (one elected lane of warp 0); `first` = the weight slot has to be waited for ---
-    auto issue = [&](int ctx, int layer, bool first) {        // layer: 0 conv1, 1 conv A / heads, 2 conv B, 3 conv C
-        if (warp == 0) {
-            umma::fence_after_sync();
-            if (umma::elect_one()) {
-                const uint32_t tb = tm(ctx);
-                if (layer == 0) {
-                    if (!conv1_ready) { umma::mbar_wait(&barW[3], 0); conv1_ready = true; }
-                    bias_mma(tb + T_X, dWC1, 64, ID64, false);
-                    umma::gemm_issue_ts<64>(tb + T_X, tb + T_XB, dWC1, 0, ID64, true);
-                } else if (layer == 1) {
-                    if (first) { umma::mbar_wait(&barW[0], phW0); phW0 ^= 1; }
-                    bias_mma(tb + T_AO, dWA, 64, ID32, false);
-                    umma::gemm_issue_ts<64>(tb + T_AO, tb + T_XB, dWA, 0, ID32, true);
-                } else if (layer == 2) {
-                    if (first) { umma::mbar_wait(&barW[1], phW1); phW1 ^= 1; }
-                    const umma::DescBase dY = ctx ? dY1 : dY0;
-                    bias_mma(tb + T_AO, dWB, 288, ID32, false);
-#pragma unroll
-                    for (int d = 0; d < 3; d++)
-#pragma unroll
-                        for (int dxi = 0; dxi < 3; dxi++)
-#pragma unroll
-                            for (int ks = 0; ks < 2; ks++)
-                                umma::mma_bf16(tb + T_AO, umma::desc_at(dY, (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO)),
-                                               umma::desc_at(dWB, (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128)), ID32, true);
-                } else {
-                    if (first) { umma::mbar_wait(&barW[2], phW2); phW2 ^= 1; }
-                    bias_mma(tb + T_X, dWC, 32, ID64, true);
-                    umma::gemm_issue_ts<32>(tb + T_X, tb + T_XB, dWC, 0, ID64, true);
-                }
-                umma::commit(&bar[ctx]);
-            }
-            __syncwarp();
-        }
-    };
-
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const int64_t tile = 2 * pair + ctx;
-        const bool alone = 2 * pair + 1 >= n_tiles;        // the last pair of an odd tile count: context 1 has no tile
-        if (tile >= n_tiles) break;
-        const int c = ctx;
-        uint32_t pw[2];
-        load_planes(2 * (pair + gridDim.x) + ctx, pw);       // next pair's planes land while this tile computes
-        build_conv1(c); tmem_sync(); issue(c, 0, true);
-        wait_mma(c); finish_x(c); tmem_sync(); issue(c, 1, true);
-        for (int b = 0; b < 9; b++) {
-            const uint8_t *wnext = wb + tcl::W_BLOCK0 + ((b + 1) % 9) * tcl::W_BLOCK;
-            wait_mma(c);                                   // conv A done -> 3x3 operand -> conv B
-            slot_release(0, S5_WA, b < 8 ? wnext + tcl::W_BA : wb + tcl::W_HEADS, tcl::B_A, alone);
-            epi_a(c); smem_sync(); issue(c, 2, true);
-            wait_mma(c);                                   // conv B done -> M2B -> conv C onto the residual
-            slot_release(1, S5_WB, wnext + tcl::W_BB, tcl::B_B, alone);
-            epi_b(c); tmem_sync(); issue(c, 3, true);
-            wait_mma(c);                                   // conv C done -> ReLU in place -> conv A of the next block / heads
-            slot_release(2, S5_WC, wnext + tcl::W_BC, tcl::B_C, alone);
-            finish_x(c); tmem_sync(); issue(c, 1, true);
-        }
-        wait_mma(c);                                       // heads
-        slot_release(0, S5_WA, wb + tcl::W_BLOCK0 + tcl::W_BA, tcl::B_A, alone);
-        const int64_t pos0 = tile * POS;
-        const int n_pos = (int)min((int64_t)POS, n - pos0);
-        {
-            float v[16];
-            umma::tmem_ld16(trow_of(c) + T_AO + h * 16, v);
-            if (live && p_local < n_pos) {
-                if (h == 0) {
-#pragma unroll
-                    for (int q = 0; q < 16; q++) v[q] = fmaxf(v[q], 0.f);
-                    const int64_t pos = pos0 + p_local;
-                    const int k = cell * 16, chunk = k >= 208, kk = k - chunk * 208;
-                    uint8_t *dst = reinterpret_cast<uint8_t *>(polc) + (pos >> 7) * pd3::TILE_B + (chunk ? pd3::A0_B : 0) +
-                                   umma::op_offset((int)(pos & 127), kk, chunk ? 192 : 208);
-                    *reinterpret_cast<uint4 *>(dst) = pack8(v);
-                    *reinterpret_cast<uint4 *>(dst + 128) = pack8(v + 8);
-                } else {
-                    reinterpret_cast<float *>(smem + S5_VALC + c * VALC_CTX)[p_local * 25 + cell] = fmaxf(v[0], 0.f);
-                }
-            }
-        }
-        store_planes(c, pw);
-        umma::fence_before_sync();
-        ctx_barrier();
-        if (warp < n_pos) {                                // value head: dense_1 25 -> 32 ReLU, value_head 32 -> 1 tanh, fp32
-            const float *valc = reinterpret_cast<const float *>(smem + S5_VALC + c * VALC_CTX) + warp * 25;
-            float acc = sF[FO_D1B + lane];
-            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], sF[FO_D1W + k * 32 + lane], acc);
-            float sv = fmaxf(acc, 0.f) * sF[FO_VHW + lane];
-#pragma unroll
-            for (int off = 16; off; off >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, off);
-            if (lane == 0) value[pos0 + warp] = tanhf(sv + sF[FO_VHB]);
-        }
-        ctx_barrier();                                     // the value staging is rewritten by the next tile's heads epilogue
-    }
-    // the last refills must land before the CTA's shared memory is released: both contexts are past their last release here
-    umma::fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x < 32 && umma::elect_one()) {
-        // context 0's issuing lane has consumed every phase that was ever completed for it; one more refill per slot is in flight
-        umma::mbar_wait(&barW[0], phW0); umma::mbar_wait(&barW[1], phW1); umma::mbar_wait(&barW[2], phW2);
-        if (!conv1_ready) umma::mbar_wait(&barW[3], 0);
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x < 32) umma::tmem_free(tmem0, 256);
-}
-
 // Policy dense v3: logits[B x 294] = flat(policy conv)[B x 400] * W + b as 128-position x 80-output tiles (grid = row tiles x
 // 4 column quarters: 128 CTAs at the self-play batch of 4,096).  Both operands of a tile arrive as FOUR bulk copies issued by
 // one thread (the trunk kernel already wrote the activations in the operand layout; the quarter's weight rows are a contiguous
@@ -1267,10 +699,6 @@ int ccx_net_load_tc(ccx_handle *h, const void *bf16_blob_host, int64_t blob_byte
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pd3::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::S_TOTAL));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc4::S_TOTAL));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::S5_TOTAL));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::S5_TOTAL));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc6<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::S5_TOTAL));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_tc6<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::S5_TOTAL));
     return CCX_OK;
 }
 
@@ -1307,18 +735,6 @@ int ccx_net_forward_tc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int64
     {
         int64_t tiles = (n + tc4::POS - 1) / tc4::POS;
         unsigned grid = (unsigned)(tiles < 3 * h->num_sms ? tiles : 3 * h->num_sms);     // three resident CTAs per SM
-        static const bool v5 = getenv("CCX_TRUNK5") != nullptr, v6 = getenv("CCX_TRUNK6") != nullptr;
-        if (v6) {
-            int64_t pairs = (tiles + 1) / 2;
-            unsigned g6 = (unsigned)(pairs < 2 * h->num_sms ? pairs : 2 * h->num_sms);      // two resident CTAs (four tiles) per SM
-            if (tc->fp16) k_net_trunk_tc6<true><<<g6, 2 * tc4::THREADS, tc5::S5_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
-            else k_net_trunk_tc6<false><<<g6, 2 * tc4::THREADS, tc5::S5_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
-        } else if (v5) {
-            int64_t pairs = (tiles + 1) / 2;
-            unsigned g5 = (unsigned)(pairs < 2 * h->num_sms ? pairs : 2 * h->num_sms);      // two resident CTAs (four tiles) per SM
-            if (tc->fp16) k_net_trunk_tc5<true><<<g5, tc4::THREADS, tc5::S5_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
-            else k_net_trunk_tc5<false><<<g5, tc4::THREADS, tc5::S5_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
-        } else
         if (tc->fp16) k_net_trunk_tc4<true><<<grid, tc4::THREADS, tc4::S_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
         else k_net_trunk_tc4<false><<<grid, tc4::THREADS, tc4::S_TOTAL, stream>>>(tc->wb, tc->fb, planes, n, polc, value);
     }
