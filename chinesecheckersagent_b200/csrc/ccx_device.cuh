@@ -218,12 +218,13 @@ CCX_HD void movegen_rays(u64 occ_all, u64 cells, u64 (&dest)[6], const uint8_t *
     u64 occ = occ_all & ~o;
     u64 todo = o, reach = 0;
     for (;;) {
+        // any expansion order gives the same closure; the top set bit is the cheapest to find on the GPU (one FLO)
 #ifdef __CUDA_ARCH__
-        int i = __ffsll((long long)todo) - 1;
+        int i = 63 - __clzll((long long)todo);
 #else
-        int i = __builtin_ctzll(todo);
+        int i = 63 - __builtin_clzll(todo);
 #endif
-        todo &= todo - 1;
+        todo ^= 1ULL << i;
         u64 nw = expand_cell(i, occ, T) & ~(reach | o);
         reach |= nw;
         todo |= nw;

@@ -284,8 +284,8 @@ __device__ __forceinline__ bool expand_node(const TreeView &tv, int lane, int no
         u64 occ = occ_all & ~o, empty = ~occ & CCX_VALID;
         u64 todo = o, reach = 0;
         while (todo) {                                        // ray expansion of one cell per iteration (ccx_device.cuh)
-            int i = __ffsll((long long)todo) - 1;
-            todo &= todo - 1;
+            int i = 63 - __clzll((long long)todo);         // order-independent closure; top bit = one FLO
+            todo ^= 1ULL << i;
             u64 nw = expand_cell(i, occ, sT) & ~(reach | o);
             reach |= nw; todo |= nw;
         }
