@@ -314,6 +314,9 @@ k_greedy_candidates(const u64 *__restrict__ st, int64_t n, u64 *__restrict__ mas
 }
 
 // Game.start (game.py:58-100) with two GreedyPlayers
+// Tried and dropped (r01f): the flattened per-lane state machine of k_step_random_flat for this loop (greedy tail batched at 12
+// ready lanes) — same games bit for bit, 4.43e9 plies/s against 4.57e9 for this kernel: games of a warp end at different plies,
+// so the warp runs as long as its longest game either way and the heavier greedy tail runs for fewer lanes per execution.
 __global__ void __launch_bounds__(ENV_THREADS)
 k_play_greedy(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, int max_plies,
               u64 *__restrict__ counters, const uint8_t *__restrict__ jt)
