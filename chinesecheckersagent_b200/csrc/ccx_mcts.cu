@@ -23,6 +23,8 @@
 // on the parent's edge (eInfo) for every node but the root.
 // (Tried and dropped, r01c: keeping N_sum in the spare bits, maintained by the backup, so that sqrt(N_sum) is ready before
 // the edge statistics arrive — self-play +0.8 %, stub search -3 %: the extra read-modify-write per level costs what it saves.)
+// (Tried and dropped, r01f: an L2 prefetch of the chosen edge's W during the descent, for the backup that reads it — stub search
+// 5.49e8 -> 5.35e8 sims/s, self-play ply 18.37 -> 18.60 ms.)
 __device__ __forceinline__ u64 make_info(u32 eb, u32 ne, u32 winner, u32 expanded)
 {
     return (u64)eb | ((u64)(ne & 0xFF) << 32) | ((u64)(winner & 0xF) << 56) | ((u64)(expanded & 0xF) << 60);
