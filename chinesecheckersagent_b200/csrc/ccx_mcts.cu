@@ -810,7 +810,8 @@ static int run_net_rounds(ccx_handle *h, int64_t n, int32_t rounds, double cpuct
     // low-occupancy stretches of one half (the tail of its tree kernel = the deepest trees, the last tile of its trunk kernel)
     // are filled by the other half's kernels.  Same trees as the single-stream order, bit for bit.
     static const bool no_split = getenv("CCX_NO_SPLIT") != nullptr;
-    const bool split = !no_split && (h->net_mode == 1 || h->net_mode == 2) && n >= 8192;     // measured: 16,384 slots 65.1 -> 62.2 ms per ply; no gain at 4,096
+    static const int64_t split_min = getenv("CCX_SPLIT_MIN") ? atoll(getenv("CCX_SPLIT_MIN")) : 8192;     // diagnostics: batch size from which the two-half pipeline is used
+    const bool split = !no_split && (h->net_mode == 1 || h->net_mode == 2) && n >= split_min;     // measured: 16,384 slots 65.1 -> 62.2 ms per ply; no gain at 4,096
     int64_t part_n[2] = {split ? (n / 2) & ~(int64_t)127 : n, 0};          // halves start on a 128-position tile of the net's scratch
     part_n[1] = n - part_n[0];
     cudaStream_t streams[2] = {h->stream, h->stream};
