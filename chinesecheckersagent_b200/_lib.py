@@ -29,7 +29,8 @@ SIGNATURES = {
     "ccx_play_greedy": (i32, [vp, i64, vp, i64, u64, i32, vp]),
     "ccx_encode": (i32, [vp, i64, vp, vp, i32]),
     "ccx_mcts_search": (i32, [vp, i64, vp, i32, i32, f64, f64, i32, vp, i32, i32, vp, vp, vp, vp]),
-    "ccx_mcts_begin": (i32, [vp, i64, vp, i32, i32, i32]),
+    "ccx_mcts_begin": (i32, [vp, i64, vp, i32, i32, i32, i32]),
+    "ccx_mcts_set_tiebreak": (i32, [vp, i32, u64, i64]),
     "ccx_mcts_select": (i32, [vp, i64, f64, vp]),
     "ccx_mcts_run_net": (i32, [vp, i64, i32, f64, vp, i32, i32]),
     "ccx_mcts_expand_backup": (i32, [vp, i64, vp, vp, vp, i32, i32]),
@@ -44,7 +45,7 @@ SIGNATURES = {
     "ccx_net_eval": (i32, [vp, i64, vp, vp, vp]),
     "ccx_gamma_noise": (i32, [vp, i64, i32, f64, u64, u32, i64, vp]),
     "ccx_selfplay_advance": (i32, [vp, i64, vp, vp, vp, u64, i32, i64, vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
-    "ccx_selfplay_finish": (i32, [vp, i64, vp, i32, vp, vp, vp, vp, i32, i32, vp]),
+    "ccx_selfplay_finish": (i32, [vp, i64, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     "ccx_traj_pack": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
     "ccx_game_advance": (i32, [vp, i64, vp, vp, vp, u64, i64, f64, i32, i32, vp]),
     "ccx_greedy_generate": (i32, [vp, i64, vp, i64, u64, i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     "ccx_apply_host": (i32, [vp, i64, vp, vp, vp, vp]),
     "ccx_step_random_host": (i32, [vp, i64, vp, i64, u64, u32, i32, vp]),
     "ccx_encode_host": (i32, [vp, i64, vp, vp, i32]),
+    "ccx_info_host": (i32, [vp, i64, vp, vp]),
+    "ccx_greedy_candidates_host": (i32, [vp, i64, vp, vp]),
 }
 
 _lib = None
@@ -86,7 +89,7 @@ def load():
         fn = getattr(L, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if L.ccx_abi_version() != 1:
+    if L.ccx_abi_version() != 2:
         raise CcxError("libccx.so ABI version mismatch")
     _lib = L
     return L

@@ -9,7 +9,7 @@ the game states are plain device tensors both engines read and write."""
 import torch
 
 from .config import (C_PUCT, DEFAULT_SEED, DET_TREE_TAU, EVAL_GAMES, MCTS_SIMULATIONS, PLAYER_ONE, PLAYER_TWO,
-                     PROGRESS_MOVE_LIMIT, ST_RUNNING, TOTAL_MOVES_TILL_TAU0)
+                     PROGRESS_MOVE_LIMIT, ST_OVERFLOW, ST_RUNNING, TOTAL_MOVES_TILL_TAU0)
 from .engine import BatchedEnv, BatchedMCTS, _p
 
 GREEDY = "greedy"
@@ -19,7 +19,9 @@ class BatchedArena:
     """n games, player 1 = `p1`, player 2 = `p2`; each is a loaded ResidualCNN or the string "greedy"."""
 
     def __init__(self, p1, p2, n, seed=DEFAULT_SEED, game_id0=0, tree_tau=DET_TREE_TAU, enforce_move_limit=False,
-                 num_itr=MCTS_SIMULATIONS, cpuct=C_PUCT):
+                 num_itr=MCTS_SIMULATIONS, cpuct=C_PUCT, random_ties=True):
+        """random_ties: PUCT ties drawn uniformly like the reference's random.choice (MCTS.py:65-72), keyed per game — without
+        it (first maximal edge) every game of a match between two deterministic players at tau = 0.01 is the same game."""
         models = [p for p in (p1, p2) if p is not GREEDY and p != GREEDY]
         if not models:
             raise ValueError("at least one side must be a model (greedy-vs-greedy is BatchedEnv.play_greedy)")
@@ -32,7 +34,8 @@ class BatchedArena:
         self.eng = models[0].eng                                   # owns the game states and the bookkeeping kernel
         self.env = BatchedEnv(self.n, engine=self.eng, seed=seed, game_id0=game_id0)
         self.counters = self.eng.zeros((4,), torch.int64)
-        self.mcts = {id(m): BatchedMCTS(m.eng, cpuct=cpuct, num_itr=num_itr) for m in models}
+        self.mcts = {id(m): BatchedMCTS(m.eng, cpuct=cpuct, num_itr=num_itr, random_ties=random_ties, tie_seed=seed ^ 0xA7E4A,
+                                        tie_uid0=game_id0) for m in models}
         self.plies = 0
 
     def step(self):
@@ -58,7 +61,9 @@ class BatchedArena:
             if self.plies % poll_every == 0 and self.running() == 0:
                 break
         c = self.counters.cpu().tolist()
-        return dict(plies=c[0], p1_wins=c[1], p2_wins=c[2], stopped=c[3], unfinished=self.running(), games=self.n)
+        overflowed = int(((self.env.state[4] >> 56) == ST_OVERFLOW).sum().item())     # a search ran out of edge pool: not a draw
+        return dict(plies=c[0], p1_wins=c[1], p2_wins=c[2], stopped=c[3], overflowed=overflowed, unfinished=self.running(),
+                    games=self.n)
 
 
 def _load(model_or_path, engine=None):

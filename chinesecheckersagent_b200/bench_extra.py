@@ -13,6 +13,7 @@ MCTS_TREES = 4096            # BASELINE configs[3]
 MCTS_SIMS = 175              # config.py:35
 MCTS_BYTES_PER_SIM = 1400    # ~0.9 KB read + 0.5 KB written per simulation
 GREEDY_GAMES = 131072        # BASELINE configs[2]: 1M games / 8 GPUs
+FULL_GAMES = 8192            # cfg 5 played to completion: games started per GPU (two per slot)
 
 
 def _timed(fn, reps, world):
@@ -95,54 +96,113 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
     if peak_gbs:
         out["encode_bf16"]["frac_of_hbm_peak"] = out["encode_bf16"]["achieved_gbs"] / peak_gbs
     # ---- cfg 5: full self-play, MCTS + good_model policy/value net, 4,096 concurrent trees per GPU ---------------
+    # Headline = the ACCURATE net mode (tc_acc: split-precision tcgen05 kernels, max |dp| 2e-5 against the float64 restatement —
+    # the mode that meets the north_star's 1e-3 bar).  The 16-bit mode misses that bar (max |dp| 1.6e-2 on self-play positions)
+    # and is reported under a key that says so.
     weights = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "good_model_weights.npz")
     if os.path.exists(weights):
         from .model import ResidualCNN
-        from .selfplay import BatchedSelfPlay, all_gather_trajectories
-        model = ResidualCNN(engine=eng).load_weights(weights).set_kernel("tc")       # the throughput mode; the accurate default is timed below
-        sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=MCTS_TREES, seed=DEFAULT_SEED, rank=rank, world=world,
-                             num_itr=MCTS_SIMS, max_iters=16)
-        for _ in range(7):                                # 6 opening plies + 1 searched ply as warm-up
-            sp.step()
+        from .selfplay import BatchedSelfPlay, all_gather_trajectories, check_gathered_trajectories
+        model = ResidualCNN(engine=eng).load_weights(weights)
+
+        def ply_rate(kernel, slots, reps=2, **kw):
+            model.set_kernel(kernel)
+            sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=slots, seed=DEFAULT_SEED, rank=rank, world=world,
+                                 num_itr=MCTS_SIMS, max_iters=16, **kw)
+            for _ in range(8):                            # 6 opening plies + 2 searched plies as warm-up (the second one captures the round graph)
+                sp.step()
+            barrier()
+            l0 = eng.launches
+            t = _timed(sp.step, reps, world)
+            return dict(metric="mcts_sims_per_sec", value=world * slots * MCTS_SIMS * reps / t, unit="sims/s",
+                        net_evals_per_sec=world * slots * (MCTS_SIMS + 1) * reps / t, trees_per_gpu=slots, sims_per_move=MCTS_SIMS,
+                        ms_per_ply_iteration=t / reps * 1e3, gpu_launches=eng.launches - l0)
+        out["selfplay_net"] = dict(ply_rate("tc_acc", MCTS_TREES), net="tc_acc: split-precision tcgen05 kernels, max |dp| 2e-5 (meets the 1e-3 bar)",
+                                   tie_rule="reference (uniform among epsilon-ties, MCTS.py:65-72)")
+        out["selfplay_net_first_max_ties"] = dict(ply_rate("tc_acc", MCTS_TREES, random_ties=False), net="tc_acc", tie_rule="first maximal edge (parity mode)")
+        out["selfplay_net_16k_slots"] = dict(ply_rate("tc_acc", 4 * MCTS_TREES), net="tc_acc")
+        out["selfplay_net_fp16_out_of_tolerance"] = dict(ply_rate("tc", MCTS_TREES), net="16-bit tcgen05 kernels: max |dp| 1.6e-2 on self-play positions, "
+                                                                                         "MISSES the 1e-3 bar; throughput mode only")
+        out["selfplay_net_fp16_out_of_tolerance_16k_slots"] = dict(ply_rate("tc", 4 * MCTS_TREES), net="16-bit, out of tolerance")
+        # ---- cfg 5 for real: every rank plays FULL_GAMES games to their end in the accurate mode (train.py:58-64 semantics), the
+        # records are all-gathered over NCCL with their real, ragged counts (train.py:88-92) and checked on every rank
+        model.set_kernel("tc_acc")
+        import time
+        full = BatchedSelfPlay(eng, model.evaluate_states, n_slots=MCTS_TREES, seed=DEFAULT_SEED + 1, rank=rank, world=world,
+                               num_itr=MCTS_SIMS, max_iters=512, ring=True)
         barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launches
-        reps = 2
-        t = _timed(sp.step, reps, world)
-        sims = world * MCTS_TREES * MCTS_SIMS * reps
-        evals = world * MCTS_TREES * (MCTS_SIMS + 1) * reps
-        out["selfplay_net"] = {"metric": "mcts_sims_per_sec", "value": sims / t, "unit": "sims/s", "net_evals_per_sec": evals / t,
-                               "trees_per_gpu": MCTS_TREES, "sims_per_move": MCTS_SIMS, "ms_per_ply_iteration": t / reps * 1e3,
-                               "net": "good_model.h5 (fixture copy), tcgen05 kernels, fp16 operands / fp32 accumulate",
-                               "gpu_launches": eng.launches - l0}
-        # the same self-play step with four times the slots: the net runs at its large-batch rate and the tree kernels have
-        # 4x the warps to hide their latency chains behind (BASELINE names 4,096 trees/GPU; this is the throughput setting)
-        del sp
-        big = BatchedSelfPlay(eng, model.evaluate_states, n_slots=4 * MCTS_TREES, seed=DEFAULT_SEED, rank=rank, world=world,
-                              num_itr=MCTS_SIMS, max_iters=12)
-        for _ in range(7):
-            big.step()
+        e0.record()
+        st = full.play_games(FULL_GAMES)
+        e1.record()
+        torch.cuda.synchronize()
+        play_s = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=eng.device)
+        local = full.collect()
+        tot = torch.tensor([st["games"], st["records"], st["plies"], st["iterations"], st["discarded_repetition"] + st["discarded_no_progress"],
+                            st["discarded_overflow"], st["p1_wins"]], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(play_s, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ps = float(play_s.item())
+        games, records, plies, iters, discarded, overflow, p1 = tot.tolist()
+        searched = plies - 6 * (games + discarded + overflow)          # every started game plays 6 random opening plies (upper bound for games cut short)
+        out["selfplay_full_cfg5"] = {"games_started_per_gpu": FULL_GAMES, "slots_per_gpu": MCTS_TREES, "net": "tc_acc (accurate mode)",
+                                     "games_kept": games, "games_discarded": discarded, "games_overflowed": overflow, "p1_win_frac": p1 / max(games, 1),
+                                     "records": records, "plies": plies, "mean_plies_per_kept_game": (records + 6 * games) / max(games, 1),
+                                     "seconds": ps, "games_per_sec": (games + discarded + overflow) / ps, "records_per_sec": records / ps,
+                                     "mcts_sims_per_sec": searched * MCTS_SIMS / ps, "net_evals_per_sec": searched * (MCTS_SIMS + 1) / ps,
+                                     "iterations_per_gpu": iters / world, "gpu_launches": eng.launches - l0,
+                                     "note": "played to completion (slots restart while the budget of starts lasts, then drain): the drain tail runs at low occupancy"}
         barrier()
-        t = _timed(big.step, 2, world)
-        out["selfplay_net_16k_slots"] = {"metric": "mcts_sims_per_sec", "value": world * 4 * MCTS_TREES * MCTS_SIMS * 2 / t, "unit": "sims/s",
-                                         "trees_per_gpu": 4 * MCTS_TREES, "ms_per_ply_iteration": t / 2 * 1e3}
-        traj_src = big
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gathered = all_gather_trajectories(local)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        chk = check_gathered_trajectories(eng, local, gathered)
+        rec_local = int(local["v_y"].shape[0])
+        out["trajectory_all_gather"] = {"ms_first_call": float(gms.item()), "records_this_rank": rec_local, "records_total": chk["records_total"],
+                                        "counts_per_rank": chk["counts"], "bytes_this_rank": rec_local * (343 + 294 * 4 + 1 + 40),
+                                        "bytes_total": chk["records_total"] * (343 + 294 * 4 + 1 + 40), "synthetic_buffer": False,
+                                        "checks": "count = sum of rank counts; own slice intact; identical checksum on every rank; v_y in {+1,-1}; "
+                                                  "pi_y >= 0, sums to 1, supported on legal moves (%d sampled records)" % chk["legal_support_checked"],
+                                        "checksum": chk["checksum"], "backend": "nccl" if world > 1 else "none (1 rank)"}
+        if world > 1:
+            barrier()
+            t = _timed(lambda: all_gather_trajectories(local), 3, world)
+            out["trajectory_all_gather"]["ms"] = t / 3 * 1e3
+        del full, local, gathered
         # the reference-facing drop-in surface, one game at a time: AiPlayer.decide_move's MCTS(Node(Board()), model).search()
         # (player.py:157-158) through the Python mirror -- what a user gets by only swapping the imports
         from .board import Board
         from .MCTS import MCTS, Node
-        import time
+
         def one_decision():
             return MCTS(Node(Board(engine=eng), 1), model, num_itr=MCTS_SIMS).search()
-        one_decision()
-        torch.cuda.synchronize()
+        for kern in ("tc_acc", "tc"):
+            model.set_kernel(kern)
+            for _ in range(3):                               # direct run, graph capture, first replay
+                one_decision()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                one_decision()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 5
+            out["dropin_single_game_search" + ("" if kern == "tc_acc" else "_fp16")] = {
+                "metric": "ms_per_move_decision", "value": dt * 1e3, "unit": "ms", "sims_per_sec": MCTS_SIMS / dt, "net": kern,
+                "api": "MCTS(Node(Board(), 1), ResidualCNN).search(), one tree, all simulations inside ccx_mcts_run_net (graph replay)",
+                "graph_replays": int(eng.L.ccx_graph_replays(eng.h))}
+        b = Board(engine=eng)
         t0 = time.perf_counter()
-        for _ in range(3):
-            one_decision()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / 3
-        out["dropin_single_game_search"] = {"metric": "ms_per_move_decision", "value": dt * 1e3, "unit": "ms", "sims_per_sec": MCTS_SIMS / dt,
-                                            "api": "MCTS(Node(Board(), 1), ResidualCNN).search(), batch of one tree",
-                                            "reference_cpu": "~63 sims/s/core with a torch-CPU restatement of the net (BASELINE.md §2)"}
+        for _ in range(200):
+            b.get_valid_moves(1)
+        out["dropin_board_get_valid_moves_us"] = (time.perf_counter() - t0) / 200 * 1e6
         # net forward alone on a big batch
         planes = torch.randint(0, 7, (65536, 7, 7, 7), dtype=torch.uint8, device=eng.device)
         for kern in ("tc", "tc_acc", "simt"):
@@ -154,35 +214,9 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
             tf = 6.483264e6 * 65536 * reps / t / 1e12 * world
             out["net_forward_" + kern] = {"metric": "positions_per_sec", "value": world * 65536 * reps / t, "unit": "positions/s",
                                           "tflops": tf, "batch": 65536}
-            if kern == "tc" and peak_tflops:
-                out["net_forward_tc"]["roofline"] = {"bound": "tensor", "achieved": tf / world, "peak": peak_tflops, "unit": "TFLOP/s",
-                                                     "frac": tf / world / peak_tflops, "kernel": "k_net_trunk_tc4 + k_policy_dense_tc3"}
-        # cfg 5 with the accurate (split-precision) net: the mode in which the <= 1e-3 net bar and the >= 1e7 sims/s bar hold together
+            if kern in ("tc", "tc_acc") and peak_tflops:
+                out["net_forward_" + kern]["roofline"] = {"bound": "tensor", "achieved": tf / world, "peak": peak_tflops, "unit": "TFLOP/s",
+                                                          "frac": tf / world / peak_tflops,
+                                                          "kernel": "k_net_trunk_tc4 + k_policy_dense_tc3" if kern == "tc" else "k_net_trunk_acc + k_policy_dense_acc (useful flops; 3 MMAs per product)"}
         model.set_kernel("tc_acc")
-        acc_sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=MCTS_TREES, seed=DEFAULT_SEED, rank=rank, world=world,
-                                 num_itr=MCTS_SIMS, max_iters=12)
-        for _ in range(7):
-            acc_sp.step()
-        barrier()
-        t = _timed(acc_sp.step, 2, world)
-        out["selfplay_net_accurate"] = {"metric": "mcts_sims_per_sec", "value": world * MCTS_TREES * MCTS_SIMS * 2 / t, "unit": "sims/s",
-                                        "trees_per_gpu": MCTS_TREES, "ms_per_ply_iteration": t / 2 * 1e3,
-                                        "net": "tc_acc: split-precision tcgen05 kernels (max |dp| 2e-5 vs the float64 restatement)"}
-        del acc_sp
-        model.set_kernel("tc")
-        # trajectory all-gather (the only collective): time it when there is more than one rank
-        traj = traj_src.collect()
-        synthetic = int(traj["board_x"].shape[0]) == 0
-        if synthetic:        # no game finishes within the few plies timed above: gather a buffer the size of ~16 plies of 4,096 slots
-            m = 65536
-            traj = dict(board_x=torch.zeros((m, 7, 7, 7), dtype=torch.uint8, device=eng.device),
-                        pi_y=torch.zeros((m, 294), dtype=torch.float32, device=eng.device),
-                        v_y=torch.zeros((m,), dtype=torch.int8, device=eng.device))
-        if world > 1:
-            all_gather_trajectories(traj)
-            barrier()
-            t = _timed(lambda: all_gather_trajectories(traj), 3, world)
-            rec = int(traj["board_x"].shape[0])
-            out["trajectory_all_gather"] = {"ms": t / 3 * 1e3, "records_this_rank": rec, "synthetic_buffer": synthetic,
-                                            "bytes_per_rank": rec * (343 + 294 * 4 + 1), "backend": "nccl"}
     return out

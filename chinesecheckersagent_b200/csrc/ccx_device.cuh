@@ -206,6 +206,46 @@ CCX_HD u64 expand_cell_lut(int i, u64 occ, const uint8_t *__restrict__ T, const 
     return L;
 }
 
+// Second table layout ("occupancy-major"): T2[(len-1)*1024 + o7*8 + pos].  Lines of a sparse board share a handful of occupancy
+// patterns, so lanes of a warp mostly differ in `pos`: with the pattern-major layout above those lanes hit DIFFERENT words of
+// the SAME bank (bank = (o7 >> 2) & 31 whatever pos is), here they hit the same 8-byte row (a broadcast).
+#define CCX_JT2_BYTES (7 * 128 * 8)
+
+CCX_HD void build_jump_table2(uint8_t *T2, int first, int step)
+{
+    for (int e = first; e < CCX_JT2_BYTES; e += step) {
+        int len = e / 1024 + 1, o7 = (e / 8) % 128, pos = e % 8;
+        T2[e] = pos < len ? jump_line_entry(len, pos, o7) : 0;
+    }
+}
+
+CCX_HD u32 cell_diag_info2(int i)
+{
+    const int r = i >> 3, c = i & 7, k = c - r;
+    const int sh = k >= 0 ? k : -8 * k;
+    const int len = 7 - (k >= 0 ? k : -k);
+    const int pos = k >= 0 ? r : c;
+    return (u32)(sh & 0xFF) | ((u32)(((len > 0 ? len : 1) - 1) * 1024 + (pos & 7)) << 8);
+}
+
+CCX_HD u64 expand_cell_lut2(int i, u64 occ, const uint8_t *__restrict__ T2, const u32 *__restrict__ CI2)
+{
+    const u32 ci = CI2[i];
+    const int r = i >> 3, c = i & 7;
+    u32 row7 = (u32)(occ >> (8 * r)) & 0x7Fu;
+    u64 L = (u64)T2[6 * 1024 + row7 * 8 + c] << (8 * r);
+    u64 colx = (occ >> c) & 0x0001010101010101ULL;
+    u32 col7 = (u32)((colx * 0x0000040810204081ULL) >> 42) & 0x7Fu;
+    u64 colr = ((u64)T2[6 * 1024 + col7 * 8 + r] * 0x0002040810204081ULL) & 0x0001010101010101ULL;
+    L |= colr << c;
+    const int sh = (int)(ci & 0xFFu);
+    u64 diax = (occ >> sh) & 0x0040201008040201ULL;
+    u32 dia7 = (u32)((diax * 0x0001010101010101ULL) >> 48) & 0x7Fu;
+    u64 diar = ((u64)T2[(ci >> 8) + dia7 * 8] * 0x0001010101010101ULL) & 0x0040201008040201ULL;
+    L |= diar << sh;
+    return L;
+}
+
 // Board.get_valid_moves (board.py:215-222) with the ray formulation.  Same single-loop structure as movegen():
 // the loop body expands ONE cell of the thread's current checker (origin first, then every newly reached
 // landing cell), and a thread that exhausts a checker moves on to its next one inside the same loop.

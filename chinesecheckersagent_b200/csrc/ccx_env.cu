@@ -7,6 +7,9 @@
 #include "ccx_device.cuh"
 #include "ccx_internal.h"
 
+#ifndef CCX_STEP_DEFAULT_VARIANT
+#define CCX_STEP_DEFAULT_VARIANT 0
+#endif
 #define ENV_THREADS 64      // 1024 blocks of 2 warps for 65,536 games: 6.9 blocks per SM (148 SMs), 98.8 % balanced
 #define ENC_THREADS 128
 
@@ -297,6 +300,156 @@ k_step_random_flat(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1
 }
 
 // --------------------------------------------------------------------------------------------------
+// Generalised flattened step kernel: NS independent games ("streams") per THREAD and a choice of jump-table layout.
+// With 65,536 games there are only 3.5 warps per scheduler and every expansion is a ~100-cycle dependent chain
+// (find cell -> three table lookups -> scatter -> frontier update), so the issue slots sit idle 40 % of the time
+// (ncu r01e: issue active 57.7 %, stall `wait` 1.8 + short_scoreboard 0.9 per issue).  NS = 2 gives every warp two
+// independent chains to interleave (the expansions are written branch-free so that ptxas can schedule them as one
+// basic block) and halves the per-expansion share of the loop's bookkeeping (votes, branches); a stream only runs
+// dry while it waits for the warp's tail vote, which is the same idle fraction the one-game-per-lane kernel has.
+// LAYOUT 1 = occupancy-major jump table (ccx_device.cuh, fewer shared-memory bank conflicts).
+// Bit-identical to k_step_random / k_step_random_flat: same per-game Philox counters, same move lists.
+struct StepStream {
+    Game g;
+    u64 occ_all, o, occ, todo, reach, gid;
+    int64_t gi;
+    int cell, id, t;
+    u32 w1, w2;
+    bool act;
+};
+
+template <int LAYOUT>
+__device__ __forceinline__ u64 expand_lut_any(int c, u64 occ, const uint8_t *__restrict__ sT, const u32 *__restrict__ sCI)
+{
+    return LAYOUT ? expand_cell_lut2(c, occ, sT, sCI) : expand_cell_lut(c, occ, sT, sCI);
+}
+
+template <bool TRACE, int LAYOUT, int NS, int TPB>
+__global__ void __launch_bounds__(TPB, 1, 1)
+k_step_random_ilp(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies, int ready_threshold,
+                  u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games, const uint8_t *__restrict__ jt)
+{
+    constexpr int TBYTES = LAYOUT ? CCX_JT2_BYTES : CCX_JT_BYTES;
+    __shared__ __align__(16) uint8_t sT[TBYTES + 256];       // + zero pad: the dummy expansion of an idle stream looks up guard cell 63
+    __shared__ u64 sD[NS][6][TPB];
+    __shared__ u64 sNB[64];
+    __shared__ u32 sCI[64];
+    const int tid = threadIdx.x;
+    for (int q = tid; q < (TBYTES + 256) / 16; q += TPB)
+        reinterpret_cast<uint4 *>(sT)[q] = q < TBYTES / 16 ? reinterpret_cast<const uint4 *>(jt)[q] : make_uint4(0, 0, 0, 0);
+    for (int q = tid; q < 64; q += TPB) {
+        sNB[q] = ((CCX_VALID >> q) & 1) ? (neighbours(1ULL << q) & CCX_VALID) : 0ULL;
+        sCI[q] = LAYOUT ? cell_diag_info2(q) : (q == 63 || ((CCX_VALID >> q) & 1) ? cell_diag_info(q) : 0u);
+    }
+    __syncthreads();
+    StepStream S[NS];
+    unsigned alive[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        StepStream &X = S[s];
+        X.gi = ((int64_t)blockIdx.x * NS + s) * TPB + tid;
+        X.act = X.gi < n;
+        alive[s] = __ballot_sync(0xFFFFFFFFu, X.act);
+        X.g = load_game(st, n, X.act ? X.gi : 0);
+        X.gid = (u64)(gid0 + X.gi);
+        X.w1 = X.w2 = 0; X.t = 0; X.id = X.act ? 0 : 7;
+        X.occ_all = X.g.occ_me | X.g.occ_op;
+        X.cell = (int)(X.g.cells_me & 0xFF);
+        X.o = 1ULL << X.cell; X.occ = X.occ_all & ~X.o; X.todo = X.act ? X.o : 0ULL; X.reach = 0;
+    }
+    for (;;) {
+        // one expansion per stream, branch-free (a stream without work expands guard cell 63 and discards the result)
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            StepStream &X = S[s];
+            const u64 td = X.todo;
+            const bool has = td != 0;
+            const int c = (63 - __clzll((long long)td)) & 63;
+            u64 nw = expand_lut_any<LAYOUT>(c, X.occ, sT, sCI) & ~(X.reach | X.o);
+            nw = has ? nw : 0ULL;
+            X.reach |= nw;
+            X.todo = has ? ((td ^ (1ULL << c)) | nw) : 0ULL;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            StepStream &X = S[s];
+            if (X.todo == 0 && X.id < 6) {                      // checker exhausted: park its mask, start the next one
+                sD[s][X.id][tid] = (sNB[X.cell] & ~X.occ) | X.reach;
+                if (++X.id < 6) {
+                    X.cell = (int)((X.g.cells_me >> (8 * X.id)) & 0xFF);
+                    X.o = 1ULL << X.cell; X.occ = X.occ_all & ~X.o; X.todo = X.o; X.reach = 0;
+                }
+            }
+        }
+        int nready = 0; bool all_ready = true;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const unsigned r = __ballot_sync(0xFFFFFFFFu, S[s].id == 6);
+            nready += __popc(r);
+            all_ready = all_ready && r == alive[s];
+        }
+        if (!(nready >= ready_threshold || all_ready)) continue;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            StepStream &X = S[s];
+            if (X.id == 6) {
+                u64 dest[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) dest[k] = sD[s][k][tid];
+                u32 nonempty = 0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) nonempty += dest[k] != 0;
+                u64 *row = nullptr;
+                if (TRACE && X.gi < trace_games) {
+                    row = trace + ((int64_t)X.t * trace_games + X.gi) * CCX_TRACE_WORDS;
+                    bool p2 = (X.g.meta >> 48) & 1;
+                    row[0] = p2 ? X.g.occ_op : X.g.occ_me; row[1] = p2 ? X.g.occ_me : X.g.occ_op;
+                    row[2] = p2 ? X.g.cells_op : X.g.cells_me; row[3] = p2 ? X.g.cells_me : X.g.cells_op;
+                    row[4] = X.g.meta & 0x00FFFFFFFFFFFFFFULL;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) row[5 + k] = dest[k];
+                    row[11] = 0xFFULL | (0xFFULL << 8) | (0xFFULL << 24);
+                }
+                if (nonempty) {
+                    Philox4 rnd = philox4x32_10(k0, k1, step0 + (u32)X.t, 0u, (u32)X.gid, (u32)(X.gid >> 32));
+                    int from, to;
+                    int pid = pick_random(X.g, dest, nonempty, rnd.x, rnd.y, from, to);
+                    apply_move(X.g, pid, from, to);
+                    int win = winner_of(X.g);
+                    if (TRACE && row) row[11] = (u64)from | ((u64)to << 8) | ((u64)win << 16) | ((u64)pid << 24);
+                    if (win) { X.w1 += win == 1; X.w2 += win == 2; reset_start(X.g); }
+                }
+                if (++X.t == plies) X.id = 7;
+                else {
+                    X.occ_all = X.g.occ_me | X.g.occ_op;
+                    X.id = 0;
+                    X.cell = (int)(X.g.cells_me & 0xFF);
+                    X.o = 1ULL << X.cell; X.occ = X.occ_all & ~X.o; X.todo = X.o; X.reach = 0;
+                }
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            alive[s] = __ballot_sync(0xFFFFFFFFu, S[s].id != 7);
+            any = any || alive[s] != 0;
+        }
+        if (!any) break;
+    }
+    u32 w1 = 0, w2 = 0;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        if (!S[s].act) continue;
+        store_game(st, n, S[s].gi, S[s].g);
+        w1 += S[s].w1; w2 += S[s].w2;
+    }
+    if (w1) atomicAdd(&wins[0], (u64)w1);
+    if (w2) atomicAdd(&wins[1], (u64)w2);
+}
+
+__global__ void k_build_jump_table2(uint8_t *T2) { build_jump_table2(T2, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+
+// --------------------------------------------------------------------------------------------------
 // K4 greedy  (player.py:99-121, board_utils.py:3-7)
 
 __global__ void __launch_bounds__(ENV_THREADS)
@@ -460,8 +613,10 @@ int ccx_create(int device_ordinal, ccx_handle **out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
     if (cudaMalloc(&h->jump_table, CCX_JT_BYTES) != cudaSuccess) { delete h; return CCX_ERR_NOMEM; }
+    if (cudaMalloc(&h->jump_table2, CCX_JT2_BYTES) != cudaSuccess) { cudaFree(h->jump_table); delete h; return CCX_ERR_NOMEM; }
     k_build_jump_table<<<7, 128>>>(h->jump_table);
-    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(h->jump_table); delete h; return CCX_ERR_CUDA; }
+    k_build_jump_table2<<<7, 128>>>(h->jump_table2);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(h->jump_table); cudaFree(h->jump_table2); delete h; return CCX_ERR_CUDA; }
     *out = h;
     return CCX_OK;
 }
@@ -477,6 +632,7 @@ int ccx_destroy(ccx_handle *h)
     ccx_scratch *s[] = {&h->d_state, &h->d_aux0, &h->d_aux1, &h->d_aux2};
     for (auto *p : s) if (p->ptr) cudaFree(p->ptr);
     if (h->jump_table) cudaFree(h->jump_table);
+    if (h->jump_table2) cudaFree(h->jump_table2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -544,14 +700,35 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
     if (n == 0 || plies == 0) return CCX_OK;
     unsigned grid = blocks_for(n, ENV_THREADS);
     static const bool nested = getenv("CCX_STEP_NESTED") != nullptr;     // A/B switch for profiling the older kernel
+    // kernel variant (diagnostics / A-B runs): 0 = one game per lane (k_step_random_flat), 1 = the same with the occupancy-major
+    // jump table, 2 / 3 = two games per lane (k_step_random_ilp) with either table.  All variants are bit-identical.
+    const char *ve = getenv("CCX_STEP_VARIANT");
+    const int variant = ve ? atoi(ve) : CCX_STEP_DEFAULT_VARIANT;
+    const char *te = getenv("CCX_STEP_THRESH");
     const u32 s0 = (u32)seed, s1 = (u32)(seed >> 32);
-    if (trace && trace_games > 0) {
-        if (nested) k_step_random<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, (u64 *)trace, trace_games, h->jump_table);
-        else k_step_random_flat<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, (u64 *)trace, trace_games, h->jump_table);
+    const bool tr = trace && trace_games > 0;
+    u64 *tp = tr ? (u64 *)trace : nullptr;
+    const int64_t tg = tr ? trace_games : 0;
+#define CCX_ILP_LAUNCH(TR, LAY, NS, TPB, THR)                                                                                    \
+    k_step_random_ilp<TR, LAY, NS, TPB><<<blocks_for(n, NS * TPB), TPB, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, \
+                                                                                        te ? atoi(te) : (THR), (u64 *)wins, tp, tg,  \
+                                                                                        (LAY) ? h->jump_table2 : h->jump_table)
+    if (nested) {
+        if (tr) k_step_random<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, tp, tg, h->jump_table);
+        else k_step_random<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);
+    } else if (variant == 1) {
+        if (tr) CCX_ILP_LAUNCH(true, 1, 1, 64, 12); else CCX_ILP_LAUNCH(false, 1, 1, 64, 12);
+    } else if (variant == 2) {
+        if (tr) CCX_ILP_LAUNCH(true, 0, 2, 32, 24); else CCX_ILP_LAUNCH(false, 0, 2, 32, 24);
+    } else if (variant == 3) {
+        if (tr) CCX_ILP_LAUNCH(true, 1, 2, 32, 24); else CCX_ILP_LAUNCH(false, 1, 2, 32, 24);
+    } else if (variant == 4) {
+        if (tr) CCX_ILP_LAUNCH(true, 0, 1, 64, 12); else CCX_ILP_LAUNCH(false, 0, 1, 64, 12);
     } else {
-        if (nested) k_step_random<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);
+        if (tr) k_step_random_flat<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, tp, tg, h->jump_table);
         else k_step_random_flat<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);
     }
+#undef CCX_ILP_LAUNCH
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -650,6 +827,34 @@ int ccx_step_random_host(ccx_handle *h, int64_t n, uint64_t *state_host, int64_t
                               nullptr, 0))) return rc;
     CCX_CUDA(h, cudaMemcpyAsync(state_host, h->d_state.ptr, hot, cudaMemcpyDeviceToHost, h->stream));
     CCX_CUDA(h, cudaMemcpyAsync(wins_host, h->d_aux0.ptr, 16, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CCX_OK;
+}
+
+int ccx_greedy_candidates_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *cand_masks_host)
+{
+    if (!h || n < 0 || (n && (!state_host || !cand_masks_host))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    size_t sb = (size_t)n * CCX_STATE_WORDS * 8, mb = (size_t)n * 6 * 8;
+    int rc;
+    if ((rc = ccx_reserve(h, h->d_state, sb)) || (rc = ccx_reserve(h, h->d_aux0, mb))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_state.ptr, state_host, (size_t)n * 5 * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ccx_greedy_candidates(h, n, (const uint64_t *)h->d_state.ptr, (uint64_t *)h->d_aux0.ptr))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(cand_masks_host, h->d_aux0.ptr, mb, cudaMemcpyDeviceToHost, h->stream));
+    CCX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CCX_OK;
+}
+
+int ccx_info_host(ccx_handle *h, int64_t n, const uint64_t *state_host, int16_t *out_host)
+{
+    if (!h || n < 0 || (n && (!state_host || !out_host))) return CCX_ERR_ARG;
+    if (n == 0) return CCX_OK;
+    size_t sb = (size_t)n * CCX_STATE_WORDS * 8, ob = (size_t)n * 5 * sizeof(int16_t);
+    int rc;
+    if ((rc = ccx_reserve(h, h->d_state, sb)) || (rc = ccx_reserve(h, h->d_aux0, ob))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(h->d_state.ptr, state_host, (size_t)n * 5 * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ccx_info(h, n, (const uint64_t *)h->d_state.ptr, (int16_t *)h->d_aux0.ptr))) return rc;
+    CCX_CUDA(h, cudaMemcpyAsync(out_host, h->d_aux0.ptr, ob, cudaMemcpyDeviceToHost, h->stream));
     CCX_CUDA(h, cudaStreamSynchronize(h->stream));
     return CCX_OK;
 }

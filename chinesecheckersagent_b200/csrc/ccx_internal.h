@@ -29,6 +29,10 @@ struct ccx_handle {
     ccx_net_tc *net_tc = nullptr;
     ccx_net_acc *net_acc = nullptr;
     uint8_t *jump_table = nullptr;   // CCX_JT_BYTES, device: ray-jump lookup table (ccx_device.cuh)
+    uint8_t *jump_table2 = nullptr;  // CCX_JT2_BYTES, device: the same table, occupancy-major (k_step_random_ilp<LAYOUT = 1>)
+    int tie_mode = 0;           // PUCT tie rule of this handle's searches (ccx_mcts_set_tiebreak)
+    uint64_t tie_seed = 0;
+    int64_t tie_uid0 = 0;
     int net_mode = 0;           // 0 = fp32 SIMT kernel, 1 = 16-bit tcgen05 kernels, 2 = split-precision tcgen05 kernels (ccx_net_set_mode)
     // second stream + fork/join events of the two-half round pipeline (ccx_mcts_run_net), created on first use
     cudaStream_t stream2 = nullptr;

@@ -45,13 +45,17 @@ struct ccx_trees {
                                 // together with eChild, so a tree level costs two dependent memory round trips, not four
     uint16_t *eMove = nullptr;  // checker id << 8 | destination cell
     int32_t *path = nullptr;    // [T][PATH_MAX] edge indices of the current simulation
-    int32_t *tree_meta = nullptr;   // [T][8]: n_nodes, n_edges, overflow, path_len, leaf_node, leaf_kind, sims_done, spare
+    int32_t *tree_meta = nullptr;   // [T][8]: n_nodes, n_edges, overflow, path_len, leaf_node, leaf_kind, selections done, root hash
     size_t bytes = 0;
+    // PUCT tie rule (ccx_mcts_set_tiebreak): 0 = first maximal edge, 1 = the reference's epsilon-tie list with a Philox draw
+    int32_t tie_mode = 0;       // by value: selects the kernel instantiation (and keys the cached round graph)
+    u32 *tie_params = nullptr;  // device u32[4]: Philox key lo/hi, uid0 lo/hi — in memory so that a new seed does not invalidate the graph
 };
 
 struct TreeView {
     u64 *node; u32 *eN; double *eW; double *eP; double *eQ; int32_t *eChild; u64 *eInfo; uint16_t *eMove; int32_t *path; int32_t *meta;
     int32_t npt, ept, path_max;
+    const u32 *tie; u64 tree_index;
 };
 
 __device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
@@ -68,10 +72,13 @@ __device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
     v.path = t.path + tree * t.path_max;
     v.meta = t.tree_meta + tree * 8;
     v.npt = t.nodes_per_tree; v.ept = t.edges_per_tree; v.path_max = t.path_max;
+    v.tie = t.tie_params; v.tree_index = (u64)tree;
     return v;
 }
 
-enum { META_NNODES = 0, META_NEDGES = 1, META_OVERFLOW = 2, META_PATHLEN = 3, META_LEAF = 4, META_LEAFKIND = 5 };
+enum { META_NNODES = 0, META_NEDGES = 1, META_OVERFLOW = 2, META_PATHLEN = 3, META_LEAF = 4, META_LEAFKIND = 5, META_SELECTS = 6,
+       META_SERIAL = 7 };
+#define TIE_EPSILON 1e-5        // config.py:36 EPSILON
 enum { LEAF_EVAL = 0, LEAF_TERMINAL = 1, LEAF_DEAD = 2 };
 enum { EVAL_UNIFORM = 0, EVAL_HASH = 1, EVAL_NET = 2 };
 
@@ -163,11 +170,14 @@ __device__ __forceinline__ u64 leaf_hash(const Game &g, int lane)
 // is ONE dependent memory round trip (the chosen edge's pair comes out of a shuffle).  Pays off for the deep, narrow trees a
 // real net produces (round-based kernels: -1.9 % per self-play ply); costs bandwidth on the wide, shallow trees of the
 // uniform-prior stub (persistent kernel: -19 %), which therefore reads the pair after the arg-max.
-template <bool PREFETCH>
+template <bool PREFETCH, bool TIES>
 __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double cpuct, int &path_len, int &leaf_kind)
 {
     int node = 0, depth = 0;
     u64 info = tv.node[5];
+    // tie rule 1: simulation index and search serial of this tree key the Philox draws (read before lane 0 advances the counter)
+    const u32 sim_index = TIES ? (u32)tv.meta[META_SELECTS] : 0u;
+    const u32 serial = TIES ? (u32)tv.meta[META_SERIAL] : 0u;
     for (;;) {
         int winner = info_winner(info);
         int ne = info_ne(info);
@@ -193,14 +203,17 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
         nsum = __reduce_add_sync(FULL, nsum);                    // N_sum (MCTS.py:58-59)
         double sq = sqrt_count(nsum);                            // np.sqrt(N_sum)
         double best = -INFINITY; int besti = 0x7FFFFFFF;
+        double QUr[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             int j = lane + 32 * c;
+            QUr[c] = -INFINITY;
             if (j < ne) {
                 u32 N = Nr[c];
                 double Q = Wr[c];                                                               // MCTS.py:89,118
                 double U = __ddiv_rn(__dmul_rn(__dmul_rn(cpuct, Pr[c]), sq), __dadd_rn(1.0, (double)N));   // :62
                 double QU = __dadd_rn(Q, U);                                                    // :63
+                if (TIES) QUr[c] = QU;
                 if (QU > best) { best = QU; besti = j; }                                        // :65-67
             }
         }
@@ -213,6 +226,32 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
             u32 mhi = __reduce_max_sync(FULL, hi);
             u32 mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
             besti = (int)__reduce_min_sync(FULL, (hi == mhi && lo == mlo) ? (u32)besti : 0x7FFFFFFFu);
+            if (TIES) {
+                // MCTS.py:65-72: chosen_edges = [first edge attaining the maximum] + every later edge with fabs(QU - maxQU) < EPSILON
+                // (earlier near-ties were dropped by the reset at :66-67); random.choice -> Philox, index = mulhi(x, len)
+                const u64 mkey = ((u64)mhi << 32) | mlo;
+                const double M = __longlong_as_double((long long)((mkey >> 63) ? (mkey & 0x7FFFFFFFFFFFFFFFULL) : ~mkey));
+                u32 cm[4]; int total = 0;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int j = lane + 32 * c;
+                    bool cand = j < ne && (j == besti || (j > besti && fabs(QUr[c] - M) < TIE_EPSILON));
+                    cm[c] = __ballot_sync(FULL, cand);
+                    total += __popc(cm[c]);
+                }
+                if (total > 1) {
+                    const u64 uid = (((u64)tv.tie[3] << 32) | tv.tie[2]) + tv.tree_index;
+                    Philox4 rnd = philox4x32_10(tv.tie[0], tv.tie[1], sim_index, (u32)depth, (u32)uid ^ (serial * 0x9E3779B9u),
+                                                (u32)(uid >> 32) ^ 0x7E1Bu);
+                    int k = (int)__umulhi(rnd.x, (u32)total);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        int pc = __popc(cm[c]);
+                        if (k >= 0 && k < pc) { besti = 32 * c + (int)__fns(cm[c], 0, k + 1); k = -1; }
+                        else if (k >= 0) k -= pc;
+                    }
+                }
+            }
         }
         int e = eb + besti;
         if (lane == 0 && depth < tv.path_max) tv.path[depth] = e;
@@ -252,6 +291,7 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
         info = cinfo;
     }
     path_len = depth;
+    if (TIES && lane == 0) tv.meta[META_SELECTS] = (int32_t)(sim_index + 1u);
     return node;
 }
 
@@ -375,11 +415,18 @@ __device__ __forceinline__ void mix_root_noise(const TreeView &tv, int lane, con
 
 // A root whose status is not RUNNING or whose ply count is below min_ply gets an inactive tree
 // (META_OVERFLOW = 2): every later phase skips it (self-play: opening random plies, finished games).
-__device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u64 *roots, int64_t n, int64_t tree, int min_ply = 0)
+__device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u64 *roots, int64_t n, int64_t tree, int min_ply = 0,
+                                          int ply_parity = -1)
 {
     if (lane == 0) {
         u64 m = roots[4 * n + tree];
         bool inactive = min_ply >= 0 && ((m >> 56) != 0 || (int)((m >> 32) & 0xFFFF) < min_ply);
+        if (ply_parity >= 0 && (int)((m >> 32) & 1) != ply_parity) inactive = true;      // two-net self-play: the other net's plies
+        tv.meta[META_SELECTS] = 0;
+        // "search serial" of the tie rule: a hash of the root position, so that the draws of a search depend on (seed, tree uid,
+        // root) only — never on what the handle searched before
+        u64 z = roots[0 * n + tree] * 0x9E3779B97F4A7C15ULL + roots[1 * n + tree] * 0xC2B2AE3D27D4EB4FULL + (m & 0x0000FFFFFFFFFFFFULL);
+        tv.meta[META_SERIAL] = (int32_t)((u32)(z >> 32) ^ (u32)z);
         Game g = game_of_words(roots[0 * n + tree], roots[1 * n + tree], roots[2 * n + tree], roots[3 * n + tree],
                                roots[4 * n + tree] & 0x00FFFFFFFFFFFFFFULL);
         store_node(tv, 0, g, make_info(0, 0, (u32)winner_of(g), 0));
@@ -389,7 +436,7 @@ __device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u6
 }
 
 // Persistent search with an in-kernel evaluator: every warp runs all simulations of its tree.
-template <int EVAL>
+template <int EVAL, bool TIES>
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num_itr, double cpuct, int pre_expand,
               const double *__restrict__ noise, int noise_stride, const uint8_t *__restrict__ jt)
@@ -406,9 +453,11 @@ k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num
         eval_expand_backup<EVAL>(tv, lane, 0, 0, sT);
         if (noise) mix_root_noise(tv, lane, noise + tree * noise_stride);
     }
+    if (pre_expand && TIES && lane == 0) tv.meta[META_SELECTS] = 1;      // the round-based drivers spend selection 0 on the root expansion
+    __syncwarp();
     for (int it = 0; it < num_itr; it++) {                                   // MCTS.py:123-125
         int path_len, kind;
-        int leaf = select_leaf<false>(tv, lane, cpuct, path_len, kind);
+        int leaf = select_leaf<false, TIES>(tv, lane, cpuct, path_len, kind);
         __syncwarp();
         if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
         else if (kind == LEAF_EVAL) eval_expand_backup<EVAL>(tv, lane, leaf, path_len, sT);
@@ -420,6 +469,7 @@ k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num
 // ---- round-based pieces for an external evaluator (the policy/value net) ----------------------------
 // phase A: select one leaf per tree; terminal leaves are backed up at once; for the others the leaf's
 // state words are written to leaf_state[5][n] (input of ccx_encode / the net)
+template <bool TIES>
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_select(ccx_trees trees, int64_t n, double cpuct, u64 *__restrict__ leaf_state)
 {
@@ -438,7 +488,7 @@ k_mcts_select(ccx_trees trees, int64_t n, double cpuct, u64 *__restrict__ leaf_s
         return;
     }
     int path_len, kind;
-    int leaf = select_leaf<true>(tv, lane, cpuct, path_len, kind);
+    int leaf = select_leaf<true, TIES>(tv, lane, cpuct, path_len, kind);
     __syncwarp();
     if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
     if (lane < 5) leaf_state[lane * n + tree] = tv.node[(int64_t)leaf * NODE_WORDS + lane];
@@ -470,6 +520,7 @@ k_mcts_expand_backup(ccx_trees trees, int64_t n, const double *__restrict__ p, c
 // phase A': select + utils.to_model_input of the leaf (utils.py:101-160) written straight into the net's uint8
 // input batch, one warp per tree (the leaf's 343 bytes are staged in shared memory: zero, scatter the 36
 // labels, copy out)
+template <bool TIES>
 __device__ __forceinline__ void do_select_encode(const TreeView &tv, int lane, double cpuct, uint8_t *__restrict__ sp,
                                                  uint8_t *__restrict__ dst)
 {
@@ -480,7 +531,7 @@ __device__ __forceinline__ void do_select_encode(const TreeView &tv, int lane, d
         reset_start(g);
     } else {
         int path_len, kind;
-        int leaf = select_leaf<true>(tv, lane, cpuct, path_len, kind);
+        int leaf = select_leaf<true, TIES>(tv, lane, cpuct, path_len, kind);
         __syncwarp();
         if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
         if (lane == 0) { tv.meta[META_PATHLEN] = path_len; tv.meta[META_LEAF] = leaf; tv.meta[META_LEAFKIND] = kind; }
@@ -507,6 +558,7 @@ __device__ __forceinline__ void do_select_encode(const TreeView &tv, int lane, d
     for (int i = lane; i < 343; i += 32) dst[i] = sp[i];
 }
 
+template <bool TIES>
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_select_encode(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, uint8_t *__restrict__ planes)
 {
@@ -515,7 +567,7 @@ k_mcts_select_encode(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, ui
     int lane = threadIdx.x & 31;
     if (tree >= tree0 + n) return;
     TreeView tv = tree_view(trees, tree);
-    do_select_encode(tv, lane, cpuct, sP[threadIdx.x >> 5], planes + tree * 343);
+    do_select_encode<TIES>(tv, lane, cpuct, sP[threadIdx.x >> 5], planes + tree * 343);
 }
 
 // phase B': float64 softmax over all 294 logits (model.py:21-24, utils.py:187-192; same arithmetic as
@@ -567,6 +619,7 @@ k_mcts_softmax_expand_backup(ccx_trees trees, int64_t tree0, int64_t n, const fl
 
 // one launch per round in steady state: finish the previous round's leaf (softmax + expand + backup), then select and encode
 // the next one — the same warp owns the tree in both halves, so the halves need no grid-wide ordering between them
+template <bool TIES>
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
 k_mcts_round(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, const float *__restrict__ logits, const float *__restrict__ value,
              const double *__restrict__ noise, int noise_stride, int noise_normalize, uint8_t *__restrict__ planes,
@@ -583,16 +636,16 @@ k_mcts_round(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, const floa
                              noise_normalize, sPr[threadIdx.x >> 5], sT);
     __syncwarp();
     __threadfence_block();
-    do_select_encode(tv, lane, cpuct, sP[threadIdx.x >> 5], planes + tree * 343);
+    do_select_encode<TIES>(tv, lane, cpuct, sP[threadIdx.x >> 5], planes + tree * 343);
 }
 
 __global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
-k_mcts_init(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int min_ply)
+k_mcts_init(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int min_ply, int ply_parity)
 {
     int64_t tree = (int64_t)blockIdx.x * MCTS_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tree >= n) return;
     TreeView tv = tree_view(trees, tree);
-    init_tree(tv, threadIdx.x & 31, roots, n, tree, min_ply);
+    init_tree(tv, threadIdx.x & 31, roots, n, tree, min_ply, ply_parity);
 }
 
 // ---- finalize (MCTS.py:131-137): visit counts, pi = N^(1/tau) / sum, root Q ---------------------------
@@ -699,7 +752,7 @@ void ccx_trees_free(ccx_handle *h)
     ccx_trees *t = h->trees;
     if (!t) return;
     ccx_round_graph_free(h);
-    void *ptrs[] = {t->node, t->eN, t->eW, t->eP, t->eQ, t->eChild, t->eInfo, t->eMove, t->path, t->tree_meta};
+    void *ptrs[] = {t->node, t->eN, t->eW, t->eP, t->eQ, t->eChild, t->eInfo, t->eMove, t->path, t->tree_meta, t->tie_params};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete t;
     h->trees = nullptr;
@@ -726,6 +779,7 @@ static int trees_reserve(ccx_handle *h, int64_t n, int32_t num_itr, int32_t edge
     t = new (std::nothrow) ccx_trees();
     if (!t) return CCX_ERR_NOMEM;
     h->trees = t;
+    t->tie_mode = h->tie_mode;
     t->cap_trees = n; t->nodes_per_tree = npt; t->edges_per_tree = ept; t->path_max = pm;
     size_t T = (size_t)n;
     CCX_CUDA(h, cudaMalloc(&t->node, T * npt * NODE_WORDS * 8));
@@ -738,6 +792,11 @@ static int trees_reserve(ccx_handle *h, int64_t n, int32_t num_itr, int32_t edge
     CCX_CUDA(h, cudaMalloc(&t->eMove, T * ept * 2));
     CCX_CUDA(h, cudaMalloc(&t->path, T * pm * 4));
     CCX_CUDA(h, cudaMalloc(&t->tree_meta, T * 8 * 4));
+    CCX_CUDA(h, cudaMalloc(&t->tie_params, 16));
+    {
+        const u32 tp[4] = {(u32)h->tie_seed, (u32)(h->tie_seed >> 32), (u32)(uint64_t)h->tie_uid0, (u32)((uint64_t)h->tie_uid0 >> 32)};
+        CCX_CUDA(h, cudaMemcpyAsync(t->tie_params, tp, 16, cudaMemcpyHostToDevice, h->stream));    // pageable source: staged before the call returns
+    }
     t->bytes = T * ((size_t)npt * NODE_WORDS * 8 + (size_t)ept * 42 + (size_t)pm * 4 + 32);
     return CCX_OK;
 }
@@ -757,25 +816,39 @@ int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t eva
     int rc = trees_reserve(h, n, num_itr, edges_per_tree);
     if (rc) return rc;
     unsigned grid = tree_blocks(n);
-    if (evaluator == EVAL_UNIFORM)
-        k_mcts_search<EVAL_UNIFORM><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, num_itr,
-                                                                                      cpuct, pre_expand, root_noise, noise_stride, h->jump_table);
-    else
-        k_mcts_search<EVAL_HASH><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, num_itr,
-                                                                                   cpuct, pre_expand, root_noise, noise_stride, h->jump_table);
+#define CCX_SEARCH(EV, TI) k_mcts_search<EV, TI><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, num_itr, \
+                                                                                                   cpuct, pre_expand, root_noise, noise_stride, h->jump_table)
+    const bool ties = h->trees->tie_mode != 0;
+    if (evaluator == EVAL_UNIFORM) { if (ties) CCX_SEARCH(EVAL_UNIFORM, true); else CCX_SEARCH(EVAL_UNIFORM, false); }
+    else { if (ties) CCX_SEARCH(EVAL_HASH, true); else CCX_SEARCH(EVAL_HASH, false); }
+#undef CCX_SEARCH
     CCX_LAUNCHED(h);
     k_mcts_finalize<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, 1.0 / tau, visits, pi, q, n_nodes);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
 
-int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree, int32_t min_ply)
+int ccx_mcts_set_tiebreak(ccx_handle *h, int32_t mode, uint64_t seed, int64_t uid0)
 {
-    if (!h || n < 0 || num_itr < 0 || (n && !roots)) return CCX_ERR_ARG;
+    if (!h || (mode != 0 && mode != 1)) return CCX_ERR_ARG;
+    h->tie_mode = mode; h->tie_seed = seed; h->tie_uid0 = uid0;
+    if (h->trees) {
+        ccx_trees *t = h->trees;
+        t->tie_mode = mode;                           // by-value kernel argument: selects the instantiation, keys the cached round graph
+        const u32 tp[4] = {(u32)seed, (u32)(seed >> 32), (u32)(uint64_t)uid0, (u32)((uint64_t)uid0 >> 32)};
+        CCX_CUDA(h, cudaMemcpyAsync(t->tie_params, tp, 16, cudaMemcpyHostToDevice, h->stream));     // in stream order with the searches
+    }
+    return CCX_OK;
+}
+
+int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree, int32_t min_ply,
+                   int32_t ply_parity)
+{
+    if (!h || n < 0 || num_itr < 0 || (n && !roots) || ply_parity < -1 || ply_parity > 1) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
     int rc = trees_reserve(h, n, num_itr, edges_per_tree);
     if (rc) return rc;
-    k_mcts_init<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, min_ply);
+    k_mcts_init<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, (const u64 *)roots, n, min_ply, ply_parity);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -784,7 +857,8 @@ int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state
 {
     if (!h || !h->trees || n < 0 || n > h->trees->cap_trees || (n && !leaf_state)) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
-    k_mcts_select<<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, (u64 *)leaf_state);
+    if (h->trees->tie_mode) k_mcts_select<true><<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, (u64 *)leaf_state);
+    else k_mcts_select<false><<<tree_blocks(n), 32 * MCTS_WARPS_PER_BLOCK, 0, h->stream>>>(*h->trees, n, cpuct, (u64 *)leaf_state);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -840,11 +914,16 @@ static int run_net_rounds(ccx_handle *h, int64_t n, int32_t rounds, double cpuct
             cudaStream_t st = streams[q];
             const unsigned grid = tree_blocks(nq);
             const double *nz = root_noise;
-            if (r == 0)
-                k_mcts_select_encode<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, planes);
-            else if (r < rounds)
-                k_mcts_round<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, logits, value, r == 1 ? nz : nullptr,
-                                                                         noise_stride, noise_normalize, planes, h->jump_table);
+            const bool ties = h->trees->tie_mode != 0;
+            if (r == 0) {
+                if (ties) k_mcts_select_encode<true><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, planes);
+                else k_mcts_select_encode<false><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, planes);
+            } else if (r < rounds) {
+                if (ties) k_mcts_round<true><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, logits, value, r == 1 ? nz : nullptr,
+                                                                                       noise_stride, noise_normalize, planes, h->jump_table);
+                else k_mcts_round<false><<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, cpuct, logits, value, r == 1 ? nz : nullptr,
+                                                                                     noise_stride, noise_normalize, planes, h->jump_table);
+            }
             else
                 k_mcts_softmax_expand_backup<<<grid, 32 * MCTS_WARPS_PER_BLOCK, 0, st>>>(*h->trees, t0, nq, logits, value,
                                                                                          rounds == 1 ? nz : nullptr, noise_stride,

@@ -321,8 +321,8 @@ int ccx_net_set_mode(ccx_handle *h, int32_t mode)
     if (!h || (mode != 0 && mode != 1 && mode != 2)) return CCX_ERR_ARG;
     if (mode == 1 && !h->net_tc) return CCX_ERR_STATE;
     if (mode == 2 && (!h->net_tc || !h->net_acc || !h->net || !h->net->w)) return CCX_ERR_STATE;
+    if (h->net_mode != mode) h->epoch++;             // a cached round graph holds the old mode's kernels
     h->net_mode = mode;
-    h->epoch++;
     return CCX_OK;
 }
 

@@ -121,8 +121,8 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
         Philox4 r = philox4x32_10(k0, k1, (u32)ply, 0u, (u32)uid, (u32)(uid >> 32));
         id = pick_random(gm, dest, nonempty, r.x, r.y, from, to);
     } else {
-        if (tree_nodes[g] < 0) {         // pool overflow: the search result is unusable -> discard the game
-            if (lane == 0) { st[4 * n + g] = (meta & 0x00FFFFFFFFFFFFFFULL) | ((u64)CCX_ST_MOVE_LIMIT << 56); atomicAdd(&counters[5], 1ULL); }
+        if (tree_nodes[g] < 0) {         // pool overflow: the search result is unusable -> discard the game (counted by k_selfplay_finish)
+            if (lane == 0) st[4 * n + g] = (meta & 0x00FFFFFFFFFFFFFFULL) | ((u64)CCX_ST_OVERFLOW << 56);
             return;
         }
         // pi = N^(1/tau) / sum (MCTS.py:131-137); tau = DET_TREE_TAU once len(play_history) + 6 > 16 (selfplay.py:62-65)
@@ -136,8 +136,8 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
         to = (off / 7) * 8 + (off % 7);
         from = (int)((gm.cells_me >> (8 * id)) & 0xFF);
         // play_history.append((root.state, pi))  (selfplay.py:128)
-        if (iter < rec_iters) {
-            int64_t rec = (int64_t)iter * n + g;
+        {
+            int64_t rec = (int64_t)(iter % rec_iters) * n + g;          // ring over iterations
             if (lane < 5) rec_state[rec * 5 + lane] = st[lane * n + g];
             for (int a = lane; a < CCX_NUM_ACTIONS; a += 32) rec_visits[rec * CCX_NUM_ACTIONS + a] = (uint16_t)vis[a];
             if (lane == 0) rec_flag[rec] = (uint8_t)(REC_PENDING | (det ? REC_TAU_DET : 0));
@@ -171,8 +171,8 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
     st[2 * n + g] = np2 ? gm.cells_op : gm.cells_me; st[3 * n + g] = np2 ? gm.cells_me : gm.cells_op;
     st[4 * n + g] = gm.meta; st[5 * n + g] = lo; st[6 * n + g] = hi; st[7 * n + g] = aux;
     atomicAdd(&counters[0], 1ULL);                                       // plies played
-    if (move_log && iter < rec_iters)       // from | to<<8 | status after the move<<16 | 1<<24 (valid) | recorded-by-MCTS<<25
-        move_log[(int64_t)iter * n + g] = (u32)from | ((u32)to << 8) | ((u32)status << 16) | (1u << 24) |
+    if (move_log)       // from | to<<8 | status after the move<<16 | 1<<24 (valid) | recorded-by-MCTS<<25
+        move_log[(int64_t)(iter % rec_iters) * n + g] = (u32)from | ((u32)to << 8) | ((u32)status << 16) | (1u << 24) |
                                           ((ply - 1 >= random_plies ? 1u : 0u) << 25);
 }
 
@@ -206,7 +206,7 @@ k_game_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visits, 
     u64 uid = (u64)(uid0 + g);
     int id, from, to, status = CCX_ST_RUNNING;
     if (visits) {
-        if (tree_nodes && tree_nodes[g] < 0) status = CCX_ST_MOVE_LIMIT;        // pool overflow: the search result is unusable
+        if (tree_nodes && tree_nodes[g] < 0) status = CCX_ST_OVERFLOW;          // pool overflow: the search result is unusable
         else {
             bool det = tau != 1.0 || ply > tau0_after;                          // total_moves == plies played so far
             double inv_tau = ply > tau0_after ? 1.0 / 0.01 : 1.0 / tau;
@@ -254,18 +254,24 @@ k_game_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visits, 
 // limit, [5] discarded by pool overflow, [6] records kept, [7] games finished (kept)
 __global__ void __launch_bounds__(128)
 k_selfplay_finish(u64 *__restrict__ st, int64_t n, int iter, int32_t *__restrict__ start_iter, int64_t *__restrict__ serial,
-                  const u64 *__restrict__ rec_state, uint8_t *__restrict__ rec_flag, int rec_iters, int restart,
-                  u64 *__restrict__ counters)
+                  const u64 *__restrict__ rec_state, uint8_t *__restrict__ rec_flag, int rec_iters, int max_game_iters, int restart,
+                  long long *__restrict__ starts_left, u64 *__restrict__ counters)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     u64 meta = st[4 * n + g];
     int status = (int)(meta >> 56);
-    if (status == CCX_ST_RUNNING) return;
+    const int first = start_iter[g];
+    if (status == CCX_ST_RUNNING) {
+        // a game about to outgrow the record ring is discarded while all of its records are still intact
+        if (max_game_iters <= 0 || iter - first + 1 < max_game_iters) return;
+        status = CCX_ST_OVERFLOW;
+        st[4 * n + g] = (meta & 0x00FFFFFFFFFFFFFFULL) | ((u64)CCX_ST_OVERFLOW << 56);
+    }
+    if (first > iter) return;                                     // ended earlier and was not allowed to restart: already accounted for
     int kept = 0;
-    int last = iter < rec_iters ? iter : rec_iters - 1;
-    for (int it = start_iter[g]; it <= last; it++) {
-        int64_t rec = (int64_t)it * n + g;
+    for (int it = (iter - first >= rec_iters) ? iter - rec_iters + 1 : first; it <= iter; it++) {
+        int64_t rec = (int64_t)(it % rec_iters) * n + g;
         uint8_t f = rec_flag[rec];
         if ((f & 0xF) != REC_PENDING) continue;
         if (status == CCX_ST_WON_P1 || status == CCX_ST_WON_P2) {
@@ -282,12 +288,17 @@ k_selfplay_finish(u64 *__restrict__ st, int64_t n, int iter, int32_t *__restrict
     else if (status == CCX_ST_WON_P2) atomicAdd(&counters[2], 1ULL);
     else if (status == CCX_ST_REPETITION) atomicAdd(&counters[3], 1ULL);
     else if (status == CCX_ST_MOVE_LIMIT) atomicAdd(&counters[4], 1ULL);
+    else if (status == CCX_ST_OVERFLOW) atomicAdd(&counters[5], 1ULL);
     if (kept) { atomicAdd(&counters[6], (u64)kept); atomicAdd(&counters[7], 1ULL); }
-    if (restart) {
+    // train.py:58-64 plays exactly num_self_play games: a slot restarts only while the caller's budget of game starts lasts
+    bool again = restart != 0;
+    if (again && starts_left)                                    // old value > 0: one more start was available (the counter may go negative)
+        again = (long long)atomicAdd((unsigned long long *)starts_left, (unsigned long long)-1LL) > 0;
+    start_iter[g] = again ? iter + 1 : 0x7FFFFFFF;               // records settled; a slot that stays ended is never accounted twice
+    if (again) {
         st[0 * n + g] = CCX_START_OCC1; st[1 * n + g] = CCX_START_OCC2;
         st[2 * n + g] = CCX_START_CELLS1; st[3 * n + g] = CCX_START_CELLS2;
         st[4 * n + g] = CCX_START_META; st[5 * n + g] = CCX_HIST_EMPTY; st[6 * n + g] = CCX_HIST_EMPTY; st[7 * n + g] = 0;
-        start_iter[g] = iter + 1;
         serial[g] += 1;
     }
 }
@@ -338,7 +349,8 @@ int ccx_selfplay_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32
                          int32_t random_plies, int32_t tau_switch, int32_t move_limit, uint64_t *rec_state,
                          uint16_t *rec_visits, uint8_t *rec_flag, int32_t rec_iters, uint64_t *counters, uint32_t *move_log)
 {
-    if (!h || n < 0 || (n && (!state || !visits || !tree_nodes || !serial || !rec_state || !rec_visits || !rec_flag || !counters)))
+    if (!h || n < 0 || rec_iters < 1 || iter < 0 ||
+        (n && (!state || !visits || !tree_nodes || !serial || !rec_state || !rec_visits || !rec_flag || !counters)))
         return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
     k_selfplay_advance<<<(unsigned)((n + SP_WARPS - 1) / SP_WARPS), 32 * SP_WARPS, 0, h->stream>>>(
@@ -349,13 +361,16 @@ int ccx_selfplay_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32
 }
 
 int ccx_selfplay_finish(ccx_handle *h, int64_t n, uint64_t *state, int32_t iter, int32_t *start_iter, int64_t *serial,
-                        const uint64_t *rec_state, uint8_t *rec_flag, int32_t rec_iters, int32_t restart, uint64_t *counters)
+                        const uint64_t *rec_state, uint8_t *rec_flag, int32_t rec_iters, int32_t max_game_iters, int32_t restart,
+                        int64_t *starts_left, uint64_t *counters)
 {
-    if (!h || n < 0 || (n && (!state || !start_iter || !serial || !rec_state || !rec_flag || !counters))) return CCX_ERR_ARG;
+    if (!h || n < 0 || rec_iters < 1 || iter < 0 || (n && (!state || !start_iter || !serial || !rec_state || !rec_flag || !counters)))
+        return CCX_ERR_ARG;
+    if (max_game_iters > rec_iters) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
     k_selfplay_finish<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>((u64 *)state, n, iter, start_iter, serial,
-                                                                         (const u64 *)rec_state, rec_flag, rec_iters, restart,
-                                                                         (u64 *)counters);
+                                                                         (const u64 *)rec_state, rec_flag, rec_iters, max_game_iters,
+                                                                         restart, (long long *)starts_left, (u64 *)counters);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }

@@ -181,9 +181,16 @@ class BatchedMCTS:
     """Batched counterpart of MCTS.MCTS (MCTS.py:40-153): one tree per root state, all trees advanced one
     simulation at a time; returns visit-count policies."""
 
-    def __init__(self, engine, cpuct=3.5, num_itr=175, tree_tau=1.0, edges_per_tree=0):
+    def __init__(self, engine, cpuct=3.5, num_itr=175, tree_tau=1.0, edges_per_tree=0, random_ties=False, tie_seed=DEFAULT_SEED,
+                 tie_uid0=0):
+        """random_ties=False: PUCT ties go to the first maximal edge (bit-exact parity mode); True: the reference's rule
+        (MCTS.py:65-72: uniform among the epsilon-tie list), drawn with Philox keyed by (tie_seed, tie_uid0 + tree index)."""
         self.eng = engine
         self.cpuct, self.num_itr, self.tree_tau, self.edges_per_tree = float(cpuct), int(num_itr), float(tree_tau), int(edges_per_tree)
+        self.random_ties, self.tie_seed, self.tie_uid0 = bool(random_ties), int(tie_seed), int(tie_uid0)
+
+    def _tie_rule(self):
+        self.eng.call("ccx_mcts_set_tiebreak", 1 if self.random_ties else 0, self.tie_seed, self.tie_uid0)
 
     def _outputs(self, n, want_q=True):
         e = self.eng
@@ -196,6 +203,7 @@ class BatchedMCTS:
         n = roots.shape[1]
         visits, pi, q, nodes = self._outputs(n)
         stride = 0 if root_noise is None else root_noise.shape[1]
+        self._tie_rule()
         self.eng.call("ccx_mcts_search", n, _p(roots), int(evaluator), self.num_itr, self.cpuct, self.tree_tau,
                       int(bool(pre_expand)), _p(root_noise), stride, self.edges_per_tree, _p(visits), _p(pi), _p(q), _p(nodes))
         return dict(visits=visits, pi=pi, q=q, n_nodes=nodes)
@@ -207,7 +215,8 @@ class BatchedMCTS:
         e = self.eng
         leaf = e.empty((5, n), torch.int64)
         stride = 0 if root_noise is None else root_noise.shape[1]
-        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree, -1)
+        self._tie_rule()
+        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree, -1, -1)
         rounds = self.num_itr + (1 if pre_expand else 0)
         for r in range(rounds):
             e.call("ccx_mcts_select", n, self.cpuct, _p(leaf))
@@ -226,7 +235,8 @@ class BatchedMCTS:
         e = self.eng
         stride = 0 if root_noise is None else root_noise.shape[1]
         # min_ply_status: roots whose status is not RUNNING get an inactive tree (finished arena / self-play games)
-        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree, 0 if min_ply_status else -1)
+        self._tie_rule()
+        e.call("ccx_mcts_begin", n, _p(roots), self.num_itr + 1, self.edges_per_tree, 0 if min_ply_status else -1, -1)
         rounds = self.num_itr + (1 if pre_expand else 0)
         e.call("ccx_mcts_run_net", n, rounds, self.cpuct, _p(root_noise) if pre_expand else None, stride, 0)
         visits, pi, q, nodes = self._outputs(n)

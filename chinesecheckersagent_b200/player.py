@@ -41,8 +41,7 @@ class GreedyPlayer:
                 board.visualise(cur_player=self.player_num)
                 print('GreedyPlayer moved from {} to {}\n'.format(pick_start, pick_end))
             return board_utils.human_coord_to_np_index(pick_start), board_utils.human_coord_to_np_index(pick_end)
-        env = _engine.BatchedEnv(1, engine=board._eng, state=board._pack(self.player_num - 1))
-        masks = env.greedy_candidates().cpu().numpy().view(np.uint64)[:, 0]
+        masks = board._host().greedy(board._pack(self.player_num - 1))
         moves = []
         for cid in range(6):
             m = int(masks[cid])

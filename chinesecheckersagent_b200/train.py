@@ -184,41 +184,55 @@ def combine_prev_iters_train_data(board_x, pi_y, v_y, iteration_count, save_dir=
     return combine_train_data(board_x, pi_y, v_y, iteration_count - PAST_ITER_COUNT, iteration_count - 1, save_dir, pref)
 
 
-def generate_self_play(model, num_games=NUM_SELF_PLAY, n_slots=None, seed=0, max_iters=512, **selfplay_kw):
-    """generate_self_play_in_parallel (train.py:73-86) without the process pool: `num_games` finished games out of one
-    BatchedSelfPlay batch, returned as (board_x, pi_y, v_y) NumPy arrays in convert_to_train_data's format (all-gathered
-    over the ranks when torch.distributed is initialised)."""
+def generate_self_play(model, num_games=NUM_SELF_PLAY, n_slots=None, seed=0, max_iters=512, opponent=None, **selfplay_kw):
+    """generate_self_play_in_parallel (train.py:58-105) without the process pool: exactly `num_games` games are started across
+    the ranks (work shares like train.py:74-79: num_games // world each, the remainder on the last rank), every one is played
+    to its end, discarded games are dropped (train.py:62-64), and the records come back as (board_x, pi_y, v_y) NumPy arrays
+    in convert_to_train_data's format — all-gathered over the ranks when torch.distributed is initialised.
+    `opponent`: a second loaded ResidualCNN in its own Engine = the reference's model2 (selfplay.py:11-29)."""
+    import torch.distributed as dist
+
     from .selfplay import BatchedSelfPlay, all_gather_trajectories
-    slots = int(n_slots or max(32, min(4096, num_games)))
-    sp = BatchedSelfPlay(model.eng, model.evaluate_states, n_slots=slots, seed=seed, max_iters=max_iters, **selfplay_kw)
-    sp.run(target_games=num_games)
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+    share = num_games // world + (num_games % world if rank == world - 1 else 0)
+    slots = int(n_slots or max(32, min(4096, share)))
+    sp = BatchedSelfPlay(model.eng, model.evaluate_states, n_slots=slots, seed=seed, max_iters=max_iters, rank=rank, world=world,
+                         ring=True, opponent=opponent, **selfplay_kw)
+    stats = sp.play_games(share)
     traj = all_gather_trajectories(sp.collect())
-    return (traj["board_x"].cpu().numpy(), traj["pi_y"].cpu().numpy(), traj["v_y"].cpu().numpy().astype(np.float32)), sp.stats()
+    return (traj["board_x"].cpu().numpy(), traj["pi_y"].cpu().numpy(), traj["v_y"].cpu().numpy().astype(np.float32)), stats
 
 
 def evolve(cur_model_path, other_opponent_for_selfplay=None, iteration_count=0, best_model=None, max_iterations=1,
            num_self_play=NUM_SELF_PLAY, eval_games=EVAL_GAMES, data_dir=SAVE_TRAIN_DATA_DIR, weights_dir=SAVE_WEIGHTS_DIR,
            seed=0, epochs=EPOCHS, log=print, **selfplay_kw):
     """train.evolve (train.py:235-317) with a bound on the number of iterations: self-play with the best (else current)
-    model -> augment -> save data-for-iter-N.h5 -> pool with previous iterations -> train (retention min(1/iters, 0.5)) ->
-    save versionNNNN-weights.h5 -> arena against the best model, promote on more than int(0.55 * eval_games) wins.
-    Returns (cur_model_path, best_model, iteration_count) as they stand after the last iteration.
-    Self-play between two different nets (`other_opponent_for_selfplay`) is not built: the recorded search runs one net
-    per batch; the arena (arena.agent_match) is the two-net path."""
+    model — against `other_opponent_for_selfplay` when given (train.py:62, selfplay.py:11-29: the generator plays the even
+    plies, the opponent the odd ones) -> augment -> save data-for-iter-N.h5 -> pool with previous iterations -> train
+    (retention min(1/iters, 0.5)) -> save versionNNNN-weights.h5 -> arena against the best model, promote on more than
+    int(0.55 * eval_games) wins.  `cur_model_path=None` starts from a freshly initialised net like the reference's version 0
+    (train.py:41-46 `model_path is None`).  Returns (cur_model_path, best_model, iteration_count) after the last iteration."""
     import os
 
     from . import utils
     from .arena import evaluate
-    from .model import ResidualCNN, read_weight_file
-    if other_opponent_for_selfplay is not None:
-        raise NotImplementedError("self-play against a second net is not part of this build; see arena.agent_match")
     from .engine import Engine
+    from .model import ResidualCNN, read_weight_file
     engine = Engine(0)
+    opp_engine = Engine(0) if other_opponent_for_selfplay is not None else None
+    if cur_model_path is None:                                     # un-trained model: materialise it so that every stage can load it
+        os.makedirs(weights_dir, exist_ok=True)
+        torch.manual_seed(int(seed))
+        cur_model_path = TrainableResidualCNN().save_weights(os.path.join(weights_dir, "%s-untrained-weights.h5" % MODEL_PREFIX))
     for _ in range(int(max_iterations)):
         generator_path = best_model if best_model is not None else cur_model_path
         net = ResidualCNN(engine=engine).load_weights(generator_path)
-        (board_x, pi_y, v_y), stats = generate_self_play(net, num_self_play, seed=seed + iteration_count, **selfplay_kw)
-        log("iteration %d: self-play with %s: %s" % (iteration_count, generator_path, stats))
+        opponent = (ResidualCNN(engine=opp_engine).load_weights(other_opponent_for_selfplay)
+                    if other_opponent_for_selfplay is not None else None)
+        (board_x, pi_y, v_y), stats = generate_self_play(net, num_self_play, seed=seed + iteration_count, opponent=opponent,
+                                                         **selfplay_kw)
+        log("iteration %d: self-play with %s%s: %s" % (iteration_count, generator_path,
+                                                       " vs %s" % other_opponent_for_selfplay if opponent is not None else "", stats))
         if len(board_x):
             board_x, pi_y, v_y = utils.augment_train_data(board_x, pi_y, v_y)
             utils.save_train_data(board_x, pi_y, v_y, version=iteration_count, directory=data_dir, prefix=SAVE_TRAIN_DATA_PREF)

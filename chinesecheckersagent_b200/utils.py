@@ -9,8 +9,7 @@ from .config import BOARD_HEIGHT, BOARD_WIDTH, DTYPE_U8, PLAYER_ONE, PLAYER_TWO,
 
 def to_model_input(board, cur_player):
     """(7,7,7) float64 channels-last, like the reference; computed by the fused encoder kernel."""
-    env = _engine.BatchedEnv(1, engine=board._eng, state=board._pack(cur_player - 1))
-    return env.encode(DTYPE_U8)[0].cpu().numpy().astype(np.float64)
+    return board._host().encode(board._pack(cur_player - 1)).astype(np.float64)
 
 
 def encode_checker_index(checker_id, coord):
@@ -118,3 +117,26 @@ def count_items(v_y):
 def get_train_label_count(path):
     """count_labels.get_train_label_count: label histogram of one data-for-iter file."""
     return count_items(load_train_data(path)[2])
+
+
+# ---- small host helpers the reference's scripts call (utils.py:12-31) ------------------------------------------------
+def stress_message(message, extra_newline=False):
+    """The message framed by two '=' rules of its own length (greedy_vs_greedy.py:16, ai_vs_ai.py:36 print game banners with it)."""
+    rule = '=' * len(message)
+    pad = '\n' if extra_newline else ''
+    print(pad + rule + '\n' + message + '\n' + rule + pad)
+
+
+def find_version_given_filename(filename, prefixes=("version", "greedy-model")):
+    """4-digit version inside `<prefix>NNNN[-weights].h5` (ai_vs_ai.py:21 tags model.version with it), -1 when absent."""
+    import re
+    m = re.search(r'(?:%s)(\d{4})(?:-weights)?\.(?:h5|npz)' % '|'.join(re.escape(p) for p in prefixes), str(filename))
+    if m is None:
+        print('No 4-digit version number found in filename "{}"!'.format(filename))
+        return -1
+    return int(m.group(1))
+
+
+def cur_time():
+    import datetime
+    return datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S")

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define CCX_ABI_VERSION 1
+#define CCX_ABI_VERSION 2
 #define CCX_STATE_WORDS 8
 #define CCX_NUM_CHECKERS 6          /* config.py:8  */
 #define CCX_BOARD_W 7               /* config.py:10 */
@@ -52,7 +52,8 @@ enum { CCX_OK = 0, CCX_ERR_ARG = -1, CCX_ERR_CUDA = -2, CCX_ERR_NOMEM = -3, CCX_
        CCX_ERR_UNSUPPORTED = -5, CCX_ERR_OVERFLOW = -6 };
 /* status byte of META */
 enum { CCX_ST_RUNNING = 0, CCX_ST_WON_P1 = 1, CCX_ST_WON_P2 = 2, CCX_ST_REPETITION = 3,
-       CCX_ST_MOVE_LIMIT = 4, CCX_ST_NO_MOVES = 5 };
+       CCX_ST_MOVE_LIMIT = 4, CCX_ST_NO_MOVES = 5,
+       CCX_ST_OVERFLOW = 6 /* engine-side stop, no reference counterpart: the search's edge pool or the record ring overflowed */ };
 enum { CCX_RESET_START = 0, CCX_RESET_RANDOMISED = 1 };
 enum { CCX_DTYPE_U8 = 0, CCX_DTYPE_BF16 = 1, CCX_DTYPE_F32 = 2 };
 
@@ -142,8 +143,18 @@ int ccx_mcts_search(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t eva
 /* min_ply: roots that are not RUNNING or have fewer plies get an inactive tree that every phase skips
  * (self-play opening, selfplay.py:32; finished games); pass -1 to search every root.  n_nodes reports
  * -1 for an overflowed pool and -2 for an inactive tree. */
+/* ply_parity: -1 = every root; 0 / 1 = only roots whose ply count is even / odd get an active tree (two-net self-play:
+ * model1 moves on even plies, model2 on odd ones, selfplay.py:29,58). */
 int ccx_mcts_begin(ccx_handle *h, int64_t n, const uint64_t *roots, int32_t num_itr, int32_t edges_per_tree,
-                   int32_t min_ply);
+                   int32_t min_ply, int32_t ply_parity);
+/* PUCT tie rule of this handle's searches (MCTS.py:65-72).  mode 0 (default): the first maximal edge (what the reference
+ * does when `random.choice` is replaced by seq[0]; the bit-exact parity mode).  mode 1: the reference's rule — chosen_edges =
+ * the first edge attaining the maximum plus every LATER edge with fabs(QU - max) < EPSILON (1e-5, config.py:36), one of them
+ * drawn uniformly — with Philox4x32-10 in place of Python's `random`: key = seed, counter = (simulation index of the tree,
+ * depth, tree uid ^ root hash), index = mulhi(x, len(chosen_edges)).  uid of tree i = uid0 + i; root hash = fold32(OCC1 *
+ * 0x9E3779B97F4A7C15 + OCC2 * 0xC2B2AE3D27D4EB4F + (META & 0xFFFFFFFFFFFF)): the draws of a search are a function of
+ * (seed, uid, root position), never of what the handle searched before. */
+int ccx_mcts_set_tiebreak(ccx_handle *h, int32_t mode, uint64_t seed, int64_t uid0);
 int ccx_mcts_select(ccx_handle *h, int64_t n, double cpuct, uint64_t *leaf_state);
 /* The same rounds with the library's own net as the evaluator (ccx_net_load / ccx_net_load_tc, mode from
  * ccx_net_set_mode), fused: per round  select + to_model_input -> net forward -> float64 softmax + expand +
@@ -206,8 +217,10 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes);
  * for the driver loop.  Records live in caller-owned device buffers indexed rec = iter*n + slot:
  *   rec_state uint64[rec_iters*n][5], rec_visits uint16[rec_iters*n][294], rec_flag uint8[rec_iters*n]
  *   (low nibble: 0 none, 1 pending, 2 mover won, 3 mover lost, 4 dropped; 0x10 = pi uses DET_TREE_TAU).
+ *   The buffers are a RING over iterations: the record of (iter, slot) lives at row (iter % rec_iters)*n + slot, so a caller
+ *   that consumes finished records in time (chinesecheckersagent_b200/selfplay.py does) can play indefinitely.
  * counters uint64[8] += {plies, P1 wins, P2 wins, repetition discards, progress-limit discards,
- *   pool-overflow discards, records kept, games kept}.
+ *   overflow discards (edge pool or record ring; status CCX_ST_OVERFLOW), records kept, games kept}.
  * ccx_gamma_noise: raw Gamma(alpha) draws [n][stride] for the root Dirichlet noise (selfplay.py:121).
  * ccx_selfplay_advance: opening plies (ply < random_plies) take selfplay.make_random_move's choice
  *   (selfplay.py:83-104); later plies sample np.random.choice(294, p=pi) from this iteration's visit counts
@@ -215,7 +228,11 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes);
  *   (state, visits) (selfplay.py:128), then apply the move and the repetition / progress / win / useless-move
  *   rules in the reference's order (selfplay.py:40-74).  Game uid = serial*total_slots + uid0 + slot keys Philox.
  * ccx_selfplay_finish: labels the records of games that ended (reward from the mover's point of view,
- *   utils.py:65-71) or drops them for discarded games (selfplay.py:47,74); restart != 0 resets the slot.
+ *   utils.py:65-71) or drops them for discarded games (selfplay.py:47,74); a running game that has been recorded for
+ *   max_game_iters iterations (> 0) is discarded as CCX_ST_OVERFLOW before its records wrap around the ring.
+ *   restart != 0 resets the slot of an ended game — if starts_left (device int64, may be NULL) is NULL or still positive
+ *   (it is decremented per restart): train.py:58-64 plays exactly num_self_play games, so the caller sets
+ *   starts_left = num_self_play - n and drains.  A slot that may not restart keeps its final status.
  * ccx_traj_pack: gathers kept records rows[m] into out_state uint64[5][m] (feed to ccx_encode for board_x),
  *   pi_y float32[m][294] and v_y int8[m]. */
 int ccx_gamma_noise(ccx_handle *h, int64_t n, int32_t stride, double alpha, uint64_t seed, uint32_t iter, int64_t uid0,
@@ -226,7 +243,8 @@ int ccx_selfplay_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32
                          uint16_t *rec_visits, uint8_t *rec_flag, int32_t rec_iters, uint64_t *counters,
                          uint32_t *move_log /* may be NULL: [rec_iters*n] from | to<<8 | status<<16 | 1<<24 | mcts<<25 */);
 int ccx_selfplay_finish(ccx_handle *h, int64_t n, uint64_t *state, int32_t iter, int32_t *start_iter, int64_t *serial,
-                        const uint64_t *rec_state, uint8_t *rec_flag, int32_t rec_iters, int32_t restart, uint64_t *counters);
+                        const uint64_t *rec_state, uint8_t *rec_flag, int32_t rec_iters, int32_t max_game_iters, int32_t restart,
+                        int64_t *starts_left, uint64_t *counters);
 int ccx_traj_pack(ccx_handle *h, int64_t m, const int64_t *rows, const uint64_t *rec_state, const uint16_t *rec_visits,
                   const uint8_t *rec_flag, uint64_t *out_state, float *pi_y, int8_t *v_y);
 
@@ -245,7 +263,8 @@ int ccx_debug_umma_gemm_rows(ccx_handle *h, const void *A, int32_t rows, int32_t
  * (uint32[n][294] from ccx_mcts_finalize, tree_nodes its n_nodes): the move is sampled from N^(1/tau), tau switching
  * to DET_TREE_TAU once more than tau0_after plies were played (player.py:151-154).  visits == NULL: the mover is the
  * GreedyPlayer (uniform among filtered_best_moves).  Then winner / repetition stop / optional move limit
- * (move_limit = 0: off).  counters uint64[4] += {plies, P1 wins, P2 wins, stopped games}. */
+ * (move_limit = 0: off).  A search whose edge pool overflowed stops the game with CCX_ST_OVERFLOW.
+ * counters uint64[4] += {plies, P1 wins, P2 wins, stopped games}. */
 int ccx_game_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32_t *visits, const int32_t *tree_nodes, uint64_t seed,
                      int64_t uid0, double tau, int32_t tau0_after, int32_t move_limit, uint64_t *counters);
 
@@ -273,6 +292,8 @@ int ccx_apply_host(ccx_handle *h, int64_t n, uint64_t *state_host, const uint8_t
 int ccx_step_random_host(ccx_handle *h, int64_t n, uint64_t *state_host, int64_t game_id0, uint64_t seed,
                          uint32_t step0, int32_t plies, uint64_t *wins_host);
 int ccx_encode_host(ccx_handle *h, int64_t n, const uint64_t *state_host, void *out_host, int dtype);
+int ccx_info_host(ccx_handle *h, int64_t n, const uint64_t *state_host, int16_t *out_host);
+int ccx_greedy_candidates_host(ccx_handle *h, int64_t n, const uint64_t *state_host, uint64_t *cand_masks_host);
 
 #ifdef __cplusplus
 }

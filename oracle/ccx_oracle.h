@@ -87,6 +87,15 @@ void orc_mcts_stub_batch(const uint64_t *st, int64_t n, int32_t num_itr, double 
                          int pre_expand, uint32_t *visits /* [n][294] */, double *pi /* [n][294] */,
                          int32_t *n_nodes, int32_t nthreads);
 
+/* batched searches over packed roots; orc_mcts_batch_ties adds the reference's epsilon-tie list (MCTS.py:65-72) with the engine's
+ * Philox draw in place of random.choice (ccx_mcts_set_tiebreak mode 1) */
+void orc_mcts_batch(const uint64_t *st, int64_t n, int32_t num_itr, double cpuct, double tau, int pre_expand,
+                    int evaluator, const double *noise, int32_t noise_stride, uint32_t *visits, double *pi,
+                    int32_t *n_nodes, double *q, int32_t nthreads);
+void orc_mcts_batch_ties(const uint64_t *st, int64_t n, int32_t num_itr, double cpuct, double tau, int pre_expand,
+                         int evaluator, const double *noise, int32_t noise_stride, uint32_t *visits, double *pi,
+                         int32_t *n_nodes, double *q, int32_t nthreads, uint64_t tie_seed, int64_t tie_uid0);
+
 /* pthread parallel-for used by the batched drivers (nthreads <= 1 runs inline) */
 typedef void (*orc_range_fn)(void *ctx, int64_t lo, int64_t hi);
 void orc_parallel_for(orc_range_fn fn, void *ctx, int64_t n, int32_t nthreads);

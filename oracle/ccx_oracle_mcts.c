@@ -47,24 +47,39 @@ static void free_arena(arena *a)
     free(a->all);
 }
 
-/* MCTS.py:49-76 with first-maximum tie-break */
-static onode *move_to_leaf(onode *root, double cpuct, oedge **crumbs, int *ncrumbs)
+/* tie rule of the engine's mode 1 (include/ccx.h ccx_mcts_set_tiebreak): `random.choice(chosen_edges)` (MCTS.py:72) drawn with
+ * Philox4x32-10, key = seed, counter = (simulation index, depth, uid ^ roothash*0x9E3779B9, (uid >> 32) ^ 0x7E1B), index = mulhi(x, len) */
+typedef struct { int on; uint64_t seed, uid; uint32_t serial, sim; } tie_rule;
+
+/* MCTS.py:49-76.  tie == NULL or !tie->on: first-maximum tie-break (random.choice -> seq[0]); else the reference's
+ * chosen_edges list (strict '>' resets it, fabs(QU - maxQU) < EPSILON appends, :65-69) with the Philox draw above. */
+static onode *move_to_leaf(onode *root, double cpuct, oedge **crumbs, int *ncrumbs, const tie_rule *tie)
 {
     onode *cur = root;
     *ncrumbs = 0;
+    int depth = 0;
     while (cur->n_edges != 0) {
         double maxQU = -INFINITY;
         int64_t N_sum = 0;
         oedge *chosen = NULL;
+        oedge *list[128]; int nlist = 0;
         for (int i = 0; i < cur->n_edges; i++) N_sum += cur->edges[i].N;              /* :58-59 */
         for (int i = 0; i < cur->n_edges; i++) {
             oedge *e = &cur->edges[i];
             double U = cpuct * e->P * sqrt((double)N_sum) / (1. + (double)e->N);         /* :62 */
             double QU = e->Q + U;                                                        /* :63 */
-            if (QU > maxQU) { maxQU = QU; chosen = e; }                                  /* :65-67 */
+            if (QU > maxQU) { maxQU = QU; chosen = e; nlist = 0; list[nlist++] = e; }   /* :65-67 */
+            else if (fabs(QU - maxQU) < 1e-5 && nlist < 128) list[nlist++] = e;          /* :68-69, EPSILON config.py:36 */
+        }
+        if (tie && tie->on && nlist > 1) {                                               /* :72 random.choice(chosen_edges) */
+            uint32_t out[4];
+            orc_philox((uint32_t)tie->seed, (uint32_t)(tie->seed >> 32), tie->sim, (uint32_t)depth,
+                       (uint32_t)tie->uid ^ (tie->serial * 0x9E3779B9u), (uint32_t)(tie->uid >> 32) ^ 0x7E1Bu, out);
+            chosen = list[(uint32_t)(((uint64_t)out[0] * (uint64_t)nlist) >> 32)];
         }
         crumbs[(*ncrumbs)++] = chosen;                                                   /* :73 */
         cur = chosen->out;
+        depth++;
     }
     return cur;
 }
@@ -123,9 +138,20 @@ static void expand_and_backup(arena *a, onode *leaf, oedge **crumbs, int ncrumbs
     }
 }
 
+static int mcts_search_impl(const uint64_t rootw[8], int32_t num_itr, double cpuct, double tau, int pre_expand,
+                            int canonical, const double *root_noise, orc_eval_fn eval, void *ctx,
+                            uint32_t visits[ORC_NACT], double pi[ORC_NACT], int32_t *n_nodes, double *q_out, tie_rule *tie);
+
 int orc_mcts_search(const uint64_t rootw[8], int32_t num_itr, double cpuct, double tau, int pre_expand,
                     int canonical, const double *root_noise, orc_eval_fn eval, void *ctx,
                     uint32_t visits[ORC_NACT], double pi[ORC_NACT], int32_t *n_nodes, double *q_out)
+{
+    return mcts_search_impl(rootw, num_itr, cpuct, tau, pre_expand, canonical, root_noise, eval, ctx, visits, pi, n_nodes, q_out, NULL);
+}
+
+static int mcts_search_impl(const uint64_t rootw[8], int32_t num_itr, double cpuct, double tau, int pre_expand,
+                            int canonical, const double *root_noise, orc_eval_fn eval, void *ctx,
+                            uint32_t visits[ORC_NACT], double pi[ORC_NACT], int32_t *n_nodes, double *q_out, tie_rule *tie)
 {
     arena a = {0};
     orc_board b; int tm;
@@ -145,7 +171,8 @@ int orc_mcts_search(const uint64_t rootw[8], int32_t num_itr, double cpuct, doub
             }
     }
     for (int it = 0; it < num_itr; it++) {                                               /* MCTS.py:123-125 */
-        onode *leaf = move_to_leaf(root, cpuct, crumbs, &ncrumbs);
+        if (tie) tie->sim = (uint32_t)(it + (pre_expand ? 1 : 0));                       /* the engine spends selection 0 on the root expansion */
+        onode *leaf = move_to_leaf(root, cpuct, crumbs, &ncrumbs, tie);
         expand_and_backup(&a, leaf, crumbs, ncrumbs, canonical, eval, ctx);
     }
     double sum = 0.0;
@@ -209,6 +236,7 @@ typedef struct {
     const uint64_t *st; int64_t n; int32_t num_itr; double cpuct, tau; int pre_expand, evaluator;
     const double *noise; int32_t noise_stride;
     uint32_t *visits; double *pi; int32_t *n_nodes; double *q;
+    int tie_on; uint64_t tie_seed; int64_t tie_uid0;
 } mcts_job;
 
 static void mcts_range(void *vj, int64_t lo, int64_t hi)
@@ -217,11 +245,13 @@ static void mcts_range(void *vj, int64_t lo, int64_t hi)
     for (int64_t i = lo; i < hi; i++) {
         uint64_t w[8];
         for (int k = 0; k < 8; k++) w[k] = jb->st[k * jb->n + i];
-        orc_mcts_search(w, jb->num_itr, jb->cpuct, jb->tau, jb->pre_expand, 1,
-                        jb->noise ? jb->noise + i * jb->noise_stride : NULL,
-                        jb->evaluator == 0 ? eval_uniform : eval_hash, NULL,
-                        jb->visits + i * ORC_NACT, jb->pi + i * ORC_NACT, jb->n_nodes ? jb->n_nodes + i : NULL,
-                        jb->q ? jb->q + i * ORC_NACT : NULL);
+        uint64_t z = w[0] * 0x9E3779B97F4A7C15ull + w[1] * 0xC2B2AE3D27D4EB4Full + (w[4] & 0x0000FFFFFFFFFFFFull);   /* include/ccx.h: root hash */
+        tie_rule tie = { jb->tie_on, jb->tie_seed, (uint64_t)(jb->tie_uid0 + i), (uint32_t)(z >> 32) ^ (uint32_t)z, 0 };
+        mcts_search_impl(w, jb->num_itr, jb->cpuct, jb->tau, jb->pre_expand, 1,
+                         jb->noise ? jb->noise + i * jb->noise_stride : NULL,
+                         jb->evaluator == 0 ? eval_uniform : eval_hash, NULL,
+                         jb->visits + i * ORC_NACT, jb->pi + i * ORC_NACT, jb->n_nodes ? jb->n_nodes + i : NULL,
+                         jb->q ? jb->q + i * ORC_NACT : NULL, jb->tie_on ? &tie : NULL);
     }
 }
 
@@ -231,7 +261,17 @@ void orc_mcts_batch(const uint64_t *st, int64_t n, int32_t num_itr, double cpuct
                     int evaluator, const double *noise, int32_t noise_stride, uint32_t *visits, double *pi,
                     int32_t *n_nodes, double *q, int32_t nthreads)
 {
-    mcts_job jb = { st, n, num_itr, cpuct, tau, pre_expand, evaluator, noise, noise_stride, visits, pi, n_nodes, q };
+    mcts_job jb = { st, n, num_itr, cpuct, tau, pre_expand, evaluator, noise, noise_stride, visits, pi, n_nodes, q, 0, 0, 0 };
+    orc_parallel_for(mcts_range, &jb, n, nthreads);
+}
+
+/* the same with the engine's tie rule 1 (ccx_mcts_set_tiebreak(h, 1, seed, uid0)) */
+void orc_mcts_batch_ties(const uint64_t *st, int64_t n, int32_t num_itr, double cpuct, double tau, int pre_expand,
+                         int evaluator, const double *noise, int32_t noise_stride, uint32_t *visits, double *pi,
+                         int32_t *n_nodes, double *q, int32_t nthreads, uint64_t tie_seed, int64_t tie_uid0)
+{
+    mcts_job jb = { st, n, num_itr, cpuct, tau, pre_expand, evaluator, noise, noise_stride, visits, pi, n_nodes, q,
+                    1, tie_seed, tie_uid0 };
     orc_parallel_for(mcts_range, &jb, n, nthreads);
 }
 

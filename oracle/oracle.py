@@ -19,7 +19,13 @@ _u64p = ctypes.POINTER(ctypes.c_uint64)
 
 
 def build(force=False):
-    """Compile the oracle with gcc (seconds)."""
+    """Compile the oracle with gcc (seconds) and, where the read-only reference checkout exists (build container), stage its
+    .py files under oracle/_ref/reference so that they travel to the GPU box (refrun.stage; git-ignored)."""
+    try:
+        import refrun
+        refrun.stage()
+    except Exception as e:                      # staging is best effort: the port below is always available
+        print("oracle: reference staging skipped: %s" % e)
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
@@ -50,6 +56,8 @@ def lib():
         L.orc_greedy_list_batch.argtypes = [vp, i64, vp, vp]
         L.orc_mcts_stub_batch.argtypes = [vp, i64, i32, dbl, dbl, i32, vp, vp, vp, i32]
         L.orc_mcts_batch.argtypes = [vp, i64, i32, dbl, dbl, i32, i32, vp, i32, vp, vp, vp, vp, i32]
+        L.orc_mcts_batch_ties.argtypes = [vp, i64, i32, dbl, dbl, i32, i32, vp, i32, vp, vp, vp, vp, i32, u64, i64]
+        L.orc_mcts_batch_ties.restype = None
         L.orc_mcts_stub_batch.restype = None
         L.orc_mcts_batch.restype = None
         for name in ("orc_movegen_batch", "orc_encode_batch", "orc_greedy_batch", "orc_step_random",
@@ -216,8 +224,9 @@ def philox(k0, k1, c0, c1, c2, c3):
 EVAL_UNIFORM, EVAL_HASH = 0, 1
 
 
-def mcts(st, num_itr=175, cpuct=3.5, tau=1.0, pre_expand=0, evaluator=EVAL_UNIFORM, noise=None, nthreads=1):
-    """MCTS.search on every root (canonical edge order, first-maximum tie-break).
+def mcts(st, num_itr=175, cpuct=3.5, tau=1.0, pre_expand=0, evaluator=EVAL_UNIFORM, noise=None, nthreads=1, ties=None):
+    """MCTS.search on every root (canonical edge order).  ties=None: first-maximum tie-break; ties=(seed, uid0): the
+    reference's epsilon-tie list (MCTS.py:65-72) with the engine's Philox draw (ccx_mcts_set_tiebreak mode 1).
     Returns (visits[n,294] u32, pi[n,294] f64, root Q[n,294] f64, node count[n])."""
     st = np.ascontiguousarray(st, dtype=np.uint64)
     n = st.shape[1]
@@ -229,6 +238,11 @@ def mcts(st, num_itr=175, cpuct=3.5, tau=1.0, pre_expand=0, evaluator=EVAL_UNIFO
     if noise is not None:
         noise = np.ascontiguousarray(noise, dtype=np.float64)
         stride = noise.shape[1]
+    if ties is not None:
+        lib().orc_mcts_batch_ties(_ptr(st), n, num_itr, cpuct, tau, pre_expand, evaluator,
+                                  _ptr(noise) if noise is not None else None, stride, _ptr(visits), _ptr(pi), _ptr(nodes),
+                                  _ptr(q), nthreads, int(ties[0]), int(ties[1]))
+        return visits, pi, q, nodes
     lib().orc_mcts_batch(_ptr(st), n, num_itr, cpuct, tau, pre_expand, evaluator,
                          _ptr(noise) if noise is not None else None, stride, _ptr(visits), _ptr(pi), _ptr(nodes),
                          _ptr(q), nthreads)

@@ -1,9 +1,10 @@
 """Import shim that makes the UNMODIFIED reference importable in the build container.
 
 TEST INFRASTRUCTURE ONLY.  This module is used by ``tests/golden/gen_golden.py`` to run the real
-reference (``/root/reference``) and write golden fixtures; nothing in the product package, the
-``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports it (``/root/reference`` does not exist on the
-GPU box).
+reference (``/root/reference``) and write golden fixtures; and by ``oracle/refrun.py``
+(bench.py's CPU-baseline legs, the drop-in tests) to run the copy staged under ``oracle/_ref/reference``
+(git-ignored; ``/root/reference`` itself does not exist on the GPU box).  Nothing in the product package
+imports it.
 
 Why a shim is needed: ``utils.py:3`` imports h5py, ``model.py:3-7`` imports keras,
 ``loss.py:1`` imports tensorflow (none installed, no network) and ``utils.py:7`` imports
@@ -17,7 +18,8 @@ import sys
 import types
 import warnings
 
-REFERENCE_DIR = os.environ.get("CCX_REFERENCE_DIR", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")     # refrun.stage(): travels with gpurun
+REFERENCE_DIR = os.environ.get("CCX_REFERENCE_DIR") or ("/root/reference" if os.path.isdir("/root/reference") else _STAGED)
 
 
 class _Inert:

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     L = ctypes.CDLL(lib_path)
     for s in header_symbols():
         assert hasattr(L, s), "libccx.so lacks %s declared in include/ccx.h" % s
-    assert L.ccx_abi_version() == 1
+    assert L.ccx_abi_version() == 2
 
 
 def test_python_binding_table_matches_header():

@@ -30,7 +30,8 @@ def test_committed_gpu_line_has_the_contract_keys():
 
 def run_reference(env_extra):
     env = dict(os.environ, **env_extra)
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--no-extra"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=300)
     assert p.returncode == 0, p.stderr
     return p.stdout.strip()
@@ -40,7 +41,13 @@ def test_reference_arm_runs_on_cpu_and_only_rank0_prints():
     out = run_reference({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
     d = json.loads(out.splitlines()[-1])
     assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["metric"] == "env_steps_per_sec" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    import refrun
+    # the unmodified reference when its staged copy exists (build container, GPU box), else the C port of the same loop
+    assert d["cpu_baseline"]["kind"] == ("reference" if refrun.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(bench.GAMES_PER_GPU)          # the same dict the GPU arm prints (same_config)
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
     assert run_reference({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == ""

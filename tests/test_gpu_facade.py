@@ -12,6 +12,15 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def first_maximum_ties():
+    """the oracle comparisons below pin the deterministic tie rule; the reference-like random rule has its own tests"""
+    from chinesecheckersagent_b200.MCTS import MCTS
+    old, MCTS.TIE_RULE = MCTS.TIE_RULE, "first"
+    yield
+    MCTS.TIE_RULE = old
+
+
 def test_board_start_position_known_answer():
     from chinesecheckersagent_b200.board import Board
     b = Board()
@@ -156,3 +165,57 @@ def test_stochastic_greedy_branch_samples_legal_forward_moves():
     assert min(adv) > 0
     want = sum(d * d for d in dists) / sum(dists)
     assert abs(np.mean(adv) - want) < 0.15
+
+
+def test_native_search_path_equals_the_per_simulation_round_trips():
+    """MCTS(...).search() with the package's own net runs all simulations inside libccx (ccx_mcts_run_net, graph replay);
+    the visit counts must be the ones the per-simulation select / predict / expand_backup round trips produce."""
+    from chinesecheckersagent_b200.board import Board, default_engine
+    from chinesecheckersagent_b200.MCTS import MCTS, Node
+    from chinesecheckersagent_b200.model import ResidualCNN
+    model = ResidualCNN(engine=default_engine()).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+
+    class Foreign:                                   # same arithmetic, but opaque to the fast path: forces the round trips
+        version = 0
+
+        def predict(self, x):
+            return model.predict(x)
+    for flow in ("decide_move", "make_move"):
+        out = []
+        for m in (model, Foreign(), model, model):   # the third / fourth native search replay the cached graph
+            np.random.seed(4)
+            tree = MCTS(Node(Board(), 1), m, num_itr=40)
+            assert tree._native == (m is model)
+            if flow == "make_move":
+                tree.expandAndBackUp(tree.root, breadcrumbs=[])
+            pi, edge = tree.search()
+            out.append((pi.copy(), [e.stats['N'] for e in tree.root.edges], [e.stats['W'] for e in tree.root.edges]))
+        for o in out[1:]:
+            assert np.array_equal(out[0][0], o[0]) and out[0][1] == o[1]
+            assert np.allclose(out[0][2], o[2], rtol=0, atol=1e-12)
+        assert sum(out[0][1]) == (39 if flow == "decide_move" else 40)
+
+
+def test_random_tie_rule_is_seeded_by_python_random_and_spreads_first_visits():
+    """MCTS.TIE_RULE = "random" (the default): ties within EPSILON are drawn uniformly (MCTS.py:65-72).  With the uniform
+    stub every edge of a fresh node ties, so the first visits must not all go to edge 0, and `random.seed` must make the
+    search reproducible like it does for the reference's random.choice."""
+    import random
+
+    from chinesecheckersagent_b200.board import Board
+    from chinesecheckersagent_b200.MCTS import MCTS, Node
+    MCTS.TIE_RULE = "random"
+    runs = []
+    for seed in (11, 11, 12):
+        random.seed(seed); np.random.seed(0)
+        root = Node(Board(), 1)
+        MCTS(root, StubModel(), num_itr=8).search()
+        runs.append([e.stats['N'] for e in root.edges])
+    assert runs[0] == runs[1] and sum(runs[0]) == 7
+    firsts = set()
+    for seed in range(12):
+        random.seed(100 + seed); np.random.seed(0)
+        root = Node(Board(), 1)
+        MCTS(root, StubModel(), num_itr=2).search()          # simulation 1 expands the root, simulation 2 visits one edge
+        firsts.add([e.stats['N'] for e in root.edges].index(1))
+    assert len(firsts) >= 4, firsts

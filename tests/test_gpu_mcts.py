@@ -102,3 +102,44 @@ def test_edge_pool_overflow_is_flagged(eng):
     roots = dev(cfg4_roots(8))
     out = BatchedMCTS(eng, edges_per_tree=200).search(roots)
     assert np.all(out["n_nodes"].cpu().numpy() == -1)
+
+
+@pytest.mark.parametrize("evaluator,pre_expand", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_reference_tie_rule_vs_oracle(eng, evaluator, pre_expand):
+    """ccx_mcts_set_tiebreak mode 1 = MCTS.py:65-72 as written (the first maximal edge plus later edges within EPSILON,
+    one of them drawn uniformly) with Philox standing in for random.choice.  The C oracle builds the chosen_edges list
+    literally and draws with the same counter, so N, Q and pi must agree bit for bit — in the persistent kernel and in the
+    round-based pipeline — and must differ from the first-maximum rule."""
+    from chinesecheckersagent_b200.engine import BatchedMCTS
+    roots = cfg4_roots(192, seed=77)
+    m = BatchedMCTS(eng, num_itr=120, random_ties=True, tie_seed=0xC0FFEE, tie_uid0=1000)
+    out = m.search(dev(roots), evaluator=evaluator, pre_expand=bool(pre_expand))
+    v, pi, q, nodes = orc.mcts(roots, 120, 3.5, 1.0, pre_expand, evaluator, nthreads=8, ties=(0xC0FFEE, 1000))
+    assert np.array_equal(out["visits"].cpu().numpy().astype(np.uint32), v)
+    assert np.array_equal(out["q"].cpu().numpy(), q)
+    assert np.array_equal(out["pi"].cpu().numpy(), pi)
+    assert np.array_equal(out["n_nodes"].cpu().numpy(), nodes)
+    again = m.search(dev(roots), evaluator=evaluator, pre_expand=bool(pre_expand))       # no dependence on the handle's history
+    assert torch.equal(again["visits"], out["visits"])
+    first = BatchedMCTS(eng, num_itr=120).search(dev(roots), evaluator=evaluator, pre_expand=bool(pre_expand))
+    assert not torch.equal(first["visits"], out["visits"])
+    if evaluator == 0:
+        n = roots.shape[1]
+        p = torch.full((n, 294), 1 / 294., dtype=torch.float64, device="cuda")
+        z = torch.zeros((n,), dtype=torch.float64, device="cuda")
+        rb = m.search_with(dev(roots), lambda leaf: (p, z), pre_expand=bool(pre_expand))
+        assert torch.equal(rb["visits"], out["visits"]) and torch.equal(rb["q"], out["q"])
+
+
+def test_uniform_ties_spread_the_first_visits(eng):
+    """With the uniform stub every edge of a fresh node ties (N_sum = 0 => U = 0): under the reference rule the first
+    visit below the root is uniform over the root's edges, under the first-maximum rule it is always edge 0."""
+    from chinesecheckersagent_b200.engine import BatchedMCTS
+    roots = orc.start_states(4096)
+    out = BatchedMCTS(eng, num_itr=2, random_ties=True, tie_seed=9).search(dev(roots), evaluator=0)
+    v = out["visits"].cpu().numpy()
+    assert np.all(v.sum(1) == 1)
+    counts = v.sum(0)[np.nonzero(v.sum(0))[0]]
+    assert len(counts) == 10                                              # the start position has 10 legal moves
+    chi2 = float(((counts - 409.6) ** 2 / 409.6).sum())
+    assert chi2 < 33.7, (chi2, counts)                                    # 9 degrees of freedom, p = 1e-4

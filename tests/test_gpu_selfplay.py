@@ -159,3 +159,78 @@ def test_full_selfplay_with_real_net_at_size(eng):
     # records are positions after the six random opening plies: planes 0/1 hold six labelled checkers each
     bx = traj["board_x"].cpu().numpy()
     assert np.all((bx[..., 0] > 0).sum((1, 2)) == 6) and np.all((bx[..., 1] > 0).sum((1, 2)) == 6)
+
+
+def test_collect_consumes_its_records(eng):
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    model = ResidualCNN(engine=eng).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+    sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=128, num_itr=16, max_iters=110, seed=3)
+    sp.run(iters=110)
+    a = sp.collect()
+    assert a["v_y"].shape[0] == sp.stats()["records"] > 0
+    b = sp.collect()
+    assert b["v_y"].shape[0] == 0 and b["board_x"].shape == (0, 7, 7, 7)
+
+
+def test_ring_buffer_plays_past_max_iters(eng):
+    """ring=True: the record buffers hold 48 iterations but the loop runs 200; finished records are moved out in time, games
+    longer than max_iters // 2 iterations are discarded as overflow, and every kept record is delivered exactly once."""
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay, UniformEvaluator
+    model = ResidualCNN(engine=eng).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+    n = 192
+    sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=n, seed=21, num_itr=12, max_iters=160, ring=True)
+    st = sp.run(iters=400)
+    assert st["iterations"] == 400 and st["plies"] > 0
+    traj = sp.collect()
+    assert traj["v_y"].shape[0] == st["records"] > 0
+    assert sp.collect()["v_y"].shape[0] == 0
+    ended = st["p1_wins"] + st["p2_wins"] + st["discarded_repetition"] + st["discarded_no_progress"] + st["discarded_overflow"]
+    assert ended > n                                          # slots restarted
+    state = traj["state"].cpu().numpy().view(np.uint64)
+    full = np.zeros((8, state.shape[1]), dtype=np.uint64); full[:5] = state
+    assert np.array_equal(traj["board_x"].cpu().numpy(), orc.encode(full))
+    # a linear buffer of the same size refuses to go past its end
+    lin = BatchedSelfPlay(eng, UniformEvaluator(eng, n), n_slots=n, seed=21, num_itr=8, max_iters=6)
+    lin.run(iters=6)
+    with pytest.raises(RuntimeError):
+        lin.step()
+
+
+def test_play_games_starts_exactly_the_requested_games(eng):
+    """train.py:58-64: exactly num_self_play games are started and every one is played out (kept or discarded); nothing is
+    left in flight and no slot plays extra games."""
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    model = ResidualCNN(engine=eng).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+    for n, games in ((64, 150), (64, 40), (32, 32)):
+        sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=n, seed=5, num_itr=12, max_iters=400)
+        st = sp.play_games(games)
+        ended = st["p1_wins"] + st["p2_wins"] + st["discarded_repetition"] + st["discarded_no_progress"] + st["discarded_overflow"]
+        assert st["unfinished"] == 0 and st["games_started"] == games and ended == games, st
+        assert st["games"] == st["p1_wins"] + st["p2_wins"] > 0
+        assert int(sp.serial.sum().item()) == games - min(n, games)            # restarts = games beyond the first one per slot
+        assert sp.collect()["v_y"].shape[0] == st["records"]
+
+
+def test_two_net_selfplay_with_twin_nets_equals_single_net(eng):
+    """selfplay(model1, model2) (selfplay.py:11-29,58): model1 searches the even plies, model2 the odd ones.  With the same
+    weights loaded into two engines the split search must reproduce the single-net games bit for bit."""
+    from chinesecheckersagent_b200.engine import Engine
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    w = os.path.join(GOLDEN, "good_model_weights.npz")
+    m1 = ResidualCNN(engine=eng).load_weights(w)
+    eng2 = Engine(0)
+    m2 = ResidualCNN(engine=eng2).load_weights(w)
+    kw = dict(n_slots=96, num_itr=16, max_iters=40, seed=13, log_moves=True)
+    a = BatchedSelfPlay(eng, m1.evaluate_states, **kw)
+    a.run(iters=40)
+    b = BatchedSelfPlay(eng, m1.evaluate_states, opponent=m2, **kw)
+    b.run(iters=40)
+    assert torch.equal(a.move_log, b.move_log) and torch.equal(a.rec_visits, b.rec_visits) and torch.equal(a.rec_flag, b.rec_flag)
+    assert a.stats() == b.stats()
+    with pytest.raises(ValueError):
+        BatchedSelfPlay(eng, m1.evaluate_states, opponent=m1, **kw)
+    eng2.close()
