@@ -169,16 +169,37 @@ def read_tree(path):
     return out
 
 
+def _canonical_layer_names(names):
+    """Keras numbers auto-named layers per process, not per model: the second ResidualCNN built in a process owns conv2d_31..60,
+    batch_normalization_31..60 and dense_2.  `load_weights` matches layers by position, so such files load in the reference; here
+    each auto-named family is renumbered from 1 in ascending suffix order (= creation = topological order)."""
+    import re
+    fam = {}
+    for n in names:
+        m = re.fullmatch(r"(conv2d|batch_normalization|dense)_(\d+)", n)
+        if m:
+            fam.setdefault(m.group(1), []).append(int(m.group(2)))
+    ren = {}
+    for f, idx in fam.items():
+        for new, old in enumerate(sorted(set(idx)), start=1):
+            ren["%s_%d" % (f, old)] = "%s_%d" % (f, new)
+    return ren
+
+
 def read_weights(path):
-    """Keras save_weights layout '/<layer>/<layer>/<param>:0'  ->  {'<layer>/<param>': float32 array}."""
-    out = {}
+    """Keras save_weights layout '/<layer>/<layer>/<param>:0' (optionally under '/model_weights', which is where a full
+    `model.save` file keeps it)  ->  {'<layer>/<param>': float32 array} with canonical layer numbering."""
+    raw = {}
     for k, v in read_tree(path).items():
         parts = k.strip("/").split("/")
+        if parts and parts[0] == "model_weights":
+            parts = parts[1:]
         if len(parts) == 3 and parts[0] == parts[1] and parts[2].endswith(":0"):
-            out["%s/%s" % (parts[0], parts[2][:-2])] = np.asarray(v, dtype=np.float32)
-    if not out:
+            raw[(parts[0], parts[2][:-2])] = np.asarray(v, dtype=np.float32)
+    if not raw:
         raise H5Error("no Keras weights found in %s" % path)
-    return out
+    ren = _canonical_layer_names({layer for layer, _ in raw})
+    return {"%s/%s" % (ren.get(layer, layer), param): v for (layer, param), v in raw.items()}
 
 
 # =====================================================================================================

@@ -5,14 +5,15 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from conftest import ROOT
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
              "dtype", "data", "config", "e2e", "gpu_launches"}
 
 
-def test_committed_gpu_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01d_bench_1gpu.json")))
+def validate_gpu_line(d, steps=None):
     assert BASE_KEYS <= set(d) and {"roofline", "cpu_baseline", "clocks"} <= set(d)
     assert d["metric"] == "env_steps_per_sec" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True
     assert "workload" in d["config"] and d["config"]["games_per_gpu"] == 65536 and "model" not in d["config"]
@@ -24,8 +25,27 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference") and c["cores"] == 1
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
-    assert d["gpu_launches"] == d["steps"]
+    assert d["gpu_launches"] == d["steps"] and (steps is None or d["steps"] == steps)
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_committed_gpu_line_has_the_contract_keys():
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02a_bench_1gpu.json")).read().strip().splitlines()[-1])
+    validate_gpu_line(d)
+    assert d["clocks"]["samples"] >= 10                     # NVML sampler: tens of samples inside a 70 ms timed region
+    assert d["cpu_baseline"]["kind"] == "reference"         # the unmodified Python reference ran on the GPU box's host
+
+
+@pytest.mark.gpu
+def test_fresh_gpu_line_has_the_contract_keys():
+    """the line bench.py prints NOW, on this GPU (not a committed one)"""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "3", "--no-extra"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    validate_gpu_line(d, steps=4)
+    assert d["value"] > 1e9                                 # the north_star's bar, with a wide margin below the measured 4.9e9
+    assert d["config"] == __import__("bench").workload_config(65536)
 
 
 def run_reference(env_extra):

@@ -143,3 +143,17 @@ def test_uniform_ties_spread_the_first_visits(eng):
     assert len(counts) == 10                                              # the start position has 10 legal moves
     chi2 = float(((counts - 409.6) ** 2 / 409.6).sum())
     assert chi2 < 33.7, (chi2, counts)                                    # 9 degrees of freedom, p = 1e-4
+
+
+@pytest.mark.parametrize("pre_expand", [0, 1])
+def test_stub_search_matches_reference_on_256_roots(eng, pre_expand):
+    """cfg 4 against the REFERENCE itself (not the C oracle): 256 roots searched by the unmodified MCTS.py
+    (tests/golden/gen_golden_mcts256.py), both entry paths; per-edge N, root Q and pi bit for bit."""
+    from chinesecheckersagent_b200.engine import BatchedMCTS
+    g = dict(np.load(os.path.join(GOLDEN, "mcts_golden_256.npz")))
+    assert g["roots"].shape[1] >= 256
+    out = BatchedMCTS(eng).search(dev(g["roots"]), evaluator=0, pre_expand=bool(pre_expand))
+    assert np.array_equal(out["visits"].cpu().numpy().astype(np.uint32), g["visits%d" % pre_expand])
+    assert np.array_equal(out["q"].cpu().numpy(), g["q%d" % pre_expand])
+    assert np.array_equal(out["pi"].cpu().numpy(), g["pi%d" % pre_expand])
+    assert np.array_equal(out["n_nodes"].cpu().numpy(), g["nodes%d" % pre_expand])

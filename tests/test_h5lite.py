@@ -52,3 +52,26 @@ def test_written_file_mirrors_a_real_keras_file(tmp_path):
         assert list(real.attributes(er[name])["weight_names"]) == list(mine.attributes(em[name])["weight_names"]), name
     tr, tm = h5lite.read_tree(REF_H5), h5lite.read_tree(str(tmp_path / "w.h5"))
     assert set(tr) == set(tm) and all(np.array_equal(tr[k], tm[k]) and tr[k].dtype == tm[k].dtype for k in tr)
+
+
+def test_weights_of_a_second_model_in_the_process_load_by_position(tmp_path):
+    """Keras numbers auto-named layers per process: a weights file saved from the second ResidualCNN built in a process holds
+    conv2d_31..60 / batch_normalization_31..60 / dense_2, and a full-model save keeps everything under /model_weights.  Keras'
+    load_weights matches by position, so the reference loads both; read_weights must too."""
+    import re
+
+    from chinesecheckersagent_b200 import h5lite
+    w = {k: np.asarray(v, dtype=np.float32) for k, v in np.load(os.path.join(GOLDEN, "good_model_weights.npz")).items()}
+
+    def shifted(name):
+        m = re.fullmatch(r"(conv2d|batch_normalization)_(\d+)", name)
+        if m:
+            return "%s_%d" % (m.group(1), int(m.group(2)) + 30)
+        return "dense_2" if name == "dense_1" else name
+    tree = {}
+    for k, v in w.items():
+        layer, param = k.split("/")
+        tree["model_weights/%s/%s/%s:0" % (shifted(layer), shifted(layer), param)] = v
+    path = h5lite.write_tree(str(tmp_path / "second_model.h5"), tree)
+    back = h5lite.read_weights(path)
+    assert set(back) == set(w) and all(np.array_equal(back[k], w[k]) for k in w)

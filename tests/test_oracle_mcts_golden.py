@@ -33,3 +33,13 @@ def test_terminal_backups_are_exercised(gold):
     # late greedy roots reach wins inside the horizon: Q = +-1 appears at the root for the hash evaluator
     q = gold["q2"][40:]
     assert np.any(np.abs(q) == 1.0)
+
+
+@pytest.mark.parametrize("pre_expand", [0, 1])
+def test_oracle_matches_reference_on_256_roots(pre_expand):
+    """SURVEY §8d cfg 4: >= 256 reference-run roots (tests/golden/gen_golden_mcts256.py), incl. Board(randomised=True) ones."""
+    g = dict(np.load(os.path.join(GOLDEN, "mcts_golden_256.npz")))
+    assert g["roots"].shape[1] >= 256
+    v, pi, q, nodes = orc.mcts(g["roots"], 175, 3.5, 1.0, pre_expand, 0, nthreads=8)
+    assert np.array_equal(v, g["visits%d" % pre_expand]) and np.array_equal(q, g["q%d" % pre_expand])
+    assert np.array_equal(pi, g["pi%d" % pre_expand]) and np.array_equal(nodes, g["nodes%d" % pre_expand])
