@@ -246,6 +246,117 @@ CCX_HD u64 expand_cell_lut2(int i, u64 occ, const uint8_t *__restrict__ T2, cons
     return L;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Three-layout formulation (k_step_random_tri).  The expensive parts of expand_cell are the two multiplies that GATHER a
+// column's / diagonal's occupancy into 7 bits and the two that SCATTER the 7-bit answer back.  Both disappear when the
+// occupancy is also kept column-major and diagonal-major (a move flips two bits in each copy) with every line in a BYTE of
+// its own — gathering a line is then ONE byte-permute instruction (PRMT picks byte 0-7 of a register pair; bit 7 of every
+// byte is a guard bit, so the sign-replicating selector 0x8880 | byte zero-extends it) — and when the column / diagonal
+// tables hold 64-bit answers that are already spread over the board (scatter = one shift).
+//   T layout: bit 8*c + r            (column c = byte c, index along the line = row)
+//   D layout: the nine diagonals k = c - r that are long enough to jump on (|k| <= 4): k = -3..3 in bytes 1..7, the two
+//             3-cell diagonals share byte 0 (k = -4 in bits 0-2, k = +4 in bits 4-6); position along the diagonal = r if
+//             k >= 0 else c.  Cells of the four corner diagonals (|k| >= 5, no jump possible) map to the dump bit 3.
+// Table blob (CCX_JT3_BYTES): row answers u8 [o7][64 cells]; column answers u64 [o7][8 rows], bit 8*l = landing row l in
+// column 0; diagonal answers u64 [o7][29], bit 9*l = landing l on the main diagonal, column lp = 0-2: k = -4, 3-5: k = +4
+// (occupancy in bits 4-6), 6-9: 4 cells, 10-14: 5, 15-20: 6, 21-27: 7, 28: zeros (corner diagonals).
+#define CCX_JT3_ROW 0
+#define CCX_JT3_COL (128 * 64)
+#define CCX_JT3_DIA (CCX_JT3_COL + 128 * 8 * 8)
+#define CCX_JT3_NLP 29
+#define CCX_JT3_BYTES (CCX_JT3_DIA + 128 * CCX_JT3_NLP * 8)
+
+CCX_HD int tri_tbit(int cell) { return ((cell & 7) << 3) | (cell >> 3); }
+CCX_HD int tri_dbyte(int k) { return (k == -4 || k == 4) ? 0 : k + 4; }
+CCX_HD int tri_dbit(int cell)
+{
+    const int r = cell >> 3, c = cell & 7, k = c - r;
+    if (k < -4 || k > 4) return 3;
+    return 8 * tri_dbyte(k) + (k == 4 ? 4 : 0) + (k >= 0 ? r : c);
+}
+CCX_HD int tri_lp(int k, int pos)
+{
+    const int len = 7 - (k >= 0 ? k : -k);
+    if (len < 3) return 28;
+    if (len == 3) return (k > 0 ? 3 : 0) + pos;
+    return (len == 4 ? 6 : len == 5 ? 10 : len == 6 ? 15 : 21) + pos;
+}
+// per-cell constants, two words.  lo: diagonal byte selector (0x8880 | byte) | board shift of the diagonal << 16 | byte offset of its
+// answer column << 24;  hi: row byte selector (0x8880 | r) | column byte selector (0x8880 | c) << 16
+CCX_HD u64 tri_cell_info(int cell)
+{
+    const int r = cell >> 3, c = cell & 7, k = c - r;
+    const int sh = k >= 0 ? k : -8 * k;
+    const int sel = (k < -4 || k > 4) ? 4 : tri_dbyte(k);
+    const u32 lo = (0x8880u | (u32)sel) | ((u32)(sh & 0xFF) << 16) | ((u32)(tri_lp(k, k >= 0 ? r : c) * 8) << 24);
+    const u32 hi = (0x8880u | (u32)r) | ((0x8880u | (u32)c) << 16);
+    return (u64)lo | ((u64)hi << 32);
+}
+
+CCX_HD void build_jump_table3(uint8_t *T3, int first, int step)
+{
+    for (int e = first; e < 128 * 64; e += step) {                      // rows: [o7][cell]
+        int o7 = e / 64, cell = e % 64;
+        T3[CCX_JT3_ROW + e] = ((CCX_VALID >> cell) & 1) ? jump_line_entry(7, cell & 7, o7) : 0;
+    }
+    u64 *C = reinterpret_cast<u64 *>(T3 + CCX_JT3_COL);
+    for (int e = first; e < 128 * 8; e += step) {                       // columns: [o7][row]
+        int o7 = e / 8, pos = e % 8;
+        u32 m = pos < 7 ? jump_line_entry(7, pos, o7) : 0;
+        u64 out = 0;
+        for (int l = 0; l < 7; l++) if ((m >> l) & 1) out |= 1ULL << (8 * l);
+        C[e] = out;
+    }
+    u64 *D = reinterpret_cast<u64 *>(T3 + CCX_JT3_DIA);
+    for (int e = first; e < 128 * CCX_JT3_NLP; e += step) {             // diagonals: [o7][lp]
+        int o7 = e / CCX_JT3_NLP, lp = e % CCX_JT3_NLP;
+        int len, pos, occ = o7;
+        if (lp < 3) { len = 3; pos = lp; }
+        else if (lp < 6) { len = 3; pos = lp - 3; occ = o7 >> 4; }
+        else if (lp < 10) { len = 4; pos = lp - 6; }
+        else if (lp < 15) { len = 5; pos = lp - 10; }
+        else if (lp < 21) { len = 6; pos = lp - 15; }
+        else if (lp < 28) { len = 7; pos = lp - 21; }
+        else { len = 0; pos = 0; }
+        u32 m = len ? jump_line_entry(len, pos, occ) : 0;
+        u64 out = 0;
+        for (int l = 0; l < 7; l++) if ((m >> l) & 1) out |= 1ULL << (9 * l);
+        D[e] = out;
+    }
+}
+
+#ifdef __CUDA_ARCH__
+// PRMT in its default mode (selector nibble = source byte 0-7 | 8 to replicate that byte's sign bit).  __byte_perm() masks the
+// selector with 0x7777, which would fill bytes 1-3 with copies instead of zeros, hence the inline PTX.
+static __device__ __forceinline__ u32 ccx_byte_of(u32 lo, u32 hi, u32 sel)
+{
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+}
+#else
+static inline u32 ccx_byte_of(u32 lo, u32 hi, u32 sel)        // host model of PRMT for the selectors used here (0x8880 | byte)
+{
+    u64 v = (u64)lo | ((u64)hi << 32);
+    return (u32)((v >> (8 * (sel & 7))) & 0xFF);
+}
+#endif
+
+// all mirror-jump landings from cell i; occ / occT / occD = the occupancy without the mover in the three layouts
+CCX_HD u64 expand_cell_tri(int i, u64 occ, u64 occT, u64 occD, const uint8_t *__restrict__ T3, const u64 *__restrict__ CI3)
+{
+    const u64 ci = CI3[i];
+    const u32 clo = (u32)ci, chi = (u32)(ci >> 32);
+    const int r8 = i & 0x38;
+    const u32 row7 = ccx_byte_of((u32)occ, (u32)(occ >> 32), chi);
+    u64 L = (u64)T3[CCX_JT3_ROW + row7 * 64 + i] << r8;
+    const u32 col7 = ccx_byte_of((u32)occT, (u32)(occT >> 32), chi >> 16);
+    L |= *reinterpret_cast<const u64 *>(T3 + CCX_JT3_COL + col7 * 64 + r8) << (i & 7);
+    const u32 dia7 = ccx_byte_of((u32)occD, (u32)(occD >> 32), clo);
+    L |= *reinterpret_cast<const u64 *>(T3 + CCX_JT3_DIA + dia7 * (CCX_JT3_NLP * 8) + (clo >> 24)) << ((clo >> 16) & 0xFFu);
+    return L;
+}
+
 // Board.get_valid_moves (board.py:215-222) with the ray formulation.  Same single-loop structure as movegen():
 // the loop body expands ONE cell of the thread's current checker (origin first, then every newly reached
 // landing cell), and a thread that exhausts a checker moves on to its next one inside the same loop.

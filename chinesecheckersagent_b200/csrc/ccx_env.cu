@@ -8,7 +8,7 @@
 #include "ccx_internal.h"
 
 #ifndef CCX_STEP_DEFAULT_VARIANT
-#define CCX_STEP_DEFAULT_VARIANT 0
+#define CCX_STEP_DEFAULT_VARIANT 5      // k_step_random_tri; 0 = k_step_random_flat (r01), see ccx_step_random for the A/B list
 #endif
 #define ENV_THREADS 64      // 1024 blocks of 2 warps for 65,536 games: 6.9 blocks per SM (148 SMs), 98.8 % balanced
 #define ENC_THREADS 128
@@ -447,6 +447,132 @@ k_step_random_ilp(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
     if (w2) atomicAdd(&wins[1], (u64)w2);
 }
 
+// --------------------------------------------------------------------------------------------------
+// Three-layout step kernel: the flattened per-lane state machine of k_step_random_flat with the expansion of
+// expand_cell_tri (ccx_device.cuh): the occupancy is kept row-major, column-major and diagonal-major (a move flips two
+// bits in each copy), so that gathering a line is a shift + mask and the 64-bit table answers need one shift to land on
+// the board — 4 multiplies, ~10 shifts/masks fewer per expanded cell.  The 37 KB of tables make the block the unit of
+// residency: one block of 448 lanes (14 warps) per SM covers 65,536 games on 148 SMs in one balanced wave.
+// Bit-identical to the other step kernels.
+template <int TPB> struct TriSmem {
+    static constexpr int BYTES = 6 * TPB * 8;            // dynamic part: the parked destination masks; the tables are static (47 KB)
+};
+
+__device__ __forceinline__ void tri_build(u64 cells_a, u64 cells_b, const uint8_t *__restrict__ sTB, u64 &occT, u64 &occD)
+{
+    occT = 0; occD = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        int a = (int)((cells_a >> (8 * k)) & 0x3F), b = (int)((cells_b >> (8 * k)) & 0x3F);
+        occT |= (1ULL << sTB[a]) | (1ULL << sTB[b]);
+        occD |= (1ULL << sTB[64 + a]) | (1ULL << sTB[64 + b]);
+    }
+}
+
+template <bool TRACE, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB, 1)   // cluster size bound 1: the shared-window base stays in a uniform register across the loop
+k_step_random_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies, int ready_threshold,
+                  u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games, const uint8_t *__restrict__ jt3)
+{
+    extern __shared__ __align__(16) u64 sD[];                         // [6][TPB] jump closures of the current ply (dynamic)
+    // ONE static array for every table, so that all hot loads are [register + one uniform base + constant] (with separate arrays
+    // ptxas re-derives the extra bases from SR_CgaCtaId inside the loop)
+    __shared__ __align__(16) uint8_t sAll[CCX_JT3_BYTES + 64 * 8 + 64 * 8 + 128];
+    const uint8_t *sT = sAll;                                                              // answer tables
+    u64 *sNB = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES);                              // [64] on-board neighbours
+    u64 *sCI = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 512);                        // [64] tri_cell_info
+    uint8_t *sTB = sAll + CCX_JT3_BYTES + 1024;                                            // [64] T-layout bit, [64] D-layout bit
+    const int tid = threadIdx.x;
+    for (int q = tid; q < CCX_JT3_BYTES / 16; q += TPB) reinterpret_cast<uint4 *>(sAll)[q] = reinterpret_cast<const uint4 *>(jt3)[q];
+    for (int q = tid; q < 64; q += TPB) {
+        const bool on = (CCX_VALID >> q) & 1;
+        sNB[q] = on ? (neighbours(1ULL << q) & CCX_VALID) : 0ULL;
+        sCI[q] = on ? tri_cell_info(q) : 0ULL;
+        sTB[q] = on ? (uint8_t)tri_tbit(q) : (uint8_t)62;             // off-board cells map to spare bits that no line ever reads
+        sTB[64 + q] = on ? (uint8_t)tri_dbit(q) : (uint8_t)3;
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * TPB + tid;
+    const bool act = i < n;
+    unsigned alive = __ballot_sync(0xFFFFFFFFu, act);
+    Game g = load_game(st, n, act ? i : 0);
+    const u64 gid = (u64)(gid0 + i);
+    u32 w1 = 0, w2 = 0;
+    int t = 0, id = act ? 0 : 7;
+    u64 occ_all = g.occ_me | g.occ_op, occT_all, occD_all;
+    tri_build(g.cells_me, g.cells_op, sTB, occT_all, occD_all);
+    int cell = (int)(g.cells_me & 0x3F);
+    u64 o = 1ULL << cell, occ = occ_all & ~o, todo = act ? o : 0ULL, reach = 0;
+    u64 occT = occT_all & ~(1ULL << sTB[cell]), occD = occD_all & ~(1ULL << sTB[64 + cell]);
+    for (;;) {
+        if (todo) {
+            int c = 63 - __clzll((long long)todo);
+            todo ^= 1ULL << c;
+            u64 nw = expand_cell_tri(c, occ, occT, occD, sT, sCI) & ~(reach | o);
+            reach |= nw;
+            todo |= nw;
+        }
+        if (todo == 0 && id < 6) {                          // checker exhausted: park its jump closure, start the next one
+            sD[id * TPB + tid] = reach;                       // (the walk cells are added in the tail, where more lanes are active)
+            if (++id < 6) {
+                cell = (int)((g.cells_me >> (8 * id)) & 0x3F);
+                o = 1ULL << cell; occ = occ_all & ~o; todo = o; reach = 0;
+                occT = occT_all & ~(1ULL << sTB[cell]); occD = occD_all & ~(1ULL << sTB[64 + cell]);
+            }
+        }
+        const bool ready = id == 6;
+        const unsigned r = __ballot_sync(0xFFFFFFFFu, ready);
+        if (!(__popc(r) >= ready_threshold || r == alive)) continue;
+        if (ready) {
+            u64 dest[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++)                       // destinations = empty neighbours (board.py:149-155) | jump closure
+                dest[k] = sD[k * TPB + tid] | (sNB[(g.cells_me >> (8 * k)) & 0x3F] & ~occ_all);
+            u32 nonempty = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) nonempty += dest[k] != 0;
+            u64 *row = nullptr;
+            if (TRACE && i < trace_games) {
+                row = trace + ((int64_t)t * trace_games + i) * CCX_TRACE_WORDS;
+                bool p2 = (g.meta >> 48) & 1;
+                row[0] = p2 ? g.occ_op : g.occ_me; row[1] = p2 ? g.occ_me : g.occ_op;
+                row[2] = p2 ? g.cells_op : g.cells_me; row[3] = p2 ? g.cells_me : g.cells_op;
+                row[4] = g.meta & 0x00FFFFFFFFFFFFFFULL;
+#pragma unroll
+                for (int k = 0; k < 6; k++) row[5 + k] = dest[k];
+                row[11] = 0xFFULL | (0xFFULL << 8) | (0xFFULL << 24);
+            }
+            if (nonempty) {
+                Philox4 rnd = philox4x32_10(k0, k1, step0 + (u32)t, 0u, (u32)gid, (u32)(gid >> 32));
+                int from, to;
+                int pid = pick_random(g, dest, nonempty, rnd.x, rnd.y, from, to);
+                apply_move(g, pid, from, to);
+                occT_all ^= (1ULL << sTB[from]) | (1ULL << sTB[to]);
+                occD_all ^= (1ULL << sTB[64 + from]) | (1ULL << sTB[64 + to]);
+                int win = winner_of(g);
+                if (TRACE && row) row[11] = (u64)from | ((u64)to << 8) | ((u64)win << 16) | ((u64)pid << 24);
+                if (win) { w1 += win == 1; w2 += win == 2; reset_start(g); tri_build(g.cells_me, g.cells_op, sTB, occT_all, occD_all); }
+            }
+            if (++t == plies) id = 7;
+            else {
+                occ_all = g.occ_me | g.occ_op;
+                id = 0;
+                cell = (int)(g.cells_me & 0x3F);
+                o = 1ULL << cell; occ = occ_all & ~o; todo = o; reach = 0;
+                occT = occT_all & ~(1ULL << sTB[cell]); occD = occD_all & ~(1ULL << sTB[64 + cell]);
+            }
+        }
+        alive = __ballot_sync(0xFFFFFFFFu, id != 7);
+        if (alive == 0) break;
+    }
+    if (!act) return;
+    store_game(st, n, i, g);
+    if (w1) atomicAdd(&wins[0], (u64)w1);
+    if (w2) atomicAdd(&wins[1], (u64)w2);
+}
+
+__global__ void k_build_jump_table3(uint8_t *T3) { build_jump_table3(T3, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
+
 __global__ void k_build_jump_table2(uint8_t *T2) { build_jump_table2(T2, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 
 // --------------------------------------------------------------------------------------------------
@@ -616,7 +742,9 @@ int ccx_create(int device_ordinal, ccx_handle **out)
     if (cudaMalloc(&h->jump_table2, CCX_JT2_BYTES) != cudaSuccess) { cudaFree(h->jump_table); delete h; return CCX_ERR_NOMEM; }
     k_build_jump_table<<<7, 128>>>(h->jump_table);
     k_build_jump_table2<<<7, 128>>>(h->jump_table2);
-    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(h->jump_table); cudaFree(h->jump_table2); delete h; return CCX_ERR_CUDA; }
+    if (cudaMalloc(&h->jump_table3, CCX_JT3_BYTES) != cudaSuccess) { cudaFree(h->jump_table); cudaFree(h->jump_table2); delete h; return CCX_ERR_NOMEM; }
+    k_build_jump_table3<<<28, 128>>>(h->jump_table3);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(h->jump_table); cudaFree(h->jump_table2); cudaFree(h->jump_table3); delete h; return CCX_ERR_CUDA; }
     *out = h;
     return CCX_OK;
 }
@@ -633,6 +761,7 @@ int ccx_destroy(ccx_handle *h)
     for (auto *p : s) if (p->ptr) cudaFree(p->ptr);
     if (h->jump_table) cudaFree(h->jump_table);
     if (h->jump_table2) cudaFree(h->jump_table2);
+    if (h->jump_table3) cudaFree(h->jump_table3);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -700,8 +829,14 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
     if (n == 0 || plies == 0) return CCX_OK;
     unsigned grid = blocks_for(n, ENV_THREADS);
     static const bool nested = getenv("CCX_STEP_NESTED") != nullptr;     // A/B switch for profiling the older kernel
-    // kernel variant (diagnostics / A-B runs): 0 = one game per lane (k_step_random_flat), 1 = the same with the occupancy-major
-    // jump table, 2 / 3 = two games per lane (k_step_random_ilp) with either table.  All variants are bit-identical.
+    // kernel variant (CCX_STEP_VARIANT, for A/B runs; all bit-identical; B200, 65,536 games x 256 plies, profiles/r02b_env_variants.log):
+    //   5 (default) k_step_random_tri, three occupancy layouts + pre-scattered answers, 448-lane blocks   2.82 ms  5.96e9 steps/s
+    //   6 / 7       the same with 224- / 128-lane blocks                                                  2.97 / 3.07 ms
+    //   0           k_step_random_flat (round 1)                                                          3.39 ms  4.95e9
+    //   1           flat with the occupancy-major byte table (fewer bank conflicts)                        3.31 ms
+    //   4           flat, branch-free expansion                                                           3.34 ms
+    //   2 / 3       two games per lane for instruction-level parallelism (either table)                   4.11 / 4.16 ms — the dummy
+    //               expansions of a stream waiting for the tail vote cost more than the interleaving hides
     const char *ve = getenv("CCX_STEP_VARIANT");
     const int variant = ve ? atoi(ve) : CCX_STEP_DEFAULT_VARIANT;
     const char *te = getenv("CCX_STEP_THRESH");
@@ -724,6 +859,26 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
         if (tr) CCX_ILP_LAUNCH(true, 1, 2, 32, 24); else CCX_ILP_LAUNCH(false, 1, 2, 32, 24);
     } else if (variant == 4) {
         if (tr) CCX_ILP_LAUNCH(true, 0, 1, 64, 12); else CCX_ILP_LAUNCH(false, 0, 1, 64, 12);
+    } else if (variant >= 5 && variant <= 7) {
+#define CCX_TRI_LAUNCH(TR, TPB, MINB)                                                                                            \
+        do {                                                                                                                      \
+            static bool attr_set = false;                                                                                         \
+            if (!attr_set) {                                                                                                      \
+                CCX_CUDA(h, cudaFuncSetAttribute(k_step_random_tri<TR, TPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TriSmem<TPB>::BYTES)); \
+                attr_set = true;                                                                                                  \
+            }                                                                                                                     \
+            k_step_random_tri<TR, TPB, MINB><<<blocks_for(n, TPB), TPB, TriSmem<TPB>::BYTES, h->stream>>>(                         \
+                (u64 *)state, n, game_id0, s0, s1, step0, plies, te ? atoi(te) : 14, (u64 *)wins, tp, tg, h->jump_table3);           \
+        } while (0)
+        // one 448-lane block per SM covers 148 x 448 = 66,304 games in one balanced wave; larger batches run two blocks per SM
+        const bool one_wave = n <= (int64_t)h->num_sms * 448;
+        if (variant == 5) {
+            if (one_wave) { if (tr) CCX_TRI_LAUNCH(true, 448, 1); else CCX_TRI_LAUNCH(false, 448, 1); }
+            else { if (tr) CCX_TRI_LAUNCH(true, 448, 2); else CCX_TRI_LAUNCH(false, 448, 2); }
+        }
+        else if (variant == 6) { if (tr) CCX_TRI_LAUNCH(true, 224, 2); else CCX_TRI_LAUNCH(false, 224, 2); }
+        else { if (tr) CCX_TRI_LAUNCH(true, 128, 3); else CCX_TRI_LAUNCH(false, 128, 3); }
+#undef CCX_TRI_LAUNCH
     } else {
         if (tr) k_step_random_flat<true><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, tp, tg, h->jump_table);
         else k_step_random_flat<false><<<grid, ENV_THREADS, 0, h->stream>>>((u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, nullptr, 0, h->jump_table);

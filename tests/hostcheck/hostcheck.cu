@@ -47,6 +47,36 @@ void hc_movegen_rays(const u64 *st, int64_t n, u64 *masks)
     }
 }
 
+// movegen with the three-layout expansion (expand_cell_tri / the layout-2 table), the way k_step_random_tri maintains the copies:
+// occT / occD of the whole board built from the checker cells, the mover lifted in each layout
+void hc_movegen_tri(const u64 *st, int64_t n, u64 *masks, int use_lut2)
+{
+    static uint8_t T3[CCX_JT3_BYTES] __attribute__((aligned(16)));
+    static uint8_t T2[CCX_JT2_BYTES];
+    static u64 CI3[64]; static u32 CI2[64];
+    build_jump_table3(T3, 0, 1);
+    build_jump_table2(T2, 0, 1);
+    for (int c = 0; c < 64; c++) { CI3[c] = ((CCX_VALID >> c) & 1) ? tri_cell_info(c) : 0; CI2[c] = cell_diag_info2(c); }
+    for (int64_t i = 0; i < n; i++) {
+        Game g = load_game_h(st, n, i);
+        u64 occ_all = g.occ_me | g.occ_op, occT_all = 0, occD_all = 0;
+        for (int c = 0; c < 64; c++) if ((occ_all >> c) & 1) { occT_all |= 1ULL << tri_tbit(c); occD_all |= 1ULL << tri_dbit(c); }
+        for (int k = 0; k < 6; k++) {
+            int cell = (int)((g.cells_me >> (8 * k)) & 0xFF);
+            u64 o = 1ULL << cell, occ = occ_all & ~o;
+            u64 occT = occT_all & ~(1ULL << tri_tbit(cell)), occD = occD_all & ~(1ULL << tri_dbit(cell));
+            u64 todo = o, reach = 0;
+            while (todo) {
+                int c = 63 - __builtin_clzll(todo);
+                todo ^= 1ULL << c;
+                u64 nw = (use_lut2 ? expand_cell_lut2(c, occ, T2, CI2) : expand_cell_tri(c, occ, occT, occD, T3, CI3)) & ~(reach | o);
+                reach |= nw; todo |= nw;
+            }
+            masks[k * n + i] = (neighbours(o) & ~occ & CCX_VALID) | reach;
+        }
+    }
+}
+
 void hc_greedy(const u64 *st, int64_t n, u64 *masks)
 {
     for (int64_t i = 0; i < n; i++) {

@@ -20,6 +20,7 @@ def hc():
     L.hc_movegen.argtypes = [vp, i64, vp]
     L.hc_greedy.argtypes = [vp, i64, vp]
     L.hc_movegen_rays.argtypes = [vp, i64, vp]
+    L.hc_movegen_tri.argtypes = [vp, i64, vp, i32]
     L.hc_apply.argtypes = [vp, i64, vp, vp, vp]
     L.hc_step_random.argtypes = [vp, i64, i64, u64, u32, i32, vp, vp, i64]
     L.hc_play_greedy.argtypes = [vp, i64, i64, u64, i32]
@@ -124,3 +125,18 @@ def test_play_greedy_vs_reference_games(hc, greedy_golden):
     st = orc.start_states(n)
     hc.hc_play_greedy(P(st), n, 0, int(g["seed"]), 100000)
     assert np.array_equal(st[:7], g["final"][:7])
+
+
+@pytest.mark.parametrize("use_lut2", [0, 1])
+def test_three_layout_and_occupancy_major_expansions_vs_oracle(hc, env_golden, use_lut2):
+    """expand_cell_tri (row / column-major / diagonal-major occupancy copies, pre-scattered 64-bit answers) and expand_cell_lut2
+    (occupancy-major byte table) give the reference's move lists on the fixture positions and the oracle's on 20,000 random
+    boards and 20,000 positions reached by random play."""
+    st = np.ascontiguousarray(env_golden["state"])
+    masks = np.zeros((6, st.shape[1]), dtype=np.uint64)
+    hc.hc_movegen_tri(P(st), st.shape[1], P(masks), use_lut2)
+    assert np.array_equal(masks, canonical_masks(env_golden["ref_moves"], env_golden["ref_nmoves"]))
+    for st in (orc.random_states(20000, seed=11), orc.step_random(orc.start_states(20000), 5, 0, 37, nthreads=8)[0]):
+        masks = np.zeros((6, st.shape[1]), dtype=np.uint64)
+        hc.hc_movegen_tri(P(st), st.shape[1], P(masks), use_lut2)
+        assert np.array_equal(masks, orc.movegen(st))
