@@ -30,6 +30,7 @@ SEED = 0x5EED2026
 METRIC = "env_steps_per_sec"
 UNIT = "env steps/s"
 N_SMS, SCHEDULERS_PER_SM = 148, 4
+STEP_KERNEL = "k_step_random_tri<false, 448, 1>"     # the default variant of ccx_step_random (csrc/ccx_env.cu)
 
 
 def workload_config(n):
@@ -351,7 +352,7 @@ def main():
             "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": workload_config(n),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": traffic, "peak_source": peaks["source"], "kernel": "k_step_random_flat<false>",
+                         "traffic": traffic, "peak_source": peaks["source"], "kernel": STEP_KERNEL,
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * PLIES_PER_STEP, "launch_ms": launch_ms,
                          "traffic_source": prof.get("source")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -366,7 +367,7 @@ def main():
             ach_i = winst / (launch_ms * 1e-3)
             peak_i = N_SMS * SCHEDULERS_PER_SM * f_mhz * 1e6
             line["roofline_issue"] = {"bound": "issue", "achieved": ach_i, "peak": peak_i, "unit": "warp-instr/s", "frac": ach_i / peak_i,
-                                      "warp_insts_per_launch": winst, "sm_mhz": f_mhz, "kernel": "k_step_random_flat<false>",
+                                      "warp_insts_per_launch": winst, "sm_mhz": f_mhz, "kernel": STEP_KERNEL,
                                       "source": "smsp__inst_executed.sum of the ncu capture named in roofline.traffic_source; launch time measured live"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()

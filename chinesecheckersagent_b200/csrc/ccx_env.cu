@@ -458,14 +458,15 @@ template <int TPB> struct TriSmem {
     static constexpr int BYTES = 6 * TPB * 8;            // dynamic part: the parked destination masks; the tables are static (47 KB)
 };
 
-__device__ __forceinline__ void tri_build(u64 cells_a, u64 cells_b, const uint8_t *__restrict__ sTB, u64 &occT, u64 &occD)
+// occupancy in the T and D layouts from the twelve checker cells; sOT / sOD = one-bit masks of every cell in those layouts
+__device__ __forceinline__ void tri_build(u64 cells_a, u64 cells_b, const u64 *__restrict__ sOT, const u64 *__restrict__ sOD, u64 &occT, u64 &occD)
 {
     occT = 0; occD = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         int a = (int)((cells_a >> (8 * k)) & 0x3F), b = (int)((cells_b >> (8 * k)) & 0x3F);
-        occT |= (1ULL << sTB[a]) | (1ULL << sTB[b]);
-        occD |= (1ULL << sTB[64 + a]) | (1ULL << sTB[64 + b]);
+        occT |= sOT[a] | sOT[b];
+        occD |= sOD[a] | sOD[b];
     }
 }
 
@@ -477,19 +478,23 @@ k_step_random_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
     extern __shared__ __align__(16) u64 sD[];                         // [6][TPB] jump closures of the current ply (dynamic)
     // ONE static array for every table, so that all hot loads are [register + one uniform base + constant] (with separate arrays
     // ptxas re-derives the extra bases from SR_CgaCtaId inside the loop)
-    __shared__ __align__(16) uint8_t sAll[CCX_JT3_BYTES + 64 * 8 + 64 * 8 + 128];
+    __shared__ __align__(16) uint8_t sAll[CCX_JT3_BYTES + 5 * 64 * 8];
     const uint8_t *sT = sAll;                                                              // answer tables
     u64 *sNB = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES);                              // [64] on-board neighbours
     u64 *sCI = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 512);                        // [64] tri_cell_info
-    uint8_t *sTB = sAll + CCX_JT3_BYTES + 1024;                                            // [64] T-layout bit, [64] D-layout bit
+    // one-bit masks of every cell in the three layouts: a 64-bit `1 << x` costs three instructions, a table load one
+    u64 *sO = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 1024);                        // [64] 1 << cell
+    u64 *sOT = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 1536);                       // [64] 1 << tri_tbit(cell)
+    u64 *sOD = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 2048);                       // [64] 1 << tri_dbit(cell)
     const int tid = threadIdx.x;
     for (int q = tid; q < CCX_JT3_BYTES / 16; q += TPB) reinterpret_cast<uint4 *>(sAll)[q] = reinterpret_cast<const uint4 *>(jt3)[q];
     for (int q = tid; q < 64; q += TPB) {
         const bool on = (CCX_VALID >> q) & 1;
         sNB[q] = on ? (neighbours(1ULL << q) & CCX_VALID) : 0ULL;
         sCI[q] = on ? tri_cell_info(q) : 0ULL;
-        sTB[q] = on ? (uint8_t)tri_tbit(q) : (uint8_t)62;             // off-board cells map to spare bits that no line ever reads
-        sTB[64 + q] = on ? (uint8_t)tri_dbit(q) : (uint8_t)3;
+        sO[q] = 1ULL << q;
+        sOT[q] = on ? 1ULL << tri_tbit(q) : 0ULL;
+        sOD[q] = on ? 1ULL << tri_dbit(q) : 0ULL;
     }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * TPB + tid;
@@ -500,14 +505,14 @@ k_step_random_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
     u32 w1 = 0, w2 = 0;
     int t = 0, id = act ? 0 : 7;
     u64 occ_all = g.occ_me | g.occ_op, occT_all, occD_all;
-    tri_build(g.cells_me, g.cells_op, sTB, occT_all, occD_all);
+    tri_build(g.cells_me, g.cells_op, sOT, sOD, occT_all, occD_all);
     int cell = (int)(g.cells_me & 0x3F);
-    u64 o = 1ULL << cell, occ = occ_all & ~o, todo = act ? o : 0ULL, reach = 0;
-    u64 occT = occT_all & ~(1ULL << sTB[cell]), occD = occD_all & ~(1ULL << sTB[64 + cell]);
+    u64 o = sO[cell], occ = occ_all & ~o, todo = act ? o : 0ULL, reach = 0;
+    u64 occT = occT_all & ~sOT[cell], occD = occD_all & ~sOD[cell];
     for (;;) {
         if (todo) {
             int c = 63 - __clzll((long long)todo);
-            todo ^= 1ULL << c;
+            todo ^= sO[c];
             u64 nw = expand_cell_tri(c, occ, occT, occD, sT, sCI) & ~(reach | o);
             reach |= nw;
             todo |= nw;
@@ -516,8 +521,8 @@ k_step_random_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
             sD[id * TPB + tid] = reach;                       // (the walk cells are added in the tail, where more lanes are active)
             if (++id < 6) {
                 cell = (int)((g.cells_me >> (8 * id)) & 0x3F);
-                o = 1ULL << cell; occ = occ_all & ~o; todo = o; reach = 0;
-                occT = occT_all & ~(1ULL << sTB[cell]); occD = occD_all & ~(1ULL << sTB[64 + cell]);
+                o = sO[cell]; occ = occ_all & ~o; todo = o; reach = 0;
+                occT = occT_all & ~sOT[cell]; occD = occD_all & ~sOD[cell];
             }
         }
         const bool ready = id == 6;
@@ -547,19 +552,19 @@ k_step_random_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
                 int from, to;
                 int pid = pick_random(g, dest, nonempty, rnd.x, rnd.y, from, to);
                 apply_move(g, pid, from, to);
-                occT_all ^= (1ULL << sTB[from]) | (1ULL << sTB[to]);
-                occD_all ^= (1ULL << sTB[64 + from]) | (1ULL << sTB[64 + to]);
+                occT_all ^= sOT[from] | sOT[to];
+                occD_all ^= sOD[from] | sOD[to];
                 int win = winner_of(g);
                 if (TRACE && row) row[11] = (u64)from | ((u64)to << 8) | ((u64)win << 16) | ((u64)pid << 24);
-                if (win) { w1 += win == 1; w2 += win == 2; reset_start(g); tri_build(g.cells_me, g.cells_op, sTB, occT_all, occD_all); }
+                if (win) { w1 += win == 1; w2 += win == 2; reset_start(g); tri_build(g.cells_me, g.cells_op, sOT, sOD, occT_all, occD_all); }
             }
             if (++t == plies) id = 7;
             else {
                 occ_all = g.occ_me | g.occ_op;
                 id = 0;
                 cell = (int)(g.cells_me & 0x3F);
-                o = 1ULL << cell; occ = occ_all & ~o; todo = o; reach = 0;
-                occT = occT_all & ~(1ULL << sTB[cell]); occD = occD_all & ~(1ULL << sTB[64 + cell]);
+                o = sO[cell]; occ = occ_all & ~o; todo = o; reach = 0;
+                occT = occT_all & ~sOT[cell]; occD = occD_all & ~sOD[cell];
             }
         }
         alive = __ballot_sync(0xFFFFFFFFu, id != 7);

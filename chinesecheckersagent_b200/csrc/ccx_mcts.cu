@@ -559,7 +559,7 @@ __device__ __forceinline__ void do_select_encode(const TreeView &tv, int lane, d
 }
 
 template <bool TIES>
-__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK, 14)
 k_mcts_select_encode(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, uint8_t *__restrict__ planes)
 {
     __shared__ __align__(16) uint8_t sP[MCTS_WARPS_PER_BLOCK][352];
@@ -619,8 +619,11 @@ k_mcts_softmax_expand_backup(ccx_trees trees, int64_t tree0, int64_t n, const fl
 
 // one launch per round in steady state: finish the previous round's leaf (softmax + expand + backup), then select and encode
 // the next one — the same warp owns the tree in both halves, so the halves need no grid-wide ordering between them
+// launch bound: 14 blocks per SM (<= 72 registers) keeps all 2,048 blocks of a 4,096-tree round resident in ONE wave (148 x 14 =
+// 2,072); at 80 registers (12 blocks per SM) the last 272 blocks start only when others finish: 1.15 waves, slowest SM 88.6 K cycles
+// against 59.7 K on average (profiles/r02b_kernels_ncu.md)
 template <bool TIES>
-__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK, 14)
 k_mcts_round(ccx_trees trees, int64_t tree0, int64_t n, double cpuct, const float *__restrict__ logits, const float *__restrict__ value,
              const double *__restrict__ noise, int noise_stride, int noise_normalize, uint8_t *__restrict__ planes,
              const uint8_t *__restrict__ jt)

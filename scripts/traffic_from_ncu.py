@@ -16,14 +16,14 @@ for rep in ("prof_step_random", "prof_mcts_search", "prof_net_acc", "prof_tree",
     hdr = rows[0]
     for r in rows[2:]:
         d = dict(zip(hdr, r))
-        name = re.sub(r"[<(].*", "", d["Kernel Name"])
+        name = re.sub(r"[<(].*", "", d["Kernel Name"]).replace("void ", "").strip()
         num = lambda k: float(d[k].replace(",", "")) if d.get(k) else 0.0
         unit = dict(zip(hdr, rows[1]))
         scale = lambda k: {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(unit.get(k, "byte"), 1.0)
         dram = num("dram__bytes_read.sum") * scale("dram__bytes_read.sum") + num("dram__bytes_write.sum") * scale("dram__bytes_write.sum")
         out[name] = int(dram)
         out[name + "_warp_insts"] = int(num("smsp__inst_executed.sum"))
-        out[name + "_launch_us"] = num("gpu__time_duration.sum") / (1e3 if unit.get("gpu__time_duration.sum") == "ns" else 1.0)
+        out[name + "_launch_us"] = num("gpu__time_duration.sum") * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit.get("gpu__time_duration.sum"), 1.0)
     used.append(rep + ".ncu-rep")
 # bench.py looks the step kernel up under this key whatever variant is the default
 for k in list(out):
