@@ -203,6 +203,16 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
         for _ in range(200):
             b.get_valid_moves(1)
         out["dropin_board_get_valid_moves_us"] = (time.perf_counter() - t0) / 200 * 1e6
+        # selfplay.selfplay(model) (selfplay.py:11-80), one game at a time through the mirror: 6 random plies, then a 175-simulation search per ply
+        from .selfplay import selfplay as selfplay_one
+        model.set_kernel("tc_acc")
+        import numpy as _np
+        _np.random.seed(7)
+        t0 = time.perf_counter()
+        hist, reward = selfplay_one(model)
+        dt = time.perf_counter() - t0
+        out["dropin_selfplay_game"] = {"seconds": dt, "searched_plies": len(hist) if hist is not None else None, "kept": hist is not None,
+                                       "api": "selfplay.selfplay(model): one game, accurate net mode"}
         # net forward alone on a big batch
         planes = torch.randint(0, 7, (65536, 7, 7, 7), dtype=torch.uint8, device=eng.device)
         for kern in ("tc", "tc_acc", "simt"):
