@@ -71,7 +71,7 @@ def _load(model_or_path, engine=None):
     if isinstance(model_or_path, ResidualCNN) or model_or_path == GREEDY:
         return model_or_path
     from .engine import Engine
-    return ResidualCNN(engine=engine or Engine(0)).load_weights(model_or_path)
+    return ResidualCNN(engine=engine or Engine()).load_weights(model_or_path)
 
 
 def agent_match(model1_path, model2_path, num_games, verbose=False, tree_tau=DET_TREE_TAU, enforce_move_limit=False, seed=DEFAULT_SEED):

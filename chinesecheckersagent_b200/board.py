@@ -15,14 +15,15 @@ from . import engine as _engine
 from .config import (BOARD_HEIGHT, BOARD_HIST_MOVES, BOARD_WIDTH, NUM_CHECKERS, PLAYER_ONE, PLAYER_TWO, STATE_WORDS,
                      TOTAL_HIST_MOVES)
 
-_default_engine = None
+_default_engines = {}
 
 
 def default_engine():
-    global _default_engine
-    if _default_engine is None:
-        _default_engine = _engine.Engine(0)
-    return _default_engine
+    """the engine of torch's CURRENT CUDA device (one per device: rank r of a multi-GPU job gets device r's)"""
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if dev not in _default_engines:
+        _default_engines[dev] = _engine.Engine(dev)
+    return _default_engines[dev]
 
 
 class _HostCalls:

@@ -17,10 +17,13 @@ _TORCH_DTYPE = {DTYPE_U8: torch.uint8, DTYPE_BF16: torch.bfloat16, DTYPE_F32: to
 class Engine:
     """One ccx handle bound to one CUDA device; kernels run on torch's current stream."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=None):
+        """device: CUDA ordinal / torch.device; None = torch's current CUDA device (rank r of a multi-GPU job: device r)"""
         if not torch.cuda.is_available():
             raise _lib.CcxError("no CUDA device: the ccx engine has no CPU path")
         self.L = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         h = ctypes.c_void_p()
         _lib.check(self.L, None, self.L.ccx_create(self.device.index, ctypes.byref(h)))
@@ -65,7 +68,7 @@ def _p(t):
 class BatchedEnv:
     """n games in SoA form on the GPU.  Mirrors Board's methods for a batch (board.py:9-288)."""
 
-    def __init__(self, n, engine=None, device=0, seed=DEFAULT_SEED, game_id0=0, randomised=False, state=None):
+    def __init__(self, n, engine=None, device=None, seed=DEFAULT_SEED, game_id0=0, randomised=False, state=None):
         self.eng = engine or Engine(device)
         self.n = int(n)
         self.seed = int(seed)
@@ -142,7 +145,7 @@ class BatchedEnv:
 class HostEnv:
     """The reference-facing path with HOST buffers: numpy in, numpy out, H2D/D2H inside each call."""
 
-    def __init__(self, engine=None, device=0):
+    def __init__(self, engine=None, device=None):
         self.eng = engine or Engine(device)
 
     @staticmethod

@@ -164,7 +164,7 @@ class ResidualCNN(Model):
     def __init__(self, input_dim=INPUT_DIM, filters=NUM_FILTERS, engine=None):
         Model.__init__(self, input_dim, filters)
         from .engine import Engine
-        self.eng = engine or Engine(0)
+        self.eng = engine or Engine()
         self.loaded = False
         self.fused_mcts = True      # engine.BatchedMCTS.search_net / BatchedSelfPlay may run the rounds inside libccx (ccx_mcts_run_net)
         # default = the accurate tensor-core mode: meets the <= 1e-3 output bar against the restated Keras graph (max |dp| 2e-5)

@@ -303,7 +303,7 @@ def selfplay(model1, model2=None, randomised=False, num_itr=MCTS_SIMULATIONS):
     from .MCTS import MCTS, Node
     model2 = model2 or model1
     player_progresses, player_turn, num_useless_moves, play_history, tree_tau = [0, 0], 0, 0, [], TREE_TAU
-    root = Node(Board(randomised=randomised), PLAYER_ONE)
+    root = Node(Board(randomised=randomised, engine=getattr(model1, "eng", None)), PLAYER_ONE)     # the model's device, not cuda:0
     use_model1 = True
     while True:
         model = model1 if use_model1 else model2

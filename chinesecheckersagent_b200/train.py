@@ -218,8 +218,8 @@ def evolve(cur_model_path, other_opponent_for_selfplay=None, iteration_count=0, 
     from .arena import evaluate
     from .engine import Engine
     from .model import ResidualCNN, read_weight_file
-    engine = Engine(0)
-    opp_engine = Engine(0) if other_opponent_for_selfplay is not None else None
+    engine = Engine()
+    opp_engine = Engine() if other_opponent_for_selfplay is not None else None
     if cur_model_path is None:                                     # un-trained model: materialise it so that every stage can load it
         os.makedirs(weights_dir, exist_ok=True)
         torch.manual_seed(int(seed))
