@@ -65,7 +65,7 @@ class GreedyDataGenerator:
     def __init__(self, randomised=False, random_start=False, engine=None, batch=256, seed=DEFAULT_SEED):
         from .engine import Engine
         self.randomised, self.random_start = randomised, random_start
-        self.gen = BatchedGreedyGenerator(engine or Engine(0), seed=seed)
+        self.gen = BatchedGreedyGenerator(engine or Engine(), seed=seed)
         self.batch, self.queue = int(batch), []
 
     def generate_play(self):
