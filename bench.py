@@ -7,7 +7,7 @@ A "step" is one pass of the fused env kernel over one batch: 65,536 games/GPU x 
 (BASELINE configs[1], SURVEY.md §8d cfg 2).  See DESIGN.md §5 for every field of the JSON line.
 
 `--impl reference` times the UNMODIFIED Python reference (its own Board.get_valid_moves / Board.place loop, staged
-under oracle/_ref/reference by oracle/refrun.py) on every host core of the box; when no staged copy exists it falls
+as oracle/_ref/reference.zip by oracle/refrun.py) on every host core of the box; when no staged copy exists it falls
 back to the C port of the same loop (oracle/ccx_oracle.c) and says so in `cpu_baseline.kind`.
 """
 import argparse
@@ -136,7 +136,7 @@ def cpu_baseline(seconds_target=10.0):
                    sample="%d games x %d plies of the unmodified reference's Board loop (get_valid_moves + selfplay.py:93-98 choice + place), "
                           "1 process, %.1f s" % (games, PLIES_PER_STEP, dt))
     else:
-        out.update(value=port, kind="port", sample="oracle port, 1 thread (no staged reference under oracle/_ref/reference)")
+        out.update(value=port, kind="port", sample="oracle port, 1 thread (no staged reference at oracle/_ref/reference.zip)")
     return out
 
 
@@ -211,7 +211,7 @@ def run_reference(args, rank):
         dt = time.perf_counter() - t
         value = games * PLIES_PER_STEP * args.steps / dt
         sample = ("%d games x %d plies per step, oracle port (C restatement of board.py) on %d threads; no staged reference under "
-                  "oracle/_ref/reference" % (games, PLIES_PER_STEP, cores))
+                  "oracle/_ref/reference.zip" % (games, PLIES_PER_STEP, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",

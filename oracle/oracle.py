@@ -20,7 +20,7 @@ _u64p = ctypes.POINTER(ctypes.c_uint64)
 
 def build(force=False):
     """Compile the oracle with gcc (seconds) and, where the read-only reference checkout exists (build container), stage its
-    .py files under oracle/_ref/reference so that they travel to the GPU box (refrun.stage; git-ignored)."""
+    .py files as oracle/_ref/reference.zip so that they travel to the GPU box (refrun.stage; git-ignored)."""
     try:
         import refrun
         refrun.stage()

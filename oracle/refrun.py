@@ -4,11 +4,12 @@ INFRASTRUCTURE, NOT PRODUCT.
 Importers: bench.py's `cpu_baseline` / `--impl reference` legs and tests/.  The product package never imports this.
 
 The reference is a flat collection of .py files with no native code, so there is nothing to compile into
-`oracle/_ref/`: the "recipe" is `stage()` below, which copies the .py files from the read-only checkout
-(`/root/reference`, build container only) to `oracle/_ref/reference/`.  That directory is git-ignored (the sources
-never enter this repository's history) but travels to the GPU box with the gpurun snapshot like a built `.so`, so
-the reference's own `Board` / `Game` / `MCTS` can be timed on the box's host cores in the same run as the GPU
-numbers.  Every function here resolves the reference through `refshim` (stubs for the missing
+`oracle/_ref/`: the "recipe" is `stage()` below, which packs the .py files of the read-only checkout
+(`/root/reference`, build container only) into ONE archive, `oracle/_ref/reference.zip`, which Python imports from
+directly (zipimport).  `oracle/_ref/` is git-ignored (the sources never enter this repository, neither its history
+nor its tree of source files) but travels to the GPU box with the gpurun snapshot like a built `.so`, so the
+reference's own `Board` / `Game` / `MCTS` can be timed on the box's host cores in the same run as the GPU numbers
+(BASELINE.md §3).  Every function here resolves the reference through `refshim` (stubs for the missing
 h5py / keras / tensorflow imports; the Keras net is never instantiated).
 
 Workloads:
@@ -22,37 +23,53 @@ import glob
 import io
 import os
 import random
-import shutil
 import sys
 import time
+import zipfile
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-STAGED = os.path.join(_HERE, "_ref", "reference")
+STAGED = os.path.join(_HERE, "_ref", "reference.zip")
 SOURCE = "/root/reference"
 
 
 def stage(force=False):
-    """Copy the reference's .py files to oracle/_ref/reference (only where the checkout exists).  Returns the staged
-    directory, or None when neither the checkout nor an earlier staging is available."""
+    """Pack the reference's .py files into oracle/_ref/reference.zip (only where the checkout exists).  Returns the archive
+    path, or None when neither the checkout nor an earlier staging is available."""
     if os.path.isdir(SOURCE):
         srcs = sorted(glob.glob(os.path.join(SOURCE, "*.py")))
-        os.makedirs(STAGED, exist_ok=True)
-        for s in srcs:
-            d = os.path.join(STAGED, os.path.basename(s))
-            if force or not os.path.exists(d) or os.path.getmtime(d) < os.path.getmtime(s):
-                shutil.copyfile(s, d)
-        with open(os.path.join(STAGED, "STAGED_FROM"), "w") as f:
-            f.write("%s (%d .py files, copied by oracle/refrun.py:stage; git-ignored, travels with gpurun)\n" % (SOURCE, len(srcs)))
-    return STAGED if os.path.exists(os.path.join(STAGED, "board.py")) else None
+        newest = max(os.path.getmtime(s) for s in srcs)
+        if force or not os.path.exists(STAGED) or os.path.getmtime(STAGED) < newest:
+            os.makedirs(os.path.dirname(STAGED), exist_ok=True)
+            tmp = STAGED + ".tmp"
+            with zipfile.ZipFile(tmp, "w", zipfile.ZIP_DEFLATED) as z:
+                for s in srcs:
+                    z.write(s, os.path.basename(s))
+                z.writestr("STAGED_FROM", "%s (%d .py files, packed by oracle/refrun.py:stage; git-ignored, travels with gpurun)\n"
+                           % (SOURCE, len(srcs)))
+            os.replace(tmp, STAGED)
+    return STAGED if os.path.exists(STAGED) else None
 
 
 def reference_dir():
-    """The staged copy when present (it is what travels), else the read-only checkout, else None."""
-    if os.path.exists(os.path.join(STAGED, "board.py")):
+    """The staged archive when present (it is what travels), else the read-only checkout, else None.  Either one works as a
+    sys.path entry."""
+    if os.path.exists(STAGED):
         return STAGED
     if os.path.exists(os.path.join(SOURCE, "board.py")):
         return SOURCE
     return None
+
+
+def reference_source(name):
+    """text of one reference file (from the archive or the checkout)"""
+    d = reference_dir()
+    if d is None:
+        raise RuntimeError("no reference available")
+    if d.endswith(".zip"):
+        with zipfile.ZipFile(d) as z:
+            return z.read(name).decode()
+    with open(os.path.join(d, name)) as f:
+        return f.read()
 
 
 def available():
@@ -62,7 +79,7 @@ def available():
 def _load():
     d = reference_dir()
     if d is None:
-        raise RuntimeError("the reference is neither staged under oracle/_ref/reference nor present at /root/reference")
+        raise RuntimeError("the reference is neither staged as oracle/_ref/reference.zip nor present at /root/reference")
     os.environ["CCX_REFERENCE_DIR"] = d
     if _HERE not in sys.path:
         sys.path.insert(0, _HERE)
@@ -184,12 +201,12 @@ class Pool:
 def greedy_vs_greedy_script():
     """greedy_vs_greedy.py as shipped (50 games, `python greedy_vs_greedy.py`), run through the shim in this process.
     Returns (seconds, captured tail of its output)."""
-    import runpy
     _load()
+    code = compile(reference_source("greedy_vs_greedy.py"), "greedy_vs_greedy.py", "exec")
     buf = io.StringIO()
     t0 = time.perf_counter()
     with contextlib.redirect_stdout(buf):
-        runpy.run_path(os.path.join(reference_dir(), "greedy_vs_greedy.py"), run_name="__main__")
+        exec(code, {"__name__": "__main__"})
     dt = time.perf_counter() - t0
     lines = [l for l in buf.getvalue().splitlines() if l.strip()]
     return dt, lines[-3:]

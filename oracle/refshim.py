@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  This module is used by ``tests/golden/gen_golden.py`` to run the real
 reference (``/root/reference``) and write golden fixtures; and by ``oracle/refrun.py``
-(bench.py's CPU-baseline legs, the drop-in tests) to run the copy staged under ``oracle/_ref/reference``
+(bench.py's CPU-baseline legs, the drop-in tests) to run the copy staged as ``oracle/_ref/reference.zip``
 (git-ignored; ``/root/reference`` itself does not exist on the GPU box).  Nothing in the product package
 imports it.
 
@@ -18,7 +18,7 @@ import sys
 import types
 import warnings
 
-_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")     # refrun.stage(): travels with gpurun
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference.zip")     # refrun.stage(): travels with gpurun
 REFERENCE_DIR = os.environ.get("CCX_REFERENCE_DIR") or ("/root/reference" if os.path.isdir("/root/reference") else _STAGED)
 
 
@@ -48,7 +48,7 @@ def install():
     global _installed
     if _installed:
         return
-    if not os.path.isdir(REFERENCE_DIR):
+    if not os.path.exists(REFERENCE_DIR):
         raise RuntimeError("reference checkout not found at %s (golden generation only runs in the "
                            "build container)" % REFERENCE_DIR)
     warnings.filterwarnings("ignore")            # utils.py:13 has an invalid escape sequence

@@ -1,5 +1,5 @@
 """The literal drop-in: the UNMODIFIED reference callers (selfplay.py, game.py, player.py, MCTS.py — the staged copy under
-oracle/_ref/reference, see oracle/refrun.py) run on top of this package with `board`, `board_utils`, `utils`, `model`
+oracle/_ref/reference.zip, see oracle/refrun.py) run on top of this package with `board`, `board_utils`, `utils`, `model`
 (and, in the first scenario, `MCTS`) replaced by the facade modules through sys.modules — what a maintainer gets by
 putting the package in front of the reference's flat modules.  GPU only (the facade has no CPU path)."""
 import contextlib
@@ -26,7 +26,7 @@ def reference_over_facade(facade_mcts):
     """sys.modules view in which the reference's callers import the facade for everything on the hot path"""
     ref_dir = refrun.reference_dir()
     if ref_dir is None:
-        pytest.skip("no staged reference under oracle/_ref/reference (run __graft_entry__.build() where /root/reference exists)")
+        pytest.skip("no staged reference (oracle/_ref/reference.zip) (run __graft_entry__.build() where /root/reference exists)")
     import chinesecheckersagent_b200.board as f_board
     import chinesecheckersagent_b200.board_utils as f_board_utils
     import chinesecheckersagent_b200.MCTS as f_mcts
@@ -44,7 +44,7 @@ def reference_over_facade(facade_mcts):
         sys.dont_write_bytecode = True
         mods = {name: importlib.import_module(name) for name in ("MCTS", "player", "game", "selfplay")}
         for name in ("player", "game", "selfplay") + (() if facade_mcts else ("MCTS",)):
-            assert os.path.dirname(os.path.abspath(mods[name].__file__)) == os.path.abspath(ref_dir), name
+            assert os.path.abspath(mods[name].__file__).startswith(os.path.abspath(ref_dir)), name      # the reference's file, not ours
         assert mods["game"].Board is f_board.Board and mods["selfplay"].Board is f_board.Board
         assert (mods["player"].MCTS is f_mcts.MCTS) == facade_mcts
         yield mods
