@@ -44,6 +44,7 @@ SIGNATURES = {
     "ccx_softmax_f64": (i32, [vp, i64, vp, vp, vp, vp]),
     "ccx_net_eval": (i32, [vp, i64, vp, vp, vp]),
     "ccx_gamma_noise": (i32, [vp, i64, i32, f64, u64, u32, i64, vp]),
+    "ccx_set_slot_ids": (i32, [vp, vp]),
     "ccx_selfplay_advance": (i32, [vp, i64, vp, vp, vp, u64, i32, i64, vp, i64, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
     "ccx_selfplay_finish": (i32, [vp, i64, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     "ccx_traj_pack": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),

@@ -1158,4 +1158,5 @@ int ccx_encode_host(ccx_handle *h, int64_t n, const uint64_t *state_host, void *
 // weak defaults so that libccx.so links before the MCTS / net translation units exist
 __attribute__((weak)) void ccx_net_free(ccx_handle *) {}
 __attribute__((weak)) void ccx_trees_free(ccx_handle *) {}
+__attribute__((weak)) void ccx_trees_set_uids(ccx_handle *, const int64_t *) {}
 __attribute__((weak)) void ccx_net_tc_free(ccx_handle *) {}

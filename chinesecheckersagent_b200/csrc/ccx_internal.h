@@ -31,6 +31,7 @@ struct ccx_handle {
     uint8_t *jump_table = nullptr;   // CCX_JT_BYTES, device: ray-jump lookup table (ccx_device.cuh)
     uint8_t *jump_table3 = nullptr;  // CCX_JT3_BYTES, device: row / column / diagonal answer tables of k_step_random_tri
     uint8_t *jump_table2 = nullptr;  // CCX_JT2_BYTES, device: the same table, occupancy-major (k_step_random_ilp<LAYOUT = 1>)
+    const int64_t *slot_ids = nullptr;   // device, caller-owned: identities of a compacted batch (ccx_set_slot_ids)
     int tie_mode = 0;           // PUCT tie rule of this handle's searches (ccx_mcts_set_tiebreak)
     uint64_t tie_seed = 0;
     int64_t tie_uid0 = 0;
@@ -92,6 +93,7 @@ const float *ccx_net_pold_bias(const ccx_handle *h);     // fp32 policy-dense bi
 // sub-module teardown hooks (defined where the sub-module lives)
 void ccx_net_free(ccx_handle *h);
 void ccx_trees_free(ccx_handle *h);
+void ccx_trees_set_uids(ccx_handle *h, const int64_t *uids);     // tie-rule identities of the trees (ccx_set_slot_ids)
 void ccx_round_graph_free(ccx_handle *h);
 void ccx_net_tc_free(ccx_handle *h);
 void ccx_net_acc_free(ccx_handle *h);

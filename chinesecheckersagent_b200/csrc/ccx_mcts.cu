@@ -50,12 +50,13 @@ struct ccx_trees {
     // PUCT tie rule (ccx_mcts_set_tiebreak): 0 = first maximal edge, 1 = the reference's epsilon-tie list with a Philox draw
     int32_t tie_mode = 0;       // by value: selects the kernel instantiation (and keys the cached round graph)
     u32 *tie_params = nullptr;  // device u32[4]: Philox key lo/hi, uid0 lo/hi — in memory so that a new seed does not invalidate the graph
+    const int64_t *tie_uids = nullptr;   // device, caller-owned (ccx_set_slot_ids): uid of tree i when the batch is compacted, else uid0 + i
 };
 
 struct TreeView {
     u64 *node; u32 *eN; double *eW; double *eP; double *eQ; int32_t *eChild; u64 *eInfo; uint16_t *eMove; int32_t *path; int32_t *meta;
     int32_t npt, ept, path_max;
-    const u32 *tie; u64 tree_index;
+    const u32 *tie; const int64_t *tie_uids; u64 tree_index;
 };
 
 __device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
@@ -72,7 +73,7 @@ __device__ __forceinline__ TreeView tree_view(const ccx_trees &t, int64_t tree)
     v.path = t.path + tree * t.path_max;
     v.meta = t.tree_meta + tree * 8;
     v.npt = t.nodes_per_tree; v.ept = t.edges_per_tree; v.path_max = t.path_max;
-    v.tie = t.tie_params; v.tree_index = (u64)tree;
+    v.tie = t.tie_params; v.tie_uids = t.tie_uids; v.tree_index = (u64)tree;
     return v;
 }
 
@@ -240,7 +241,7 @@ __device__ __forceinline__ int select_leaf(const TreeView &tv, int lane, double 
                     total += __popc(cm[c]);
                 }
                 if (total > 1) {
-                    const u64 uid = (((u64)tv.tie[3] << 32) | tv.tie[2]) + tv.tree_index;
+                    const u64 uid = tv.tie_uids ? (u64)tv.tie_uids[tv.tree_index] : (((u64)tv.tie[3] << 32) | tv.tie[2]) + tv.tree_index;
                     Philox4 rnd = philox4x32_10(tv.tie[0], tv.tie[1], sim_index, (u32)depth, (u32)uid ^ (serial * 0x9E3779B9u),
                                                 (u32)(uid >> 32) ^ 0x7E1Bu);
                     int k = (int)__umulhi(rnd.x, (u32)total);
@@ -750,6 +751,11 @@ void ccx_round_graph_free(ccx_handle *h)
     if (h->cap_stream) { cudaStreamDestroy(h->cap_stream); h->cap_stream = nullptr; }
 }
 
+void ccx_trees_set_uids(ccx_handle *h, const int64_t *uids)
+{
+    if (h->trees) h->trees->tie_uids = uids;          // by-value kernel argument: part of the cached round graph's key
+}
+
 void ccx_trees_free(ccx_handle *h)
 {
     ccx_trees *t = h->trees;
@@ -783,6 +789,7 @@ static int trees_reserve(ccx_handle *h, int64_t n, int32_t num_itr, int32_t edge
     if (!t) return CCX_ERR_NOMEM;
     h->trees = t;
     t->tie_mode = h->tie_mode;
+    t->tie_uids = h->slot_ids;
     t->cap_trees = n; t->nodes_per_tree = npt; t->edges_per_tree = ept; t->path_max = pm;
     size_t T = (size_t)n;
     CCX_CUDA(h, cudaMalloc(&t->node, T * npt * NODE_WORDS * 8));

@@ -20,12 +20,13 @@ __device__ __forceinline__ double u01(u32 x) { return (double)x / 4294967296.0; 
 // ---- Dirichlet noise: raw Gamma(alpha, 1) draws, normalised later over the root's edge count -------------
 // Marsaglia-Tsang (2000) for alpha + 1 with the U^(1/alpha) boost for alpha < 1; Philox counter RNG.
 __global__ void __launch_bounds__(128)
-k_gamma_noise(double *__restrict__ out, int64_t n, int stride, double alpha, u32 k0, u32 k1, u32 iter, int64_t uid0)
+k_gamma_noise(double *__restrict__ out, int64_t n, int stride, double alpha, u32 k0, u32 k1, u32 iter, int64_t uid0,
+              const int64_t *__restrict__ slot_ids)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * stride) return;
     int64_t tree = t / stride; int j = (int)(t % stride);
-    u64 uid = (u64)(uid0 + tree);
+    u64 uid = (u64)(slot_ids ? slot_ids[tree] : uid0 + tree);
     const double d = alpha + 1.0 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
     double g = 0.0;
     for (u32 attempt = 0; attempt < 64; attempt++) {
@@ -90,7 +91,8 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
                    u32 k0, u32 k1, int iter, int64_t uid0, const int64_t *__restrict__ serial, int64_t total_slots,
                    int random_plies, int tau_switch, int move_limit,
                    u64 *__restrict__ rec_state, uint16_t *__restrict__ rec_visits, uint8_t *__restrict__ rec_flag,
-                   int rec_iters, u64 *__restrict__ counters, u32 *__restrict__ move_log, const uint8_t *__restrict__ jt)
+                   int rec_iters, u64 *__restrict__ counters, u32 *__restrict__ move_log, const uint8_t *__restrict__ jt,
+                   const int64_t *__restrict__ slot_ids)
 {
     __shared__ __align__(16) uint8_t sT[CCX_JT_BYTES];
     for (int q = threadIdx.x; q < CCX_JT_BYTES / 16; q += blockDim.x) reinterpret_cast<uint4 *>(sT)[q] = reinterpret_cast<const uint4 *>(jt)[q];
@@ -108,7 +110,7 @@ k_selfplay_advance(u64 *__restrict__ st, int64_t n, const u32 *__restrict__ visi
     gm.cells_me = p2 ? c2 : c1;   gm.cells_op = p2 ? c1 : c2;
     u64 lo = st[5 * n + g], hi = st[6 * n + g], aux = st[7 * n + g];
     int ply = (int)((meta >> 32) & 0xFFFF);
-    u64 uid = (u64)(serial[g] * total_slots + uid0 + g);                 // unique per game instance
+    u64 uid = (u64)(serial[g] * total_slots + (slot_ids ? slot_ids[g] : uid0 + g));      // unique per game instance
     int id, from, to;
     int recorded = (int)((aux >> 32) & 0xFFFF);
     if (ply < random_plies) {
@@ -290,10 +292,10 @@ k_selfplay_finish(u64 *__restrict__ st, int64_t n, int iter, int32_t *__restrict
     else if (status == CCX_ST_MOVE_LIMIT) atomicAdd(&counters[4], 1ULL);
     else if (status == CCX_ST_OVERFLOW) atomicAdd(&counters[5], 1ULL);
     if (kept) { atomicAdd(&counters[6], (u64)kept); atomicAdd(&counters[7], 1ULL); }
-    // train.py:58-64 plays exactly num_self_play games: a slot restarts only while the caller's budget of game starts lasts
-    bool again = restart != 0;
-    if (again && starts_left)                                    // old value > 0: one more start was available (the counter may go negative)
-        again = (long long)atomicAdd((unsigned long long *)starts_left, (unsigned long long)-1LL) > 0;
+    // train.py:58-64 plays exactly num_self_play games: with a budget of starts, WHICH of this iteration's ended slots restart is
+    // decided by k_selfplay_restart in slot order (deterministic; an atomic ticket here would make it a race)
+    if (restart && starts_left) { start_iter[g] = 0x7FFFFFFE; return; }
+    const bool again = restart != 0;
     start_iter[g] = again ? iter + 1 : 0x7FFFFFFF;               // records settled; a slot that stays ended is never accounted twice
     if (again) {
         st[0 * n + g] = CCX_START_OCC1; st[1 * n + g] = CCX_START_OCC2;
@@ -301,6 +303,46 @@ k_selfplay_finish(u64 *__restrict__ st, int64_t n, int iter, int32_t *__restrict
         st[4 * n + g] = CCX_START_META; st[5 * n + g] = CCX_HIST_EMPTY; st[6 * n + g] = CCX_HIST_EMPTY; st[7 * n + g] = 0;
         serial[g] += 1;
     }
+}
+
+// Restarts under a budget: the slots that ended in this iteration (start_iter == 0x7FFFFFFE) restart in slot order while
+// *starts_left > 0; the rest stay ended.  One block scans all slots (n is a few thousand).
+__global__ void __launch_bounds__(1024)
+k_selfplay_restart(u64 *__restrict__ st, int64_t n, int iter, int32_t *__restrict__ start_iter, int64_t *__restrict__ serial,
+                   long long *__restrict__ starts_left)
+{
+    __shared__ int warp_tot[32];
+    __shared__ long long budget_s;
+    __shared__ int base_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) { budget_s = *starts_left; base_s = 0; }
+    __syncthreads();
+    const long long budget = budget_s > 0 ? budget_s : 0;
+    for (int64_t g0 = 0; g0 < n; g0 += 1024) {
+        const int64_t g = g0 + t;
+        const bool cand = g < n && start_iter[g] == 0x7FFFFFFE;
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, cand);
+        if (lane == 0) warp_tot[warp] = __popc(b);
+        __syncthreads();
+        int before = base_s;
+        for (int w = 0; w < warp; w++) before += warp_tot[w];
+        const int rank = before + __popc(b & ((1u << lane) - 1u));
+        if (cand) {
+            if ((long long)rank < budget) {
+                st[0 * n + g] = CCX_START_OCC1; st[1 * n + g] = CCX_START_OCC2;
+                st[2 * n + g] = CCX_START_CELLS1; st[3 * n + g] = CCX_START_CELLS2;
+                st[4 * n + g] = CCX_START_META; st[5 * n + g] = CCX_HIST_EMPTY; st[6 * n + g] = CCX_HIST_EMPTY; st[7 * n + g] = 0;
+                start_iter[g] = iter + 1;
+                serial[g] += 1;
+            } else {
+                start_iter[g] = 0x7FFFFFFF;
+            }
+        }
+        __syncthreads();
+        if (t == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += warp_tot[w]; base_s += tot; }
+        __syncthreads();
+    }
+    if (t == 0) *starts_left = budget_s - (long long)(base_s < budget ? base_s : budget);
 }
 
 // ---- K11 trajectory pack: kept records -> board_x (u8 planes), pi_y (float32), v_y (int8) ---------------------
@@ -333,13 +375,21 @@ k_traj_pack(const int64_t *__restrict__ rows, int64_t m, const u64 *__restrict__
 
 extern "C" {
 
+int ccx_set_slot_ids(ccx_handle *h, const int64_t *slot_ids)
+{
+    if (!h) return CCX_ERR_ARG;
+    h->slot_ids = slot_ids;
+    ccx_trees_set_uids(h, slot_ids);
+    return CCX_OK;
+}
+
 int ccx_gamma_noise(ccx_handle *h, int64_t n, int32_t stride, double alpha, uint64_t seed, uint32_t iter, int64_t uid0,
                     double *out)
 {
     if (!h || n < 0 || stride < 1 || !(alpha > 0.0) || (n && !out)) return CCX_ERR_ARG;
     if (n == 0) return CCX_OK;
     int64_t t = n * stride;
-    k_gamma_noise<<<(unsigned)((t + 127) / 128), 128, 0, h->stream>>>(out, n, stride, alpha, (u32)seed, (u32)(seed >> 32), iter, uid0);
+    k_gamma_noise<<<(unsigned)((t + 127) / 128), 128, 0, h->stream>>>(out, n, stride, alpha, (u32)seed, (u32)(seed >> 32), iter, uid0, h->slot_ids);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -355,7 +405,7 @@ int ccx_selfplay_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32
     if (n == 0) return CCX_OK;
     k_selfplay_advance<<<(unsigned)((n + SP_WARPS - 1) / SP_WARPS), 32 * SP_WARPS, 0, h->stream>>>(
         (u64 *)state, n, visits, tree_nodes, (u32)seed, (u32)(seed >> 32), iter, uid0, serial, total_slots, random_plies,
-        tau_switch, move_limit, (u64 *)rec_state, rec_visits, rec_flag, rec_iters, (u64 *)counters, move_log, h->jump_table);
+        tau_switch, move_limit, (u64 *)rec_state, rec_visits, rec_flag, rec_iters, (u64 *)counters, move_log, h->jump_table, h->slot_ids);
     CCX_LAUNCHED(h);
     return CCX_OK;
 }
@@ -372,6 +422,10 @@ int ccx_selfplay_finish(ccx_handle *h, int64_t n, uint64_t *state, int32_t iter,
                                                                          (const u64 *)rec_state, rec_flag, rec_iters, max_game_iters,
                                                                          restart, (long long *)starts_left, (u64 *)counters);
     CCX_LAUNCHED(h);
+    if (restart && starts_left) {
+        k_selfplay_restart<<<1, 1024, 0, h->stream>>>((u64 *)state, n, iter, start_iter, serial, (long long *)starts_left);
+        CCX_LAUNCHED(h);
+    }
     return CCX_OK;
 }
 

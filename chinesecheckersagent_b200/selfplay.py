@@ -47,6 +47,7 @@ class BatchedSelfPlay:
         auto = getattr(owner, "fused_mcts", False) and getattr(owner, "eng", None) is engine and getattr(evaluate, "__name__", "") == "evaluate_states"
         self.fused = bool(auto) if fused is None else bool(fused)
         self.n, self.seed, self.rank, self.world = int(n_slots), int(seed), int(rank), int(world)
+        self.n0 = self.n                                 # slots at construction: RNG keys use rank * n0 + original slot index, compaction or not
         self.num_itr, self.cpuct, self.max_iters, self.ept = int(num_itr), float(cpuct), int(max_iters), int(edges_per_tree)
         self.dirichlet, self.ring, self.random_ties = dirichlet, bool(ring), bool(random_ties)
         self.opponent = opponent
@@ -72,6 +73,8 @@ class BatchedSelfPlay:
         self.rec_visits = e.zeros((self.max_iters * n, 294), torch.int16)
         self.rec_flag = e.zeros((self.max_iters * n,), torch.uint8)
         self.move_log = e.zeros((self.max_iters * n,), torch.int32) if log_moves else None
+        self.slot_ids = torch.arange(rank * n, (rank + 1) * n, dtype=torch.int64, device=e.device)     # global identity of every slot
+        self.compactions = 0
         self.iter = 0
         self._last_collect = 0
         self._chunks = []
@@ -83,7 +86,8 @@ class BatchedSelfPlay:
     def _search(self, eng, parity, visits, tree_nodes):
         """one full search of every slot whose mover uses the net living in `eng` (parity -1: all slots)"""
         n, st = self.n, self.env.state
-        eng.call("ccx_mcts_set_tiebreak", 1 if self.random_ties else 0, self.seed ^ 0x71E5, self.rank * n)
+        eng.call("ccx_set_slot_ids", _p(self.slot_ids))
+        eng.call("ccx_mcts_set_tiebreak", 1 if self.random_ties else 0, self.seed ^ 0x71E5, self.rank * self.n0)
         eng.call("ccx_mcts_begin", n, _p(st), self.num_itr + 1, self.ept, INITIAL_RANDOM_MOVES, parity)
         if self.fused:                                   # the library's own net: all rounds in one C call, fused round kernels
             eng.call("ccx_mcts_run_net", n, self.num_itr + 1, self.cpuct, _p(self.noise) if self.dirichlet else None,
@@ -95,6 +99,7 @@ class BatchedSelfPlay:
                 noise = self.noise if (r == 0 and self.dirichlet) else None
                 eng.call("ccx_mcts_expand_backup", n, _p(p), _p(v), _p(noise), NOISE_STRIDE if noise is not None else 0, 1)
         eng.call("ccx_mcts_finalize", n, 1.0, _p(visits), None, None, _p(tree_nodes))
+        eng.call("ccx_set_slot_ids", None)               # other users of this engine identify their trees by position again
 
     # one ply for every slot
     def step(self, restart=True):
@@ -102,8 +107,9 @@ class BatchedSelfPlay:
         if not self.ring and it >= self.max_iters:
             raise RuntimeError("record buffer full after max_iters = %d iterations: construct with ring=True (or a larger max_iters)"
                                % self.max_iters)
-        uid0 = self.rank * n
+        uid0 = self.rank * self.n0
         st = self.env.state
+        e.call("ccx_set_slot_ids", _p(self.slot_ids))
         if self.dirichlet:
             e.call("ccx_gamma_noise", n, NOISE_STRIDE, DIRICHLET_ALPHA, self.seed, it, uid0, _p(self.noise))
         if self.opponent is None:
@@ -116,18 +122,46 @@ class BatchedSelfPlay:
             self._search(self.opponent.eng, 1, self.visits2, self.tree_nodes2)
             visits = self.visits + self.visits2
             tree_nodes = torch.where(self.tree_nodes == -2, self.tree_nodes2, self.tree_nodes)
+        e.call("ccx_set_slot_ids", _p(self.slot_ids))
         e.call("ccx_selfplay_advance", n, _p(st), _p(visits), _p(tree_nodes), self.seed, it, uid0, _p(self.serial),
-               self.world * n, INITIAL_RANDOM_MOVES, TOTAL_MOVES_TILL_TAU0, PROGRESS_MOVE_LIMIT, _p(self.rec_state),
+               self.world * self.n0, INITIAL_RANDOM_MOVES, TOTAL_MOVES_TILL_TAU0, PROGRESS_MOVE_LIMIT, _p(self.rec_state),
                _p(self.rec_visits), _p(self.rec_flag), self.max_iters, _p(self.counters), _p(self.move_log))
         e.call("ccx_selfplay_finish", n, _p(st), it, _p(self.start_iter), _p(self.serial), _p(self.rec_state),
                _p(self.rec_flag), self.max_iters, self.max_game_iters if self.ring else 0, int(bool(restart)),
                _p(self.starts_left), _p(self.counters))
+        e.call("ccx_set_slot_ids", None)
         self.iter += 1
         if self.ring and self.iter - self._last_collect >= self.max_iters - self.max_game_iters:
             self._drain()
 
     def running(self):
         return int(((self.env.state[4] >> 56) == 0).sum().item())
+
+    def compact(self):
+        """Drop the slots whose game has ended and may not restart (the drain of play_games): the batch every kernel and the
+        net sees shrinks to the games still running, which continue bit for bit as they would have (their Philox streams are
+        keyed by `slot_ids`, not by position).  Finished records are moved out first.  Returns the new slot count."""
+        self._drain()
+        keep = torch.nonzero((self.env.state[4] >> 56) == 0).flatten()
+        m, n, R, e = int(keep.numel()), self.n, self.max_iters, self.eng
+        if m == 0 or m == n:
+            return n
+        by_iter = lambda t: t.view(R, n, *t.shape[1:])[:, keep].reshape(R * m, *t.shape[1:]).contiguous()
+        self.rec_state, self.rec_visits, self.rec_flag = by_iter(self.rec_state), by_iter(self.rec_visits), by_iter(self.rec_flag)
+        if self.move_log is not None:
+            self.move_log = by_iter(self.move_log)
+        state = self.env.state[:, keep].contiguous()
+        self.env = BatchedEnv(m, engine=e, seed=self.seed, game_id0=self.rank * self.n0, state=state)
+        self.serial, self.start_iter, self.slot_ids = (self.serial[keep].contiguous(), self.start_iter[keep].contiguous(),
+                                                       self.slot_ids[keep].contiguous())
+        self.n = m
+        self.leaf = e.empty((5, m), torch.int64)
+        self.noise = e.empty((m, NOISE_STRIDE), torch.float64)
+        self.visits, self.tree_nodes = e.empty((m, 294), torch.int32), e.empty((m,), torch.int32)
+        if self.opponent is not None:
+            self.visits2, self.tree_nodes2 = e.empty((m, 294), torch.int32), e.empty((m,), torch.int32)
+        self.compactions += 1
+        return m
 
     def stats(self):
         c = self.counters.cpu().tolist()
@@ -155,10 +189,12 @@ class BatchedSelfPlay:
                           % (done, out["games"], target_games), RuntimeWarning)
         return out
 
-    def play_games(self, num_games, poll_every=8, max_iterations=None):
+    def play_games(self, num_games, poll_every=8, max_iterations=None, compact=True, compact_min=256):
         """train.generate_self_play's contract (train.py:58-64): exactly `num_games` games are STARTED, every one of them is
         played to its end (win, or discarded by the repetition / progress rules), nothing else is recorded.  Slots restart
-        while the budget of starts lasts, then drain.  Returns stats(); the records are in collect()."""
+        while the budget of starts lasts, then drain; during the drain the batch is compacted whenever fewer than half of its
+        slots are still playing (`compact=False` keeps the full batch: same games, same records).  Returns stats(); the records
+        are in collect()."""
         if self.iter != 0:
             raise RuntimeError("play_games() needs a fresh BatchedSelfPlay")
         self.ring = True
@@ -172,10 +208,15 @@ class BatchedSelfPlay:
         cap = max_iterations or (2 + (num_games + n - 1) // n) * self.max_game_iters
         while self.iter < cap:
             self.step()
-            if self.iter % poll_every == 0 and self.running() == 0:
-                break
+            if self.iter % poll_every == 0:
+                live = self.running()
+                if live == 0:
+                    break
+                if compact and live * 2 <= self.n and self.n > compact_min and int(self.starts_left.item()) <= 0:
+                    self.compact()
         out = self.stats()
         out["unfinished"] = self.running()
+        out["compactions"] = self.compactions
         out["games_started"] = num_games - max(0, int(self.starts_left.item()))
         return out
 

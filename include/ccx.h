@@ -230,13 +230,19 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes);
  * ccx_selfplay_finish: labels the records of games that ended (reward from the mover's point of view,
  *   utils.py:65-71) or drops them for discarded games (selfplay.py:47,74); a running game that has been recorded for
  *   max_game_iters iterations (> 0) is discarded as CCX_ST_OVERFLOW before its records wrap around the ring.
- *   restart != 0 resets the slot of an ended game — if starts_left (device int64, may be NULL) is NULL or still positive
- *   (it is decremented per restart): train.py:58-64 plays exactly num_self_play games, so the caller sets
- *   starts_left = num_self_play - n and drains.  A slot that may not restart keeps its final status.
+ *   restart != 0 resets the slot of an ended game — if starts_left (device int64, may be NULL) is NULL or still positive:
+ *   train.py:58-64 plays exactly num_self_play games, so the caller sets starts_left = num_self_play - n and drains.  The
+ *   slots that ended in one iteration take the remaining starts in slot order (deterministic), *starts_left is decremented
+ *   by the number of restarts.  A slot that may not restart keeps its final status.
  * ccx_traj_pack: gathers kept records rows[m] into out_state uint64[5][m] (feed to ccx_encode for board_x),
  *   pi_y float32[m][294] and v_y int8[m]. */
 int ccx_gamma_noise(ccx_handle *h, int64_t n, int32_t stride, double alpha, uint64_t seed, uint32_t iter, int64_t uid0,
                     double *out);
+/* Slot identities for a COMPACTED batch.  By default slot / tree i of a call is identified as uid0 + i wherever a Philox stream is
+ * keyed by it (ccx_gamma_noise, ccx_selfplay_advance, the tie rule of the searches).  With slot_ids != NULL (device int64[n], stays
+ * referenced until reset with NULL) entry i is identified as slot_ids[i] instead, so a caller can drop finished slots from the batch
+ * (chinesecheckersagent_b200/selfplay.py: BatchedSelfPlay.compact) and the surviving games continue bit for bit as they would have. */
+int ccx_set_slot_ids(ccx_handle *h, const int64_t *slot_ids);
 int ccx_selfplay_advance(ccx_handle *h, int64_t n, uint64_t *state, const uint32_t *visits, const int32_t *tree_nodes,
                          uint64_t seed, int32_t iter, int64_t uid0, const int64_t *serial, int64_t total_slots,
                          int32_t random_plies, int32_t tau_switch, int32_t move_limit, uint64_t *rec_state,

@@ -234,3 +234,28 @@ def test_two_net_selfplay_with_twin_nets_equals_single_net(eng):
     with pytest.raises(ValueError):
         BatchedSelfPlay(eng, m1.evaluate_states, opponent=m1, **kw)
     eng2.close()
+
+
+def test_compaction_during_the_drain_changes_nothing(eng):
+    """play_games() drops finished slots from the batch while it drains (the net stops evaluating dummy positions for them).
+    The surviving games must continue bit for bit — same outcomes, same records — because every Philox stream (opening moves,
+    Dirichlet noise, tie draws, move sampling) is keyed by the slot's identity, not by its position in the batch."""
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    model = ResidualCNN(engine=eng).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+
+    def run(compact):
+        sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=320, seed=9, num_itr=10, max_iters=400)
+        st = sp.play_games(400, compact=compact, compact_min=24)
+        t = sp.collect()
+        key = np.vstack([t["state"].cpu().numpy(), t["v_y"].cpu().numpy()[None].astype(np.int64),
+                         (t["pi_y"].double() * torch.arange(1, 295, device=t["pi_y"].device)).sum(1).mul(1e6).round().long().cpu().numpy()[None]])
+        order = np.lexsort(key)
+        return st, t["board_x"].cpu().numpy()[order], t["pi_y"].cpu().numpy()[order], t["v_y"].cpu().numpy()[order], sp.n
+    a, b = run(False), run(True)
+    assert b[0]["compactions"] >= 1 and a[0]["compactions"] == 0 and b[4] < a[4] == 320
+    for k in ("plies", "p1_wins", "p2_wins", "discarded_repetition", "discarded_no_progress", "discarded_overflow", "records", "games",
+              "iterations", "games_started", "unfinished"):
+        assert a[0][k] == b[0][k], k
+    assert a[1].shape == b[1].shape and a[1].shape[0] == a[0]["records"] > 0
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
