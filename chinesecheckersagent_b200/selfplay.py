@@ -189,11 +189,11 @@ class BatchedSelfPlay:
                           % (done, out["games"], target_games), RuntimeWarning)
         return out
 
-    def play_games(self, num_games, poll_every=8, max_iterations=None, compact=True, compact_min=256):
+    def play_games(self, num_games, poll_every=8, max_iterations=None, compact=True, compact_min=256, compact_ratio=0.75):
         """train.generate_self_play's contract (train.py:58-64): exactly `num_games` games are STARTED, every one of them is
         played to its end (win, or discarded by the repetition / progress rules), nothing else is recorded.  Slots restart
-        while the budget of starts lasts, then drain; during the drain the batch is compacted whenever fewer than half of its
-        slots are still playing (`compact=False` keeps the full batch: same games, same records).  Returns stats(); the records
+        while the budget of starts lasts, then drain; during the drain the batch is compacted whenever no more than `compact_ratio` of its
+        slots are still playing (`compact_ratio`; `compact=False` keeps the full batch: same games, same records).  Returns stats(); the records
         are in collect()."""
         if self.iter != 0:
             raise RuntimeError("play_games() needs a fresh BatchedSelfPlay")
@@ -212,7 +212,7 @@ class BatchedSelfPlay:
                 live = self.running()
                 if live == 0:
                     break
-                if compact and live * 2 <= self.n and self.n > compact_min and int(self.starts_left.item()) <= 0:
+                if compact and live <= compact_ratio * self.n and self.n > compact_min and int(self.starts_left.item()) <= 0:
                     self.compact()
         out = self.stats()
         out["unfinished"] = self.running()
