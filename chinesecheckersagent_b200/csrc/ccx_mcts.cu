@@ -437,8 +437,15 @@ __device__ __forceinline__ void init_tree(const TreeView &tv, int lane, const u6
 }
 
 // Persistent search with an in-kernel evaluator: every warp runs all simulations of its tree.
+// select_leaf<PREFETCH> in the persistent kernel: measured again in r02 under the 72-register cap (one resident wave): 1.321 ms
+// per 4,096-tree search with the prefetch against 1.310 ms without (round 1 saw -19 % because 84 registers split the launch
+// into 1.15 waves).  No gain either way: at 1,100 warp instructions per simulation and 59 % issue utilisation the kernel is as
+// much instruction- as latency-bound.
+#ifndef CCX_SEARCH_PREFETCH
+#define CCX_SEARCH_PREFETCH false
+#endif
 template <int EVAL, bool TIES>
-__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK)
+__global__ void __launch_bounds__(32 * MCTS_WARPS_PER_BLOCK, 14)
 k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num_itr, double cpuct, int pre_expand,
               const double *__restrict__ noise, int noise_stride, const uint8_t *__restrict__ jt)
 {
@@ -458,7 +465,7 @@ k_mcts_search(ccx_trees trees, const u64 *__restrict__ roots, int64_t n, int num
     __syncwarp();
     for (int it = 0; it < num_itr; it++) {                                   // MCTS.py:123-125
         int path_len, kind;
-        int leaf = select_leaf<false, TIES>(tv, lane, cpuct, path_len, kind);
+        int leaf = select_leaf<CCX_SEARCH_PREFETCH, TIES>(tv, lane, cpuct, path_len, kind);
         __syncwarp();
         if (kind == LEAF_TERMINAL) backup(tv, lane, path_len, 0.0, true);
         else if (kind == LEAF_EVAL) eval_expand_backup<EVAL>(tv, lane, leaf, path_len, sT);
