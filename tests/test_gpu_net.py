@@ -45,12 +45,13 @@ def test_forward_matches_restatement(model, gold, dtype):
 
 
 @pytest.mark.parametrize("tc_dtype,bar_p,bar_v", [("fp16", 5e-3, 4e-3), ("bf16", 5e-2, 2e-2)])
-def test_tensor_core_kernel_vs_restatement(model, gold, tc_dtype, bar_p, bar_v):
-    """tcgen05 path: 16-bit operands, fp32 accumulation in TMEM, fp32 residual stream in registers.
-    Measured on B200 (r01, 256 fixture positions): fp16 max|dp| 3.2e-3 (mean 5.5e-6), max|dv| 2.0e-3;
-    bf16 max|dp| 2.8e-2 (mean 4.4e-5), max|dv| 9.6e-3; argmax agreement 100 % for both.  The north_star's
-    1e-3 bar is met by the fp32 kernel (test_forward_matches_restatement); a 16-bit-operand kernel cannot meet
-    it on this net, so the bars asserted here are the measured ones with ~1.6x margin."""
+def test_16bit_throughput_mode_regression_bounds(model, gold, tc_dtype, bar_p, bar_v):
+    """NOT a parity test: the 16-bit tcgen05 mode (`set_kernel('tc')`) is OUT of the north_star's 1e-3 tolerance and is never the
+    default; parity of the net is asserted on the accurate mode and the fp32 kernel
+    (test_accurate_tensor_core_mode_meets_the_1e3_bar, test_forward_matches_restatement, test_net_bar_on_10k_positions_...).
+    This test only keeps the throughput mode from regressing: its error stays at the level measured on B200 (256 fixture
+    positions: fp16 max|dp| 3.2e-3, mean 5.5e-6, max|dv| 2.0e-3; bf16 max|dp| 2.8e-2, max|dv| 9.6e-3; ~1.6x margin) and its
+    arg-max move agrees with the reference's."""
     planes = torch.from_numpy(gold["planes"]).cuda()
     model.set_kernel("tc", tc_dtype=tc_dtype)
     ltc, vtc = model.forward(planes)
