@@ -8,7 +8,7 @@
 #include "ccx_internal.h"
 
 #ifndef CCX_STEP_DEFAULT_VARIANT
-#define CCX_STEP_DEFAULT_VARIANT 5      // k_step_random_tri; 0 = k_step_random_flat (r01), see ccx_step_random for the A/B list
+#define CCX_STEP_DEFAULT_VARIANT 8      // k_step_random_wq; 5 = k_step_random_tri, 0 = k_step_random_flat (r01), see ccx_step_random for the A/B list
 #endif
 #ifndef CCX_GREEDY_DEFAULT_VARIANT
 #define CCX_GREEDY_DEFAULT_VARIANT 1      // k_play_greedy_tri<448, 2>: 6.78e9 plies/s against 4.57e9 for k_play_greedy at 131,072 games (profiles/r02c_greedy_variants.log)
@@ -579,6 +579,117 @@ k_step_random_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
     if (w2) atomicAdd(&wins[1], (u64)w2);
 }
 
+// --------------------------------------------------------------------------------------------------
+// Work-queue step kernel (A/B variant 8): a warp owns 32 games and steps them ply by ply TOGETHER; within a ply the
+// 32 x 6 checker flood fills are work items that the lanes take from a warp-wide queue (a ballot + popc hands out the next
+// indices), so a lane that finishes a short closure continues with another game's checker instead of waiting: the ply costs
+// ~(total expansions) / 32 iterations instead of the longest lane's, and the pick / apply / win / Philox tail runs once per
+// ply with all 32 lanes.  Same three-layout expansion and tables as k_step_random_tri; bit-identical results.
+template <bool TRACE, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB, 1)
+k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies,
+                 u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games, const uint8_t *__restrict__ jt3)
+{
+    extern __shared__ __align__(16) u64 sDyn[];                       // per warp: [6][32] jump closures, then [4][32] game words of the ply
+    __shared__ __align__(16) uint8_t sAll[CCX_JT3_BYTES + 5 * 64 * 8];
+    const uint8_t *sT = sAll;
+    u64 *sNB = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES);
+    u64 *sCI = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 512);
+    u64 *sO = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 1024);
+    u64 *sOT = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 1536);
+    u64 *sOD = reinterpret_cast<u64 *>(sAll + CCX_JT3_BYTES + 2048);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = tid; q < CCX_JT3_BYTES / 16; q += TPB) reinterpret_cast<uint4 *>(sAll)[q] = reinterpret_cast<const uint4 *>(jt3)[q];
+    for (int q = tid; q < 64; q += TPB) {
+        const bool on = (CCX_VALID >> q) & 1;
+        sNB[q] = on ? (neighbours(1ULL << q) & CCX_VALID) : 0ULL;
+        sCI[q] = on ? tri_cell_info(q) : 0ULL;
+        sO[q] = 1ULL << q;
+        sOT[q] = on ? 1ULL << tri_tbit(q) : 0ULL;
+        sOD[q] = on ? 1ULL << tri_dbit(q) : 0ULL;
+    }
+    __syncthreads();
+    u64 *sD = sDyn + warp * (10 * 32);          // [6][32]
+    u64 *sG = sD + 6 * 32;                      // [4][32]: occ_all, occT_all, occD_all, cells_me of the warp's 32 games
+    const int64_t i = (int64_t)blockIdx.x * TPB + tid;
+    const bool act = i < n;
+    Game g = load_game(st, n, act ? i : 0);
+    if (!act) reset_start(g);                   // lanes past the end play a dummy game that is never stored
+    const u64 gid = (u64)(gid0 + i);
+    u32 w1 = 0, w2 = 0;
+    u64 occT_all, occD_all;
+    tri_build(g.cells_me, g.cells_op, sOT, sOD, occT_all, occD_all);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int t = 0; t < plies; t++) {
+        const u64 occ_all = g.occ_me | g.occ_op;
+        sG[0 * 32 + lane] = occ_all; sG[1 * 32 + lane] = occT_all; sG[2 * 32 + lane] = occD_all; sG[3 * 32 + lane] = g.cells_me;
+        __syncwarp();
+        // ---- the ply's 192 flood fills from the warp's queue: item idx = checker (idx >> 5) of game (idx & 31)
+        int next = 0, state = 0, gi = 0, k = 0;          // state: 0 wants an item, 1 working, 2 queue empty
+        u64 o = 0, occ = 0, occT = 0, occD = 0, todo = 0, reach = 0;
+        for (;;) {
+            const unsigned want = __ballot_sync(0xFFFFFFFFu, state == 0);
+            if (want) {
+                const int idx = next + __popc(want & lt_mask);
+                next += __popc(want);
+                if (state == 0) {
+                    if (idx < 192) {
+                        gi = idx & 31; k = idx >> 5;
+                        const int cell = (int)((sG[3 * 32 + gi] >> (8 * k)) & 0x3F);
+                        o = sO[cell];
+                        occ = sG[0 * 32 + gi] & ~o; occT = sG[1 * 32 + gi] & ~sOT[cell]; occD = sG[2 * 32 + gi] & ~sOD[cell];
+                        todo = o; reach = 0; state = 1;
+                    } else state = 2;
+                }
+            }
+            if (state == 1) {
+                const int c = 63 - __clzll((long long)todo);
+                todo ^= sO[c];
+                const u64 nw = expand_cell_tri(c, occ, occT, occD, sT, sCI) & ~(reach | o);
+                reach |= nw;
+                todo |= nw;
+                if (todo == 0) { sD[k * 32 + gi] = reach; state = 0; }
+            }
+            if (__ballot_sync(0xFFFFFFFFu, state != 2) == 0) break;
+        }
+        __syncwarp();
+        // ---- tail, all 32 lanes: destinations = empty neighbours | jump closure, pick, apply, win
+        u64 dest[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) dest[q] = sD[q * 32 + lane] | (sNB[(g.cells_me >> (8 * q)) & 0x3F] & ~occ_all);
+        u32 nonempty = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) nonempty += dest[q] != 0;
+        u64 *row = nullptr;
+        if (TRACE && i < trace_games) {
+            row = trace + ((int64_t)t * trace_games + i) * CCX_TRACE_WORDS;
+            bool p2 = (g.meta >> 48) & 1;
+            row[0] = p2 ? g.occ_op : g.occ_me; row[1] = p2 ? g.occ_me : g.occ_op;
+            row[2] = p2 ? g.cells_op : g.cells_me; row[3] = p2 ? g.cells_me : g.cells_op;
+            row[4] = g.meta & 0x00FFFFFFFFFFFFFFULL;
+#pragma unroll
+            for (int q = 0; q < 6; q++) row[5 + q] = dest[q];
+            row[11] = 0xFFULL | (0xFFULL << 8) | (0xFFULL << 24);
+        }
+        if (nonempty) {
+            Philox4 rnd = philox4x32_10(k0, k1, step0 + (u32)t, 0u, (u32)gid, (u32)(gid >> 32));
+            int from, to;
+            int pid = pick_random(g, dest, nonempty, rnd.x, rnd.y, from, to);
+            apply_move(g, pid, from, to);
+            occT_all ^= sOT[from] | sOT[to];
+            occD_all ^= sOD[from] | sOD[to];
+            int win = winner_of(g);
+            if (TRACE && row) row[11] = (u64)from | ((u64)to << 8) | ((u64)win << 16) | ((u64)pid << 24);
+            if (win) { w1 += win == 1; w2 += win == 2; reset_start(g); tri_build(g.cells_me, g.cells_op, sOT, sOD, occT_all, occD_all); }
+        }
+        __syncwarp();                             // sD / sG are rewritten by the next ply
+    }
+    if (!act) return;
+    store_game(st, n, i, g);
+    if (w1) atomicAdd(&wins[0], (u64)w1);
+    if (w2) atomicAdd(&wins[1], (u64)w2);
+}
+
 __global__ void k_build_jump_table3(uint8_t *T3) { build_jump_table3(T3, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 
 __global__ void k_build_jump_table2(uint8_t *T2) { build_jump_table2(T2, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
@@ -942,7 +1053,9 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
     unsigned grid = blocks_for(n, ENV_THREADS);
     static const bool nested = getenv("CCX_STEP_NESTED") != nullptr;     // A/B switch for profiling the older kernel
     // kernel variant (CCX_STEP_VARIANT, for A/B runs; all bit-identical; B200, 65,536 games x 256 plies, profiles/r02b_env_variants.log):
-    //   5 (default) k_step_random_tri, three occupancy layouts + pre-scattered answers, 448-lane blocks   2.82 ms  5.96e9 steps/s
+    //   8 (default) k_step_random_wq: the tri expansion, but a warp steps its 32 games ply by ply and hands the ply's 192
+    //               flood fills out from a warp-wide queue; one full-warp tail per ply                    2.62 ms  6.42e9 steps/s
+    //   5           k_step_random_tri, three occupancy layouts + pre-scattered answers, 448-lane blocks   2.76 ms  6.09e9
     //   6 / 7       the same with 224- / 128-lane blocks                                                  2.97 / 3.07 ms
     //   0           k_step_random_flat (round 1)                                                          3.39 ms  4.95e9
     //   1           flat with the occupancy-major byte table (fewer bank conflicts)                        3.31 ms
@@ -971,6 +1084,21 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
         if (tr) CCX_ILP_LAUNCH(true, 1, 2, 32, 24); else CCX_ILP_LAUNCH(false, 1, 2, 32, 24);
     } else if (variant == 4) {
         if (tr) CCX_ILP_LAUNCH(true, 0, 1, 64, 12); else CCX_ILP_LAUNCH(false, 0, 1, 64, 12);
+    } else if (variant == 8) {
+#define CCX_WQ_LAUNCH(TR, TPB, MINB)                                                                                             \
+        do {                                                                                                                      \
+            static bool attr_set = false;                                                                                         \
+            constexpr int DYN = (TPB / 32) * 10 * 32 * 8;                                                                          \
+            if (!attr_set) {                                                                                                      \
+                CCX_CUDA(h, cudaFuncSetAttribute(k_step_random_wq<TR, TPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN)); \
+                attr_set = true;                                                                                                  \
+            }                                                                                                                     \
+            k_step_random_wq<TR, TPB, MINB><<<blocks_for(n, TPB), TPB, DYN, h->stream>>>(                                          \
+                (u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, tp, tg, h->jump_table3);                              \
+        } while (0)
+        if (n <= (int64_t)h->num_sms * 448) { if (tr) CCX_WQ_LAUNCH(true, 448, 1); else CCX_WQ_LAUNCH(false, 448, 1); }
+        else { if (tr) CCX_WQ_LAUNCH(true, 448, 2); else CCX_WQ_LAUNCH(false, 448, 2); }
+#undef CCX_WQ_LAUNCH
     } else if (variant >= 5 && variant <= 7) {
 #define CCX_TRI_LAUNCH(TR, TPB, MINB)                                                                                            \
         do {                                                                                                                      \
