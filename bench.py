@@ -30,7 +30,7 @@ SEED = 0x5EED2026
 METRIC = "env_steps_per_sec"
 UNIT = "env steps/s"
 N_SMS, SCHEDULERS_PER_SM = 148, 4
-STEP_KERNEL = "k_step_random_wq<false, 448, 1>"     # the default variant of ccx_step_random (csrc/ccx_env.cu)
+STEP_KERNEL = "k_step_random_wq<false, 448, 1, true>"     # the default variant of ccx_step_random (csrc/ccx_env.cu)
 
 
 def workload_config(n):

@@ -8,7 +8,7 @@
 #include "ccx_internal.h"
 
 #ifndef CCX_STEP_DEFAULT_VARIANT
-#define CCX_STEP_DEFAULT_VARIANT 8      // k_step_random_wq; 5 = k_step_random_tri, 0 = k_step_random_flat (r01), see ccx_step_random for the A/B list
+#define CCX_STEP_DEFAULT_VARIANT 9      // k_step_random_wq with precomputed items; 5 = k_step_random_tri, 0 = k_step_random_flat (r01), see ccx_step_random
 #endif
 #ifndef CCX_GREEDY_DEFAULT_VARIANT
 #define CCX_GREEDY_DEFAULT_VARIANT 1      // k_play_greedy_tri<448, 2>: 6.78e9 plies/s against 4.57e9 for k_play_greedy at 131,072 games (profiles/r02c_greedy_variants.log)
@@ -585,7 +585,10 @@ k_step_random_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
 // indices), so a lane that finishes a short closure continues with another game's checker instead of waiting: the ply costs
 // ~(total expansions) / 32 iterations instead of the longest lane's, and the pick / apply / win / Philox tail runs once per
 // ply with all 32 lanes.  Same three-layout expansion and tables as k_step_random_tri; bit-identical results.
-template <bool TRACE, int TPB, int MINB>
+// PRE: the owner lane of a game writes the four words of each of its six items (mover bit, occupancy without the mover in the
+// three layouts) to shared memory at the start of the ply, with all 32 lanes active, instead of every lane deriving them when it
+// takes an item (a divergent block that runs for ~7 lanes in nearly every iteration).  Costs 24 KB more shared memory per 448 lanes.
+template <bool TRACE, int TPB, int MINB, bool PRE>
 __global__ void __launch_bounds__(TPB, MINB, 1)
 k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, u32 step0, int plies,
                  u64 *__restrict__ wins, u64 *__restrict__ trace, int64_t trace_games, const uint8_t *__restrict__ jt3)
@@ -609,8 +612,10 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
         sOD[q] = on ? 1ULL << tri_dbit(q) : 0ULL;
     }
     __syncthreads();
-    u64 *sD = sDyn + warp * (10 * 32);          // [6][32]
-    u64 *sG = sD + 6 * 32;                      // [4][32]: occ_all, occT_all, occD_all, cells_me of the warp's 32 games
+    constexpr int WARP_WORDS = PRE ? (6 + 4 * 6) * 32 : 10 * 32;
+    u64 *sD = sDyn + warp * WARP_WORDS;         // [6][32]
+    u64 *sG = sD + 6 * 32;                      // !PRE: [4][32] occ_all, occT_all, occD_all, cells_me of the warp's 32 games
+                                                //  PRE: [4][192] per item (idx = checker * 32 + game): o, occ, occT, occD
     const int64_t i = (int64_t)blockIdx.x * TPB + tid;
     const bool act = i < n;
     Game g = load_game(st, n, act ? i : 0);
@@ -622,7 +627,19 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int t = 0; t < plies; t++) {
         const u64 occ_all = g.occ_me | g.occ_op;
-        sG[0 * 32 + lane] = occ_all; sG[1 * 32 + lane] = occT_all; sG[2 * 32 + lane] = occD_all; sG[3 * 32 + lane] = g.cells_me;
+        if (PRE) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                const int cell = (int)((g.cells_me >> (8 * q)) & 0x3F);
+                const u64 oq = sO[cell];
+                sG[0 * 192 + q * 32 + lane] = oq;
+                sG[1 * 192 + q * 32 + lane] = occ_all & ~oq;
+                sG[2 * 192 + q * 32 + lane] = occT_all & ~sOT[cell];
+                sG[3 * 192 + q * 32 + lane] = occD_all & ~sOD[cell];
+            }
+        } else {
+            sG[0 * 32 + lane] = occ_all; sG[1 * 32 + lane] = occT_all; sG[2 * 32 + lane] = occD_all; sG[3 * 32 + lane] = g.cells_me;
+        }
         __syncwarp();
         // ---- the ply's 192 flood fills from the warp's queue: item idx = checker (idx >> 5) of game (idx & 31)
         int next = 0, state = 0, gi = 0, k = 0;          // state: 0 wants an item, 1 working, 2 queue empty
@@ -634,10 +651,15 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
                 next += __popc(want);
                 if (state == 0) {
                     if (idx < 192) {
-                        gi = idx & 31; k = idx >> 5;
-                        const int cell = (int)((sG[3 * 32 + gi] >> (8 * k)) & 0x3F);
-                        o = sO[cell];
-                        occ = sG[0 * 32 + gi] & ~o; occT = sG[1 * 32 + gi] & ~sOT[cell]; occD = sG[2 * 32 + gi] & ~sOD[cell];
+                        if (PRE) {
+                            gi = idx;                     // the parking slot sD[checker * 32 + game] is the item index itself
+                            o = sG[0 * 192 + idx]; occ = sG[1 * 192 + idx]; occT = sG[2 * 192 + idx]; occD = sG[3 * 192 + idx];
+                        } else {
+                            gi = idx & 31; k = idx >> 5;
+                            const int cell = (int)((sG[3 * 32 + gi] >> (8 * k)) & 0x3F);
+                            o = sO[cell];
+                            occ = sG[0 * 32 + gi] & ~o; occT = sG[1 * 32 + gi] & ~sOT[cell]; occD = sG[2 * 32 + gi] & ~sOD[cell];
+                        }
                         todo = o; reach = 0; state = 1;
                     } else state = 2;
                 }
@@ -648,7 +670,7 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
                 const u64 nw = expand_cell_tri(c, occ, occT, occD, sT, sCI) & ~(reach | o);
                 reach |= nw;
                 todo |= nw;
-                if (todo == 0) { sD[k * 32 + gi] = reach; state = 0; }
+                if (todo == 0) { sD[PRE ? gi : k * 32 + gi] = reach; state = 0; }
             }
             if (__ballot_sync(0xFFFFFFFFu, state != 2) == 0) break;
         }
@@ -1053,8 +1075,10 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
     unsigned grid = blocks_for(n, ENV_THREADS);
     static const bool nested = getenv("CCX_STEP_NESTED") != nullptr;     // A/B switch for profiling the older kernel
     // kernel variant (CCX_STEP_VARIANT, for A/B runs; all bit-identical; B200, 65,536 games x 256 plies, profiles/r02b_env_variants.log):
-    //   8 (default) k_step_random_wq: the tri expansion, but a warp steps its 32 games ply by ply and hands the ply's 192
-    //               flood fills out from a warp-wide queue; one full-warp tail per ply                    2.62 ms  6.42e9 steps/s
+    //   9 (default) k_step_random_wq<PRE>: as 8, the items' occupancy words precomputed by the owner lanes  2.47 ms  6.80e9 steps/s
+    //               (one wave only: 156 KB of shared memory per 448-lane block; larger batches run variant 8, two blocks per SM)
+    //   8           k_step_random_wq: the tri expansion, but a warp steps its 32 games ply by ply and hands the ply's 192
+    //               flood fills out from a warp-wide queue; one full-warp tail per ply                    2.62 ms  6.42e9
     //   5           k_step_random_tri, three occupancy layouts + pre-scattered answers, 448-lane blocks   2.76 ms  6.09e9
     //   6 / 7       the same with 224- / 128-lane blocks                                                  2.97 / 3.07 ms
     //   0           k_step_random_flat (round 1)                                                          3.39 ms  4.95e9
@@ -1084,20 +1108,23 @@ int ccx_step_random(ccx_handle *h, int64_t n, uint64_t *state, int64_t game_id0,
         if (tr) CCX_ILP_LAUNCH(true, 1, 2, 32, 24); else CCX_ILP_LAUNCH(false, 1, 2, 32, 24);
     } else if (variant == 4) {
         if (tr) CCX_ILP_LAUNCH(true, 0, 1, 64, 12); else CCX_ILP_LAUNCH(false, 0, 1, 64, 12);
-    } else if (variant == 8) {
-#define CCX_WQ_LAUNCH(TR, TPB, MINB)                                                                                             \
+    } else if (variant == 8 || variant == 9) {
+#define CCX_WQ_LAUNCH(TR, TPB, MINB, PRE)                                                                                        \
         do {                                                                                                                      \
             static bool attr_set = false;                                                                                         \
-            constexpr int DYN = (TPB / 32) * 10 * 32 * 8;                                                                          \
+            constexpr int DYN = (TPB / 32) * ((PRE) ? 30 : 10) * 32 * 8;                                                           \
             if (!attr_set) {                                                                                                      \
-                CCX_CUDA(h, cudaFuncSetAttribute(k_step_random_wq<TR, TPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN)); \
+                CCX_CUDA(h, cudaFuncSetAttribute(k_step_random_wq<TR, TPB, MINB, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN)); \
                 attr_set = true;                                                                                                  \
             }                                                                                                                     \
-            k_step_random_wq<TR, TPB, MINB><<<blocks_for(n, TPB), TPB, DYN, h->stream>>>(                                          \
+            k_step_random_wq<TR, TPB, MINB, PRE><<<blocks_for(n, TPB), TPB, DYN, h->stream>>>(                                     \
                 (u64 *)state, n, game_id0, s0, s1, step0, plies, (u64 *)wins, tp, tg, h->jump_table3);                              \
         } while (0)
-        if (n <= (int64_t)h->num_sms * 448) { if (tr) CCX_WQ_LAUNCH(true, 448, 1); else CCX_WQ_LAUNCH(false, 448, 1); }
-        else { if (tr) CCX_WQ_LAUNCH(true, 448, 2); else CCX_WQ_LAUNCH(false, 448, 2); }
+        const bool pre = variant == 9;
+        if (n <= (int64_t)h->num_sms * 448) {
+            if (pre) { if (tr) CCX_WQ_LAUNCH(true, 448, 1, true); else CCX_WQ_LAUNCH(false, 448, 1, true); }
+            else { if (tr) CCX_WQ_LAUNCH(true, 448, 1, false); else CCX_WQ_LAUNCH(false, 448, 1, false); }
+        } else { if (tr) CCX_WQ_LAUNCH(true, 448, 2, false); else CCX_WQ_LAUNCH(false, 448, 2, false); }
 #undef CCX_WQ_LAUNCH
     } else if (variant >= 5 && variant <= 7) {
 #define CCX_TRI_LAUNCH(TR, TPB, MINB)                                                                                            \

@@ -10,7 +10,7 @@ from chinesecheckersagent_b200.arena import BatchedArena, GREEDY
 eng = Engine(0)
 env = BatchedEnv(300, engine=eng)
 env.step_random(24); env.movegen(); env.encode(); env.greedy_candidates()
-for variant in ("0", "1", "2", "3", "4", "6", "7", "5", "8"):      # every env-step kernel variant, the default (8) last
+for variant in ("0", "1", "2", "3", "4", "6", "7", "5", "8", "9"): # every env-step kernel variant, the default (9) last
     os.environ["CCX_STEP_VARIANT"] = variant
     BatchedEnv(1000, engine=eng).step_random(12, trace_games=40)
     BatchedEnv(70000, engine=eng).step_random(3)                   # > 148 x 448 games: the two-blocks-per-SM instantiation
