@@ -643,12 +643,15 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
         __syncwarp();
         // ---- the ply's 192 flood fills from the warp's queue: item idx = checker (idx >> 5) of game (idx & 31)
         int next = 0, state = 0, gi = 0, k = 0;          // state: 0 wants an item, 1 working, 2 queue empty
+        int working = 32;                                // lanes in state 0 or 1 (warp-uniform): the loop ends when it reaches 0
         u64 o = 0, occ = 0, occT = 0, occD = 0, todo = 0, reach = 0;
         for (;;) {
-            const unsigned want = __ballot_sync(0xFFFFFFFFu, state == 0);
+            const unsigned want = __ballot_sync(0xFFFFFFFFu, state == 0);      // the one vote per iteration
             if (want) {
                 const int idx = next + __popc(want & lt_mask);
-                next += __popc(want);
+                const int asked = __popc(want), left = 192 - next;
+                working -= asked > left ? asked - (left > 0 ? left : 0) : 0;      // lanes that find the queue empty retire
+                next += asked;
                 if (state == 0) {
                     if (idx < 192) {
                         if (PRE) {
@@ -663,6 +666,7 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
                         todo = o; reach = 0; state = 1;
                     } else state = 2;
                 }
+                if (working == 0) break;
             }
             if (state == 1) {
                 const int c = 63 - __clzll((long long)todo);
@@ -672,7 +676,6 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
                 todo |= nw;
                 if (todo == 0) { sD[PRE ? gi : k * 32 + gi] = reach; state = 0; }
             }
-            if (__ballot_sync(0xFFFFFFFFu, state != 2) == 0) break;
         }
         __syncwarp();
         // ---- tail, all 32 lanes: destinations = empty neighbours | jump closure, pick, apply, win
