@@ -893,6 +893,11 @@ k_play_greedy_tri(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1,
     }
 }
 
+// Tried and dropped (r02): Game.start as a warp work queue like k_step_random_wq (the warp's 32 games ply by ply, the flood fills of
+// the games still running handed out from a warp-wide queue, one greedy tail per ply): same games bit for bit, but 0.996 ms per
+// 131,072 games against 0.841 ms for k_play_greedy_tri — games end at different plies, so a ply-synchronous warp spends its last
+// 20-30 plies on a handful of games at full per-ply overhead, and the 156 KB block leaves one block per SM.
+
 // --------------------------------------------------------------------------------------------------
 // K5 plane encoder  (utils.py:101-160): planes (2k, 2k+1) = id-labelled (mover, opponent) position k
 // plies ago, k < min(plies, 2) + 1; plane 6 = 1 iff player 2 is to move.  Each block stages G games'
