@@ -4,7 +4,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libccx.so")
+LIB_PATH = os.environ.get("CCX_LIB_PATH") or os.path.join(PKG, "libccx.so")     # CCX_LIB_PATH: an instrumented build of the same sources (experiments)
 
 i64, i32, u64, u32, f64, vp = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32,
                                ctypes.c_double, ctypes.c_void_p)
@@ -59,6 +59,7 @@ SIGNATURES = {
     "ccx_net_forward_u8": (i32, [vp, i64, vp, vp, vp]),
     "ccx_net_acc_blob_bytes": (i32, []),
     "ccx_net_load_acc": (i32, [vp, vp, i64]),
+    "ccx_net_set_acc_contexts": (i32, [vp, i32]),
     "ccx_debug_umma_gemm": (i32, [vp, vp, vp, i32, i32, vp]),
     "ccx_debug_umma_gemm_ts": (i32, [vp, vp, vp, i32, vp]),
     "ccx_debug_umma_gemm_rows": (i32, [vp, vp, i32, i32, vp, i32, i32, vp]),

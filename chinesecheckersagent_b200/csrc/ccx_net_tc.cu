@@ -1073,6 +1073,410 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
     if (warp == 0) umma::tmem_free(tmem, 256);
 }
 
+// =====================================================================================================
+// Accurate trunk, multi-context form (r02 second session): ONE CTA per SM runs NCTX independent 256-thread contexts, one
+// tile each, that SHARE the streamed weight slots.  k_net_trunk_acc keeps a private 58 KB weight copy per CTA, so only two
+// tiles fit on an SM; its ncu profile (profiles/r02c_kernels_ncu.md) shows every context waiting for the tensor core half of
+// its time while the tensor core is busy 55 % of the time — two contexts are not enough to keep it fed.  Sharing the slots
+// makes room for three (221 KB of shared memory, 3 x 160 of the 512 TMEM columns, 80 registers):
+//  * TMEM per context: X fp32 [64] | XH|XL split 16-bit residual [32+32], REUSED as conv B's N = 64 accumulator (conv A has
+//    consumed XH / XL by then) | AO [32]: conv A / heads output, REUSED for conv C's operand (hi 16 | lo 16).  The three
+//    regions of all contexts are laid out region-major so that every accumulator starts at a multiple of its width.
+//  * weight slots: a layer's operand lands once per CTA; each context's issuing lane waits for the slot's "full" barrier
+//    before its MMAs and counts itself off after they complete; the last of the contexts still working in this round
+//    streams the next layer in.  A context runs at most one slot use ahead of the slowest one.
+//  * tiles: tile = round * (grid * NCTX) + ctx * grid + block, so the last, partial round is spread over the SMs instead of
+//    filling some CTAs' three contexts; contexts without a tile leave (the counts above use the round's active contexts).
+//  * the next tile's input planes are prefetched into registers while the current tile computes (k_net_trunk_acc staged them
+//    byte by byte at the tile start: 8 % of its time), the value-head dense lives in shared memory.
+// Arithmetic per tile is k_net_trunk_acc's, bit for bit (tests/test_gpu_net.py::test_acc_multi_context_equals_single).
+namespace acm {
+using namespace acl;
+constexpr int CTX_T = 256;
+constexpr int C_YH = 0, C_YL = 3 * Y_COPY, C_PLANES = 6 * Y_COPY, C_VALC = C_PLANES + 1376;
+constexpr int CTX_B = ((C_VALC + 512 + 127) / 128) * 128;                     // per-context shared memory: 51,840 B
+constexpr int NF = tcl::F_TOTAL - tcl::F_D1W, F_BYTES = ((NF * 4 + 15) / 16) * 16;
+constexpr int FO_D1W = 0, FO_D1B = 800, FO_VHW = 832, FO_VHB = 864;
+__host__ __device__ constexpr int s_wa(int nctx) { return nctx * CTX_B; }
+__host__ __device__ constexpr int s_wb(int nctx) { return s_wa(nctx) + B_A; }
+__host__ __device__ constexpr int s_wc(int nctx) { return s_wb(nctx) + B_B; }
+__host__ __device__ constexpr int s_ones(int nctx) { return s_wc(nctx) + B_C; }
+__host__ __device__ constexpr int s_f(int nctx) { return s_ones(nctx) + 128 * 16 * 2; }
+__host__ __device__ constexpr int s_total(int nctx) { return s_f(nctx) + F_BYTES; }
+__host__ __device__ constexpr int tmem_cols(int nctx) { return nctx * 160 <= 256 ? 256 : 512; }
+static_assert(s_total(3) <= 227 * 1024, "three contexts fit in one SM's shared memory");
+static_assert(CTX_B % 128 == 0 && B_A % 128 == 0 && B_B % 128 == 0 && B_C % 128 == 0 && C_YL % 128 == 0 && C_PLANES % 16 == 0, "alignment");
+}  // namespace acm
+
+template <int NCTX, bool SPLIT_A>
+__global__ void __launch_bounds__(NCTX * acm::CTX_T, 1)
+k_net_trunk_accm(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
+                 uint8_t *__restrict__ polc_h, uint8_t *__restrict__ polc_l, float *__restrict__ value)
+{
+    using namespace acm;
+    constexpr bool FP16 = true;
+    constexpr int S_WA = s_wa(NCTX), S_WB = s_wb(NCTX), S_WC = s_wc(NCTX), S_ONES = s_ones(NCTX), S_F = s_f(NCTX);
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar[NCTX], barW[3];            // per context: MMAs of a phase done; weight slots A, B, C landed
+    __shared__ unsigned slot_done[3];                  // contexts that have finished with a slot's current layer, cumulative
+    __shared__ uint32_t tmem_slot;
+    const int ctx = threadIdx.x >> 8;
+    const int t = threadIdx.x & 255, warp = t >> 5, lane = t & 31;
+    const int rg = warp & 3, h = warp >> 2;
+    const int r = rg * 32 + lane;
+    const int p_local = r / POS_ROWS, rem = r % POS_ROWS, cy = rem / 6, cx = rem % 6;
+    const bool live = r < LIVE_ROWS && cx < 5;
+    const int cell = cy * 5 + cx;
+    const uint32_t sbase = umma::smem_u32(smem);
+    uint8_t *const sctx = smem + ctx * CTX_B;
+    const float *sF = reinterpret_cast<const float *>(smem + S_F);
+    const int64_t n_tiles = (n + POS - 1) / POS;
+    const int64_t round_tiles = (int64_t)gridDim.x * NCTX;
+    const bool planes_aligned = (reinterpret_cast<uintptr_t>(planes) & 3) == 0;
+    auto tile_of = [&](int64_t round, int c) { return round * round_tiles + (int64_t)c * gridDim.x + blockIdx.x; };
+    // contexts of this CTA that have a tile in `round` (tile_of grows with the context index: they are contexts 0 .. count-1)
+    auto active_in = [&](int64_t round) {
+        unsigned a = 0;
+#pragma unroll
+        for (int c = 0; c < NCTX; c++) a += tile_of(round, c) < n_tiles ? 1u : 0u;
+        return a;
+    };
+
+    auto refill_slot = [&](int slot, int dst, const uint8_t *src, uint32_t bytes) {
+        umma::mbar_expect_tx(&barW[slot], bytes);
+        umma::bulk_g2s(sbase + dst, src, bytes, &barW[slot]);
+    };
+    // words t and 256 + t (< 343) of a tile's input planes; bytes past the last position read as zero
+    auto load_planes = [&](int64_t tile, uint32_t (&w)[2]) {
+        w[0] = 0u; w[1] = 0u;
+        if (tile >= n_tiles) return;
+        const int bytes = (int)min((int64_t)POS, n - tile * POS) * 343;
+        const uint8_t *src = planes + tile * (POS * 343);
+        if (bytes == POS * 343 && planes_aligned) {
+            w[0] = __ldg(reinterpret_cast<const uint32_t *>(src) + t);
+            if (t < 343 - CTX_T) w[1] = __ldg(reinterpret_cast<const uint32_t *>(src) + CTX_T + t);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                for (int k = 0; k < 4; k++) {
+                    const int byte = (q * CTX_T + t) * 4 + k;
+                    if (byte < bytes) w[q] |= (uint32_t)__ldg(src + byte) << (8 * k);
+                }
+        }
+    };
+    auto store_planes = [&](const uint32_t (&w)[2]) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int idx = q * CTX_T + t;
+            if (idx < 344) reinterpret_cast<uint32_t *>(sctx + C_PLANES)[idx] = w[q];
+        }
+    };
+
+    for (int i = threadIdx.x; i < NCTX * CTX_B / 16; i += NCTX * CTX_T) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);   // guard rows of every copy set
+    for (int i = threadIdx.x; i < NF; i += NCTX * CTX_T) reinterpret_cast<float *>(smem + S_F)[i] = __ldg(fb + tcl::F_D1W + i);
+    for (int i = threadIdx.x; i < 128 * 2; i += NCTX * CTX_T) {
+        const int rr = i >> 1, chunk = i & 1;
+        *reinterpret_cast<uint4 *>(smem + S_ONES + umma::op_offset(rr, chunk * 8, 16)) = make_uint4(chunk == 0 ? pack2<FP16>(1.f, 1.f) : 0u, 0u, 0u, 0u);
+    }
+    __syncthreads();                                   // the zero fill above covers the plane staging areas written next
+    {
+        uint32_t w0[2];
+        load_planes(tile_of(0, ctx), w0);
+        store_planes(w0);
+    }
+    if (threadIdx.x == 0) {
+        slot_done[0] = 0u; slot_done[1] = 0u; slot_done[2] = 0u;
+#pragma unroll
+        for (int q = 0; q < NCTX; q++) umma::mbar_init(&bar[q], 1);
+#pragma unroll
+        for (int q = 0; q < 3; q++) umma::mbar_init(&barW[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        refill_slot(1, S_WB, wb + W_CONV1, B_CONV1);                     // slot B: conv1 first, conv B of block 0 right after it
+        refill_slot(0, S_WA, wb + W_BLOCK0 + W_BA, B_A);
+        refill_slot(2, S_WC, wb + W_BLOCK0 + W_BC, B_C);
+    }
+    if (threadIdx.x < 32) umma::tmem_alloc(&tmem_slot, tmem_cols(NCTX));
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    uint32_t phW0 = 0, phW1 = 0, phW2 = 0;             // parities of the weight-slot barriers (tracked by each context's issuing lane)
+    unsigned due0 = 0, due1 = 0, due2 = 0;             // cumulative count at which a slot's current layer has been consumed by everyone
+    // TMEM columns, region-major over the contexts: X [ctx*64, +64) | XH|XL = conv B accumulator [NCTX*64 + ctx*64, +64) | AO [NCTX*128 + ctx*32, +32)
+    const uint32_t tmem = tmem_slot;
+    const uint32_t T_Xc = (uint32_t)(ctx * 64), T_XHc = (uint32_t)(NCTX * 64 + ctx * 64), T_XLc = T_XHc + 32u, T_BOc = T_XHc;
+    const uint32_t T_AOc = (uint32_t)(NCTX * 128 + ctx * 32), T_CHc = T_AOc, T_CLc = T_AOc + 16u;
+    const uint32_t trow = tmem + ((uint32_t)(rg * 32) << 16);
+    uint32_t phase = 0;
+    const umma::DescBase dYH = umma::desc_base(sbase + ctx * CTX_B + C_YH, Y_LBO, 128u), dYL = umma::desc_base(sbase + ctx * CTX_B + C_YL, Y_LBO, 128u);
+    const umma::DescBase dC1H = umma::desc_base(sbase + S_WB, 128u, 80 / 8 * 128u), dC1L = umma::desc_base(sbase + S_WB + hi_b(64, 64), 128u, 64 / 8 * 128u);
+    const umma::DescBase dAH = umma::desc_base(sbase + S_WA, 128u, 80 / 8 * 128u), dAL = umma::desc_base(sbase + S_WA + hi_b(32, 64), 128u, 64 / 8 * 128u);
+    const umma::DescBase dBH = umma::desc_base(sbase + S_WB, 128u, 304 / 8 * 128u);          // rows 0-31 hi, rows 32-63 lo
+    const umma::DescBase dCH = umma::desc_base(sbase + S_WC, 128u, 48 / 8 * 128u), dCL = umma::desc_base(sbase + S_WC + hi_b(64, 32), 128u, 32 / 8 * 128u);
+    const umma::DescBase dONES = umma::desc_base(sbase + S_ONES, 128u, 16 / 8 * 128u);
+    constexpr uint32_t ID32 = umma::make_idesc(32, FP16), ID64 = umma::make_idesc(64, FP16);
+
+    auto ctx_barrier = [&]() { asm volatile("bar.sync %0, 256;" :: "r"(1 + ctx) : "memory"); };        // this context's 8 warps only
+    auto tmem_sync = [&]() { umma::tmem_wait_st(); umma::fence_before_sync(); ctx_barrier(); };
+    auto smem_sync = [&]() { umma::fence_async_smem(); umma::fence_before_sync(); ctx_barrier(); };
+    auto wait_mma = [&]() { umma::mbar_wait(&bar[ctx], phase); phase ^= 1; umma::fence_after_sync(); };
+    auto bias_mma = [&](uint32_t tmem_d, umma::DescBase w, int K, uint32_t idesc, bool accumulate) {
+        umma::mma_bf16(tmem_d, umma::desc_at(dONES, 0u), umma::desc_at(w, (uint32_t)(K / 8) * 128u), idesc, accumulate);
+    };
+    // this context's MMAs of the slot's current layer are complete: count it off; the last one streams the next layer in
+    auto slot_release = [&](int slot, unsigned &due, unsigned nact, int dst, const uint8_t *src, uint32_t bytes, bool wanted) {
+        due += nact;
+        if (warp == 0 && umma::elect_one()) {
+            if (atomicAdd(&slot_done[slot], 1u) + 1u == due && wanted) refill_slot(slot, dst, src, bytes);
+        }
+    };
+    // this thread's 32 residual columns: ReLU in place in TMEM X (fp32) and the split 16-bit copies XH / XL
+    auto finish_x = [&]() {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            float v[16];
+            umma::tmem_ld16(trow + T_Xc + h * 32 + half * 16, v);
+            uint32_t f[16], ph[8], pl[8];
+#pragma unroll
+            for (int j = 0; j < 16; j++) { v[j] = fmaxf(v[j], 0.f); f[j] = __float_as_uint(v[j]); }
+#pragma unroll
+            for (int j = 0; j < 8; j++) split2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+            umma::tmem_st16(trow + T_Xc + h * 32 + half * 16, f);
+            umma::tmem_st8(trow + T_XHc + h * 16 + half * 8, ph);
+            umma::tmem_st8(trow + T_XLc + h * 16 + half * 8, pl);
+        }
+    };
+
+#ifdef CCX_ACC_TIMING
+    long long ts[128]; int nts = 0;
+#define ACC_TS() do { if (threadIdx.x == 0 && blockIdx.x == 0 && nts < 128) ts[nts++] = clock64(); } while (0)
+#else
+#define ACC_TS() do { } while (0)
+#endif
+    for (int64_t round = 0; tile_of(round, ctx) < n_tiles; round++) {
+#ifdef CCX_ACC_TIMING
+        nts = 0;
+        ACC_TS();
+#endif
+        const int64_t tile = tile_of(round, ctx);
+        const int64_t pos0 = tile * POS;
+        const int n_pos = (int)min((int64_t)POS, n - pos0);
+        const unsigned nact = active_in(round);
+        const bool more = tile_of(round + 1, 0) < n_tiles;             // somebody in this CTA works in the next round
+        uint32_t pw[2];
+        load_planes(tile_of(round + 1, ctx), pw);                      // lands while this tile computes
+        // conv1 operand: the uint8 plane values are exact in half precision, so only the weights are split (a_lo = 0)
+        {
+            const uint8_t *pl = sctx + C_PLANES + (live ? p_local * 343 : 0);
+#pragma unroll
+            for (int c8 = 0; c8 < 2; c8++) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    float v2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int kk = h * 32 + c8 * 16 + q * 2 + e;
+                        const int tap = kk / 7, ch = kk % 7, dy = tap / 3, dx = tap % 3;
+                        v2[e] = (live && kk < 63) ? (float)pl[((cy + dy) * 7 + (cx + dx)) * 7 + ch] : 0.f;
+                    }
+                    pk[q] = pack2<FP16>(v2[0], v2[1]);
+                }
+                umma::tmem_st8(trow + T_XHc + h * 16 + c8 * 8, pk);
+            }
+        }
+        tmem_sync(); ACC_TS();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
+                bias_mma(tmem + T_Xc, dC1H, 64, ID64, false);
+                umma::gemm_issue_ts<64>(tmem + T_Xc, tmem + T_XHc, dC1H, 0, ID64, true);
+                umma::gemm_issue_ts<64>(tmem + T_Xc, tmem + T_XHc, dC1L, 0, ID64, true);
+                umma::commit(&bar[ctx]);
+            }
+            __syncwarp();
+        }
+        wait_mma(); ACC_TS();
+        slot_release(1, due1, nact, S_WB, wb + W_BLOCK0 + W_BB, B_B, true);              // conv B of block 0
+        finish_x();
+        for (int b = 0; b < 9; b++) {
+            const uint8_t *wnext = wb + W_BLOCK0 + ((b + 1) % 9) * W_BLOCK;
+            // A: 1x1 conv 64 -> 32
+            tmem_sync(); ACC_TS();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[0], phW0); phW0 ^= 1;
+                    bias_mma(tmem + T_AOc, dAH, 64, ID32, false);
+                    umma::gemm_issue_ts<64>(tmem + T_AOc, tmem + T_XHc, dAH, 0, ID32, true);
+                    umma::gemm_issue_ts<64>(tmem + T_AOc, tmem + T_XLc, dAH, 0, ID32, true);
+                    umma::gemm_issue_ts<64>(tmem + T_AOc, tmem + T_XHc, dAL, 0, ID32, true);
+                    umma::commit(&bar[ctx]);
+                }
+                __syncwarp();
+            }
+            wait_mma(); ACC_TS();
+            slot_release(0, due0, nact, S_WA, b < 8 ? wnext + W_BA : wb + W_HEADS, B_A, true);
+            {
+                float v[16];
+                umma::tmem_ld16(trow + T_AOc + h * 16, v);
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q], 0.f), fmaxf(v[2 * q + 1], 0.f), ph[q], pl[q]);
+                // B: 3x3 conv 32 -> 32: (hi, hi) + (lo, hi) + (hi, lo) over the nine row-shifted taps; the N = 64 accumulator
+                // takes the place of XH | XL, which conv A has consumed.  SPLIT_A: the copy of kernel row dy = -1 is written
+                // first and its three taps' MMAs are in flight while the other two copies are written (same MMA order).
+                auto store_copy = [&](int d) {
+                    const int oy = cy - (d - 1);
+                    if (live && oy >= 0 && oy <= 4) {
+                        const int off = d * Y_COPY + (2 * h) * Y_LBO + (1 + r - 6 * (d - 1)) * 16;
+                        *reinterpret_cast<uint4 *>(sctx + C_YH + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4 *>(sctx + C_YH + off + Y_LBO) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                        *reinterpret_cast<uint4 *>(sctx + C_YL + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        *reinterpret_cast<uint4 *>(sctx + C_YL + off + Y_LBO) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                    }
+                };
+                auto issue_taps = [&](int d0, int d1) {
+#pragma unroll
+                    for (int d = d0; d < d1; d++)
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; dxi++)
+#pragma unroll
+                            for (int ks = 0; ks < 2; ks++) {
+                                const uint32_t ao = (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO), wo = (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128);
+                                umma::mma_bf16(tmem + T_BOc, umma::desc_at(dYH, ao), umma::desc_at(dBH, wo), ID64, true);
+                                umma::mma_bf16(tmem + T_BOc, umma::desc_at(dYL, ao), umma::desc_at(dBH, wo), ID32, true);
+                            }
+                };
+                store_copy(0);
+                if (SPLIT_A) {
+                    smem_sync(); ACC_TS();
+                    if (warp == 0) {
+                        umma::fence_after_sync();
+                        if (umma::elect_one()) {
+                            umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
+                            bias_mma(tmem + T_BOc, dBH, 288, ID64, false);
+                            issue_taps(0, 1);
+                        }
+                        __syncwarp();
+                    }
+                }
+                store_copy(1);
+                store_copy(2);
+                smem_sync(); ACC_TS();
+                if (warp == 0) {
+                    umma::fence_after_sync();
+                    if (umma::elect_one()) {
+                        if (!SPLIT_A) {
+                            umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
+                            bias_mma(tmem + T_BOc, dBH, 288, ID64, false);
+                            issue_taps(0, 1);
+                        }
+                        issue_taps(1, 3);
+                        umma::commit(&bar[ctx]);
+                    }
+                    __syncwarp();
+                }
+            }
+            wait_mma(); ACC_TS();
+            if (b < 8) slot_release(1, due1, nact, S_WB, wnext + W_BB, B_B, true);
+            else slot_release(1, due1, nact, S_WB, wb + W_CONV1, B_CONV1, more);         // conv1 of the next round's tiles
+            {
+                float v[16], u[16];
+                umma::tmem_ld16(trow + T_BOc + h * 16, v);
+                umma::tmem_ld16(trow + T_BOc + 32 + h * 16, u);
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q] + u[2 * q], 0.f), fmaxf(v[2 * q + 1] + u[2 * q + 1], 0.f), ph[q], pl[q]);
+                umma::tmem_st8(trow + T_CHc + h * 8, ph);        // conv C's operand: 32 channels = 16 columns, hi and lo
+                umma::tmem_st8(trow + T_CLc + h * 8, pl);
+            }
+            // C: 1x1 conv 32 -> 64 accumulated onto the residual
+            tmem_sync(); ACC_TS();
+            if (warp == 0) {
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    umma::mbar_wait(&barW[2], phW2); phW2 ^= 1;
+                    bias_mma(tmem + T_Xc, dCH, 32, ID64, true);
+                    umma::gemm_issue_ts<32>(tmem + T_Xc, tmem + T_CHc, dCH, 0, ID64, true);
+                    umma::gemm_issue_ts<32>(tmem + T_Xc, tmem + T_CLc, dCH, 0, ID64, true);
+                    umma::gemm_issue_ts<32>(tmem + T_Xc, tmem + T_CHc, dCL, 0, ID64, true);
+                    umma::commit(&bar[ctx]);
+                }
+                __syncwarp();
+            }
+            wait_mma(); ACC_TS();
+            slot_release(2, due2, nact, S_WC, wnext + W_BC, B_C, b < 8 || more);
+            finish_x();
+        }
+        // heads
+        tmem_sync(); ACC_TS();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::mbar_wait(&barW[0], phW0); phW0 ^= 1;
+                bias_mma(tmem + T_AOc, dAH, 64, ID32, false);
+                umma::gemm_issue_ts<64>(tmem + T_AOc, tmem + T_XHc, dAH, 0, ID32, true);
+                umma::gemm_issue_ts<64>(tmem + T_AOc, tmem + T_XLc, dAH, 0, ID32, true);
+                umma::gemm_issue_ts<64>(tmem + T_AOc, tmem + T_XHc, dAL, 0, ID32, true);
+                umma::commit(&bar[ctx]);
+            }
+            __syncwarp();
+        }
+        wait_mma(); ACC_TS();
+        slot_release(0, due0, nact, S_WA, wb + W_BLOCK0 + W_BA, B_A, more);
+        {
+            float v[16];
+            umma::tmem_ld16(trow + T_AOc + h * 16, v);
+            if (live && p_local < n_pos) {
+                if (h == 0) {
+                    // Flatten in (y, x, c) order = K index cell * 16 + c, written as hi / lo halves straight in the accurate policy
+                    // dense kernel's A-operand layout (128-position tiles of four K-chunks)
+                    uint32_t ph[8], pl[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) split2(fmaxf(v[2 * q], 0.f), fmaxf(v[2 * q + 1], 0.f), ph[q], pl[q]);
+                    const int64_t pos = pos0 + p_local;
+#pragma unroll
+                    for (int part = 0; part < 2; part++) {               // the cell's channels 0-7 and 8-15 may fall into different chunks
+                        const int k = cell * 16 + part * 8;
+                        const int c = k >= 304 ? 3 : k >= 208 ? 2 : k >= 112 ? 1 : 0;
+                        const int64_t off = (pos >> 7) * PD_TILE_B + pd_a_off(c) + umma::op_offset((int)(pos & 127), k - pd_k0(c), pd_kc(c));
+                        *reinterpret_cast<uint4 *>(polc_h + off) = make_uint4(ph[4 * part], ph[4 * part + 1], ph[4 * part + 2], ph[4 * part + 3]);
+                        *reinterpret_cast<uint4 *>(polc_l + off) = make_uint4(pl[4 * part], pl[4 * part + 1], pl[4 * part + 2], pl[4 * part + 3]);
+                    }
+                } else {
+                    reinterpret_cast<float *>(sctx + C_VALC)[p_local * 25 + cell] = fmaxf(v[0], 0.f);
+                }
+            }
+        }
+        store_planes(pw);
+        umma::fence_before_sync();
+        ctx_barrier();
+        if (warp < n_pos) {                                // value head: dense_1 25 -> 32 ReLU, value_head 32 -> 1 tanh, fp32
+            const float *valc = reinterpret_cast<const float *>(sctx + C_VALC) + warp * 25;
+            float acc = sF[FO_D1B + lane];
+            for (int k = 0; k < 25; k++) acc = fmaf(valc[k], sF[FO_D1W + k * 32 + lane], acc);
+            float sv = fmaxf(acc, 0.f) * sF[FO_VHW + lane];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, off);
+            if (lane == 0) value[pos0 + warp] = tanhf(sv + sF[FO_VHB]);
+        }
+        ctx_barrier();                                     // the value staging is rewritten by the next tile's heads epilogue
+#ifdef CCX_ACC_TIMING
+        ACC_TS();
+        if (threadIdx.x == 0 && blockIdx.x == 0 && (round == 0 || round == 5)) {
+            printf("ACCT round %d:", (int)round);
+            for (int i = 1; i < nts; i++) printf(" %d", (int)(ts[i] - ts[i - 1]));
+            printf("\n");
+        }
+#endif
+    }
+    // every refill that was issued had a consumer that waited for it, so nothing is in flight when the contexts meet here
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_free(tmem, tmem_cols(NCTX));
+}
+
 // Accurate policy dense: logits = flat(policy conv)[B x 400] * W + b in split precision, 128 positions x 80 outputs per CTA.
 // Four K-chunks (112, 96, 96, 96) stream through two shared-memory stages, each holding the chunk's hi and lo halves of the
 // activations (written in this layout by k_net_trunk_acc) and of the quarter's weight rows; per chunk the issuing lane fires
@@ -1194,7 +1598,19 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
     CCX_CUDA(h, cudaMemcpyAsync(a.wb, blob_host, acl::W_TOTAL, cudaMemcpyHostToDevice, h->stream));
     CCX_CUDA(h, cudaStreamSynchronize(h->stream));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, acl::S_TOTAL));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(1)));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(2)));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(3)));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(3)));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, pda::S_TOTAL));
+    return CCX_OK;
+}
+
+int ccx_net_set_acc_contexts(ccx_handle *h, int32_t contexts)
+{
+    if (!h || contexts < 0 || contexts > 3) return CCX_ERR_ARG;
+    if (h->acc_ctx != contexts) h->epoch++;          // a cached round graph holds the old kernel
+    h->acc_ctx = contexts;
     return CCX_OK;
 }
 
@@ -1231,8 +1647,23 @@ int ccx_net_forward_acc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int6
     const size_t off = (size_t)(row0 / 128) * acl::PD_TILE_B;
     uint8_t *polc_h = a.polc + off, *polc_l = a.polc + (size_t)((a.cap + 127) / 128) * acl::PD_TILE_B + off;
     int64_t tiles = (n + acl::POS - 1) / acl::POS;
-    unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);       // two resident CTAs per SM
-    k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+    if (h->acc_ctx < 0) {          // CCX_ACC_CTX: see ccx_net_set_acc_contexts
+        const char *e = getenv("CCX_ACC_CTX");
+        const int v = e ? atoi(e) : 3;
+        h->acc_ctx = v < 0 || v > 3 ? 3 : v;
+    }
+    const int acc_ctx = h->acc_ctx;
+    if (acc_ctx == 0) {
+        unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);       // two resident CTAs per SM
+        k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+    } else {
+        unsigned grid = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);               // one CTA per SM, acc_ctx tiles in flight in each
+        static const bool split_a = [] { const char *e = getenv("CCX_ACC_SPLIT"); return e ? atoi(e) != 0 : true; }();   // A/B: 0 = conv A's epilogue in one piece
+        if (acc_ctx == 1) k_net_trunk_accm<1, false><<<grid, acm::CTX_T, acm::s_total(1), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+        else if (acc_ctx == 2) k_net_trunk_accm<2, false><<<grid, 2 * acm::CTX_T, acm::s_total(2), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+        else if (split_a) k_net_trunk_accm<3, true><<<grid, 3 * acm::CTX_T, acm::s_total(3), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+        else k_net_trunk_accm<3, false><<<grid, 3 * acm::CTX_T, acm::s_total(3), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+    }
     CCX_LAUNCHED(h);
     k_policy_dense_acc<<<dim3((unsigned)((n + 127) / 128), 4), 128, pda::S_TOTAL, stream>>>(a.wb, b_pold, polc_h, polc_l, n, logits);
     CCX_LAUNCHED(h);

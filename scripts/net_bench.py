@@ -8,6 +8,7 @@ m = ResidualCNN(engine=Engine(0)).load_weights(os.path.join(ROOT, 'tests', 'gold
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 kernel = sys.argv[2] if len(sys.argv) > 2 else 'tc'
 m.set_kernel(kernel)
+if len(sys.argv) > 3: m.eng.call('ccx_net_set_acc_contexts', int(sys.argv[3]))      # accurate trunk: tiles in flight per CTA (0 = one tile per CTA)
 for n in (4096, 65536):
     x = torch.randint(0, 7, (n, 7, 7, 7), dtype=torch.uint8, device='cuda')
     for _ in range(3): m.forward(x)
@@ -17,4 +18,4 @@ for n in (4096, 65536):
     for _ in range(reps): m.forward(x)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
-    print(kernel + ' forward %d positions: %.4f ms -> %.4g positions/s, %.1f TFLOP/s' % (n, ms, n / ms * 1e3, 6.483264e6 * n / ms / 1e9))
+    print(kernel + (' ctx' + sys.argv[3] if len(sys.argv) > 3 else '') + ' forward %d positions: %.4f ms -> %.4g positions/s, %.1f TFLOP/s' % (n, ms, n / ms * 1e3, 6.483264e6 * n / ms / 1e9))

@@ -175,6 +175,27 @@ def test_accurate_tensor_core_mode_meets_the_1e3_bar(model, gold):
     model.set_kernel("tc")
 
 
+@pytest.mark.parametrize("n", [1, 4, 5, 130, 592, 1777, 4096, 7001])
+def test_acc_multi_context_equals_single(model, n):
+    """k_net_trunk_accm<1..3> (one CTA per SM, 1-3 tiles in flight sharing the weight slots) computes k_net_trunk_acc's bits:
+    batches that leave contexts without a tile, fill exactly one round, and run several rounds with a partial last one"""
+    g = torch.Generator().manual_seed(n)
+    planes = torch.randint(0, 4, (n, 7, 7, 7), dtype=torch.uint8, generator=g).cuda()
+    model.set_kernel("tc_acc")
+    try:
+        model.eng.call("ccx_net_set_acc_contexts", 0)
+        l0, v0 = model.forward(planes)
+        l0, v0 = l0.clone(), v0.clone()
+        for ctx in (1, 2, 3):
+            model.eng.call("ccx_net_set_acc_contexts", ctx)
+            for _ in range(2):                                   # twice: the second launch finds the slots' barriers re-initialised
+                l, v = model.forward(planes)
+                assert torch.equal(l, l0) and torch.equal(v, v0), "contexts=%d differs" % ctx
+    finally:
+        model.eng.call("ccx_net_set_acc_contexts", 3)
+        model.set_kernel("tc")
+
+
 def test_accurate_mode_in_the_fused_mcts_rounds(model):
     """ccx_mcts_run_net with the accurate net = the select / ccx_net_eval / expand_backup round trips in the same mode"""
     from chinesecheckersagent_b200.engine import BatchedMCTS
