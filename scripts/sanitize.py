@@ -25,6 +25,11 @@ m = ResidualCNN(engine=eng).load_weights(os.path.join(ROOT, 'tests', 'golden', '
 for n in (3, 130):
     x = torch.randint(0, 7, (n, 7, 7, 7), dtype=torch.uint8, device='cuda')
     m.set_kernel('tc'); m.forward(x); m.set_kernel('tc_acc'); m.forward(x); m.set_kernel('simt'); m.forward(x)
+m.set_kernel('tc_acc')
+for ctx in (0, 1, 2, 3):                                          # accurate trunk: one tile per CTA, and 1-3 contexts sharing the weight slots
+    m.eng.call('ccx_net_set_acc_contexts', ctx)
+    for n in (5, 700, 1900):                                      # one context with a tile / a partial last round / several rounds
+        m.forward(torch.randint(0, 7, (n, 7, 7, 7), dtype=torch.uint8, device='cuda'))
 m.set_kernel('tc')
 BatchedMCTS(eng, num_itr=6).search_net(env.state[:, :70].contiguous())
 g9 = BatchedMCTS(eng, num_itr=9); r9 = env.state[:, :70].contiguous()
