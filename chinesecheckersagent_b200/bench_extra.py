@@ -229,6 +229,6 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
             if kern in ("tc", "tc_acc") and peak_tflops:
                 out["net_forward_" + kern]["roofline"] = {"bound": "tensor", "achieved": tf / world, "peak": peak_tflops, "unit": "TFLOP/s",
                                                           "frac": tf / world / peak_tflops,
-                                                          "kernel": "k_net_trunk_tc4 + k_policy_dense_tc3" if kern == "tc" else "k_net_trunk_acc + k_policy_dense_acc (useful flops; 3 MMAs per product)"}
+                                                          "kernel": "k_net_trunk_tc4 + k_policy_dense_tc3" if kern == "tc" else "k_net_trunk_accm<3> + k_policy_dense_acc (useful flops; 3 MMAs per product are issued)"}
         model.set_kernel("tc_acc")
     return out
