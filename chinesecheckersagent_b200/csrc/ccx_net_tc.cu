@@ -1601,6 +1601,8 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(1)));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(2)));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(3)));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(1)));
+    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(2)));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(3)));
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, pda::S_TOTAL));
     return CCX_OK;
@@ -1608,7 +1610,7 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
 
 int ccx_net_set_acc_contexts(ccx_handle *h, int32_t contexts)
 {
-    if (!h || contexts < 0 || contexts > 3) return CCX_ERR_ARG;
+    if (!h || contexts < -1 || contexts > 3) return CCX_ERR_ARG;
     if (h->acc_ctx != contexts) h->epoch++;          // a cached round graph holds the old kernel
     h->acc_ctx = contexts;
     return CCX_OK;
@@ -1647,22 +1649,26 @@ int ccx_net_forward_acc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int6
     const size_t off = (size_t)(row0 / 128) * acl::PD_TILE_B;
     uint8_t *polc_h = a.polc + off, *polc_l = a.polc + (size_t)((a.cap + 127) / 128) * acl::PD_TILE_B + off;
     int64_t tiles = (n + acl::POS - 1) / acl::POS;
-    if (h->acc_ctx < 0) {          // CCX_ACC_CTX: see ccx_net_set_acc_contexts
-        const char *e = getenv("CCX_ACC_CTX");
-        const int v = e ? atoi(e) : 3;
-        h->acc_ctx = v < 0 || v > 3 ? 3 : v;
+    int acc_ctx = h->acc_ctx;      // -1 = automatic: CCX_ACC_CTX if set, else as many contexts (<= 3) as the batch can keep busy
+    bool automatic = false;
+    if (acc_ctx < 0) {
+        static const int env_ctx = [] { const char *e = getenv("CCX_ACC_CTX"); const int v = e ? atoi(e) : -1; return v < 0 || v > 3 ? -1 : v; }();
+        acc_ctx = env_ctx < 0 ? 3 : env_ctx;
+        automatic = env_ctx < 0;
     }
-    const int acc_ctx = h->acc_ctx;
     if (acc_ctx == 0) {
         unsigned grid = (unsigned)(tiles < 2 * h->num_sms ? tiles : 2 * h->num_sms);       // two resident CTAs per SM
         k_net_trunk_acc<<<grid, acl::THREADS, acl::S_TOTAL, stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
     } else {
         unsigned grid = (unsigned)(tiles < h->num_sms ? tiles : h->num_sms);               // one CTA per SM, acc_ctx tiles in flight in each
         static const bool split_a = [] { const char *e = getenv("CCX_ACC_SPLIT"); return e ? atoi(e) != 0 : true; }();   // A/B: 0 = conv A's epilogue in one piece
-        if (acc_ctx == 1) k_net_trunk_accm<1, false><<<grid, acm::CTX_T, acm::s_total(1), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
-        else if (acc_ctx == 2) k_net_trunk_accm<2, false><<<grid, 2 * acm::CTX_T, acm::s_total(2), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
-        else if (split_a) k_net_trunk_accm<3, true><<<grid, 3 * acm::CTX_T, acm::s_total(3), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
-        else k_net_trunk_accm<3, false><<<grid, 3 * acm::CTX_T, acm::s_total(3), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value);
+        // a batch that leaves the higher contexts without a tile runs the smaller instantiation (shorter prologue, no register cap)
+        const int nctx = !automatic ? acc_ctx : tiles <= h->num_sms ? 1 : tiles <= 2 * (int64_t)h->num_sms ? 2 : 3;
+#define CCX_ACCM_LAUNCH(N, S) k_net_trunk_accm<N, S><<<grid, N * acm::CTX_T, acm::s_total(N), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value)
+        if (nctx == 1) { if (split_a) CCX_ACCM_LAUNCH(1, true); else CCX_ACCM_LAUNCH(1, false); }
+        else if (nctx == 2) { if (split_a) CCX_ACCM_LAUNCH(2, true); else CCX_ACCM_LAUNCH(2, false); }
+        else { if (split_a) CCX_ACCM_LAUNCH(3, true); else CCX_ACCM_LAUNCH(3, false); }
+#undef CCX_ACCM_LAUNCH
     }
     CCX_LAUNCHED(h);
     k_policy_dense_acc<<<dim3((unsigned)((n + 127) / 128), 4), 128, pda::S_TOTAL, stream>>>(a.wb, b_pold, polc_h, polc_l, n, logits);

@@ -212,8 +212,9 @@ int ccx_net_forward_u8(ccx_handle *h, int64_t n, const uint8_t *planes, float *l
 int ccx_net_acc_blob_bytes(void);
 int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes);
 /* Tiles in flight per CTA of the accurate trunk kernel: 1-3 = k_net_trunk_accm (one CTA per SM, that many 256-thread contexts
- * sharing the streamed weight slots; default 3, or the environment variable CCX_ACC_CTX), 0 = k_net_trunk_acc (one tile per CTA, two
- * CTAs per SM).  Every setting computes the same bits (model.py:58-145 has no notion of it): it exists for A/B timing and tests. */
+ * sharing the streamed weight slots), 0 = k_net_trunk_acc (one tile per CTA, two CTAs per SM), -1 = automatic (the default: the
+ * environment variable CCX_ACC_CTX if set, else as many contexts, up to 3, as the batch has tiles per SM).  Every setting computes
+ * the same bits (model.py:58-145 has no notion of it): it exists for A/B timing and tests. */
 int ccx_net_set_acc_contexts(ccx_handle *h, int32_t contexts);
 
 /* ---- self-play (selfplay.py:11-133) and trajectory packing (utils.py:60-73) -------------------------

@@ -1,5 +1,6 @@
 set -x
 mkdir -p gpurun_out
-export CCX_LIB_PATH=$PWD/chinesecheckersagent_b200/libccx_timing.so
-( python scripts/acc_timing.py 1 4; python scripts/acc_timing.py 1 65536; python scripts/acc_timing.py 3 65536 ) > gpurun_out/acc_timing.log 2>&1
-tail -3 gpurun_out/acc_timing.log | cut -c1-300
+timeout 600 python -m pytest tests/test_gpu_net.py -m gpu -q -x > gpurun_out/pytest_part.log 2>&1; tail -3 gpurun_out/pytest_part.log
+python scripts/dropin_bench.py; CCX_ACC_CTX=3 python scripts/dropin_bench.py; CCX_ACC_CTX=0 python scripts/dropin_bench.py
+for n in 1; do python scripts/net_bench.py 20 tc_acc; done
+python scripts/fullplay_bench.py | tail -2

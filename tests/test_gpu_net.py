@@ -192,7 +192,9 @@ def test_acc_multi_context_equals_single(model, n):
                 l, v = model.forward(planes)
                 assert torch.equal(l, l0) and torch.equal(v, v0), "contexts=%d differs" % ctx
     finally:
-        model.eng.call("ccx_net_set_acc_contexts", 3)
+        model.eng.call("ccx_net_set_acc_contexts", -1)
+        l, v = model.forward(planes)                             # automatic choice
+        assert torch.equal(l, l0) and torch.equal(v, v0)
         model.set_kernel("tc")
 
 
