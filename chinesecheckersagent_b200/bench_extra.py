@@ -121,6 +121,9 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
                                    tie_rule="reference (uniform among epsilon-ties, MCTS.py:65-72)")
         out["selfplay_net_first_max_ties"] = dict(ply_rate("tc_acc", MCTS_TREES, random_ties=False), net="tc_acc", tie_rule="first maximal edge (parity mode)")
         out["selfplay_net_16k_slots"] = dict(ply_rate("tc_acc", 4 * MCTS_TREES), net="tc_acc")
+        out["selfplay_net_64k_slots"] = dict(ply_rate("tc_acc", 16 * MCTS_TREES), net="tc_acc",
+                                             note="saturated rate: the trunk's partial last round and the tree kernel's straggler tail are amortised (25 GB of trees)")
+        torch.cuda.empty_cache()
         out["selfplay_net_fp16_out_of_tolerance"] = dict(ply_rate("tc", MCTS_TREES), net="16-bit tcgen05 kernels: max |dp| 1.6e-2 on self-play positions, "
                                                                                          "MISSES the 1e-3 bar; throughput mode only")
         out["selfplay_net_fp16_out_of_tolerance_16k_slots"] = dict(ply_rate("tc", 4 * MCTS_TREES), net="16-bit, out of tolerance")

@@ -901,8 +901,11 @@ static int run_net_rounds(ccx_handle *h, int64_t n, int32_t rounds, double cpuct
     // low-occupancy stretches of one half (the tail of its tree kernel = the deepest trees, the last tile of its trunk kernel)
     // are filled by the other half's kernels.  Same trees as the single-stream order, bit for bit.
     static const bool no_split = getenv("CCX_NO_SPLIT") != nullptr;
-    static const int64_t split_min = getenv("CCX_SPLIT_MIN") ? atoll(getenv("CCX_SPLIT_MIN")) : 8192;     // diagnostics: batch size from which the two-half pipeline is used
-    const bool split = !no_split && (h->net_mode == 1 || h->net_mode == 2) && n >= split_min;     // measured: 16,384 slots 65.1 -> 62.2 ms per ply; no gain at 4,096
+    // batch size from which the two-half pipeline is used: 8,192 in the 16-bit mode; 16,384 in the accurate mode, whose three-context
+    // trunk loses more on a halved batch (r02h, accurate mode: 8,192 slots 52.2 ms unsplit / 53.7 split, 16,384 slots 100.8 / 98.3)
+    static const int64_t split_env = getenv("CCX_SPLIT_MIN") ? atoll(getenv("CCX_SPLIT_MIN")) : -1;
+    const int64_t split_min = split_env >= 0 ? split_env : h->net_mode == 2 ? 16384 : 8192;
+    const bool split = !no_split && (h->net_mode == 1 || h->net_mode == 2) && n >= split_min;     // measured (16-bit mode): 16,384 slots 65.1 -> 62.2 ms per ply; no gain at 4,096
     int64_t part_n[2] = {split ? (n / 2) & ~(int64_t)127 : n, 0};          // halves start on a 128-position tile of the net's scratch
     part_n[1] = n - part_n[0];
     cudaStream_t streams[2] = {h->stream, h->stream};

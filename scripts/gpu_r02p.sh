@@ -1,6 +1,4 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_net.py -m gpu -q -x > gpurun_out/pytest_part.log 2>&1; tail -3 gpurun_out/pytest_part.log
-python scripts/dropin_bench.py; CCX_ACC_CTX=3 python scripts/dropin_bench.py; CCX_ACC_CTX=0 python scripts/dropin_bench.py
-for n in 1; do python scripts/net_bench.py 20 tc_acc; done
-python scripts/fullplay_bench.py | tail -2
+timeout 600 python -m pytest tests/test_gpu_net.py -m gpu -q -x -k "split" > gpurun_out/pytest_part.log 2>&1; tail -3 gpurun_out/pytest_part.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 200 gpurun_out/bench.json; tail -3 gpurun_out/bench.err

@@ -136,12 +136,12 @@ def test_fused_round_loop_equals_round_trips(model, kernel, pre_expand):
 
 @pytest.mark.parametrize("kernel", ["tc", "tc_acc"])
 def test_fused_round_loop_two_stream_split_is_bit_identical(model, kernel):
-    """>= 8,192 trees: ccx_mcts_run_net runs the two halves of the batch as two pipelines on two streams (ragged halves here);
+    """>= 8,192 trees (16,384 in the accurate mode): ccx_mcts_run_net runs the two halves of the batch as two pipelines on two streams (ragged halves here);
     the trees must not depend on that (16-bit and accurate tensor-core modes; rounds 10 >= 8, so the third call also
     replays the two-branch CUDA graph)"""
     from chinesecheckersagent_b200.engine import BatchedMCTS
     model.set_kernel(kernel)
-    n = 8200 + 3
+    n = (16400 if kernel == "tc_acc" else 8200) + 3
     st, _, _ = orc.step_random(orc.start_states(n), 21, 0, 7, nthreads=8)
     roots = torch.from_numpy(np.ascontiguousarray(st).view(np.int64)).cuda()
     noise = torch.rand((n, 128), dtype=torch.float64, device="cuda")
