@@ -233,5 +233,26 @@ def run(eng, rank, world, barrier, peak_gbs=None, peak_tflops=None):
                 out["net_forward_" + kern]["roofline"] = {"bound": "tensor", "achieved": tf / world, "peak": peak_tflops, "unit": "TFLOP/s",
                                                           "frac": tf / world / peak_tflops,
                                                           "kernel": "k_net_trunk_tc4 + k_policy_dense_tc3" if kern == "tc" else "k_net_trunk_accm<3> + k_policy_dense_acc (useful flops; 3 MMAs per product are issued)"}
+        # net parity on the fixture positions (tests/golden/net_golden.npz: logits / v of the float64 restatement of model.py:58-145;
+        # Keras itself is not installable here): max |dp|, max |dv| and the move-agreement rate per kernel mode
+        gpath = os.path.join(os.path.dirname(weights), "net_golden.npz")
+        if os.path.exists(gpath):
+            import numpy as np
+            gold = np.load(gpath)
+
+            def softmax64(l):
+                e = np.exp(l.astype(np.float64) - l.astype(np.float64).max(1, keepdims=True))
+                return e / e.sum(1, keepdims=True)
+            p_ref = softmax64(gold["logits"])
+            gp = torch.from_numpy(gold["planes"]).to(eng.device)
+            par = {"positions": int(gp.shape[0]), "tolerance": 1e-3, "against": "float64 restatement of the Keras graph (parity unpinned: no Keras in the image)"}
+            for kern in ("simt", "tc", "tc_acc"):
+                model.set_kernel(kern)
+                l, v = model.forward(gp)
+                pk = softmax64(l.cpu().numpy())
+                par[kern] = {"max_abs_dp": float(np.abs(pk - p_ref).max()), "max_abs_dv": float(np.abs(v.cpu().numpy().reshape(-1) - gold["v"].reshape(-1)).max()),
+                             "move_agreement": float((pk.argmax(1) == p_ref.argmax(1)).mean())}
+                par[kern]["meets_1e-3"] = bool(par[kern]["max_abs_dp"] <= 1e-3 and par[kern]["max_abs_dv"] <= 1e-3)
+            out["net_parity"] = par
         model.set_kernel("tc_acc")
     return out

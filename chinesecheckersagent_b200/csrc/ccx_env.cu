@@ -715,6 +715,12 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
     if (w2) atomicAdd(&wins[1], (u64)w2);
 }
 
+// Tried and dropped (r02, second session): TWO queue slots per lane in k_step_random_wq<PRE> — the loop body expands one cell of each
+// slot in one straight-line block (an idle slot expands cell 0 of stale words, masked), so that the two dependent chains
+// (FLO -> LDS -> PRMT -> LDS -> shift -> mask) interleave.  Bit-identical, 91 registers, but 3.09 ms against 2.43 ms per 65,536 games x
+// 256 plies (profiles/r02h_env_variants.log): the dummy expansions of the drain and the second item-take / park blocks cost more
+// than the interleaving hides — the same outcome as two games per lane in the flat kernel (variants 2 / 3).
+
 __global__ void k_build_jump_table3(uint8_t *T3) { build_jump_table3(T3, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 
 __global__ void k_build_jump_table2(uint8_t *T2) { build_jump_table2(T2, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
