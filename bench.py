@@ -369,6 +369,17 @@ def main():
             line["roofline_issue"] = {"bound": "issue", "achieved": ach_i, "peak": peak_i, "unit": "warp-instr/s", "frac": ach_i / peak_i,
                                       "warp_insts_per_launch": winst, "sm_mhz": f_mhz, "kernel": STEP_KERNEL,
                                       "source": "smsp__inst_executed.sum of the ncu capture named in roofline.traffic_source; launch time measured live"}
+        # the unit this kernel keeps busiest: the shared-memory data pipe (the lanes' random reads of the jump tables; half of the
+        # wavefronts are bank conflicts) — wavefronts per second against one wavefront per SM and clock
+        wav = prof.get("k_step_random_flat_smem_wavefronts")
+        if wav and n == GAMES_PER_GPU:
+            f_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
+            ach_w = wav / (launch_ms * 1e-3)
+            peak_w = N_SMS * f_mhz * 1e6
+            line["roofline_smem"] = {"bound": "shared-memory data pipe", "achieved": ach_w, "peak": peak_w, "unit": "wavefronts/s", "frac": ach_w / peak_w,
+                                     "wavefronts_per_launch": wav, "bank_conflict_wavefronts_per_launch": prof.get("k_step_random_flat_smem_conflicts"),
+                                     "sm_mhz": f_mhz, "kernel": STEP_KERNEL,
+                                     "source": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum of the ncu capture named in roofline.traffic_source; launch time measured live"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
             if not args.no_extra:

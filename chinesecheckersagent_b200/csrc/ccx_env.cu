@@ -631,7 +631,7 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
 #pragma unroll
             for (int q = 0; q < 6; q++) {
                 const int cell = (int)((g.cells_me >> (8 * q)) & 0x3F);
-                const u64 oq = sO[cell];
+                const u64 oq = 1ULL << cell;      // a shift, not sO[cell]: the shared-memory data pipe is this kernel's busiest unit (78 %)
                 sG[0 * 192 + q * 32 + lane] = oq;
                 sG[1 * 192 + q * 32 + lane] = occ_all & ~oq;
                 sG[2 * 192 + q * 32 + lane] = occT_all & ~sOT[cell];
@@ -670,7 +670,7 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
             }
             if (state == 1) {
                 const int c = 63 - __clzll((long long)todo);
-                todo ^= sO[c];
+                todo ^= PRE ? 1ULL << c : sO[c];
                 const u64 nw = expand_cell_tri(c, occ, occT, occD, sT, sCI) & ~(reach | o);
                 reach |= nw;
                 todo |= nw;
@@ -720,6 +720,11 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
 // (FLO -> LDS -> PRMT -> LDS -> shift -> mask) interleave.  Bit-identical, 91 registers, but 3.09 ms against 2.43 ms per 65,536 games x
 // 256 plies (profiles/r02h_env_variants.log): the dummy expansions of the drain and the second item-take / park blocks cost more
 // than the interleaving hides — the same outcome as two games per lane in the flat kernel (variants 2 / 3).
+// Shared-memory traffic (ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared at 78 % of peak, half of the 548 M wavefronts are bank
+// conflicts of the lanes' random table reads) is what the queue loop saturates first.  Measured trades of loads against ALU work
+// (profiles/r02h_env_variants.log): one-bit masks by shift instead of sO[] in the PRE stage AND in the loop 2.435 -> 2.375 ms (kept;
+// either one alone: no change); a 32-bit per-cell table with computed row / column selectors: 2.404 ms;
+// skipping the lookups of lines without another checker (predicated loads): 2.52 ms — all bit-identical, the last three dropped.
 
 __global__ void k_build_jump_table3(uint8_t *T3) { build_jump_table3(T3, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 

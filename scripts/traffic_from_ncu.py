@@ -23,14 +23,18 @@ for rep in ("prof_step_random", "prof_mcts_search", "prof_net_acc", "prof_tree",
         dram = num("dram__bytes_read.sum") * scale("dram__bytes_read.sum") + num("dram__bytes_write.sum") * scale("dram__bytes_write.sum")
         out[name] = int(dram)
         out[name + "_warp_insts"] = int(num("smsp__inst_executed.sum"))
+        out[name + "_smem_wavefronts"] = int(num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"))
+        out[name + "_smem_conflicts"] = int(num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"))
         out[name + "_launch_us"] = num("gpu__time_duration.sum") * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit.get("gpu__time_duration.sum"), 1.0)
     used.append(rep + ".ncu-rep")
 # bench.py looks the step kernel up under this key whatever variant is the default
 for k in list(out):
-    if k.startswith("k_step_random") and not k.endswith(("_warp_insts", "_launch_us")):
+    if k.startswith("k_step_random") and not k.endswith(("_warp_insts", "_launch_us", "_smem_wavefronts", "_smem_conflicts")):
         out["k_step_random_flat"] = out[k]
         out["k_step_random_flat_warp_insts"] = out[k + "_warp_insts"]
+        out["k_step_random_flat_smem_wavefronts"] = out[k + "_smem_wavefronts"]
+        out["k_step_random_flat_smem_conflicts"] = out[k + "_smem_conflicts"]
         out["step_kernel"] = k
-out["source"] = "ncu --set full captures of the %s GPU pass (%s); per launch: dram__bytes_read.sum + dram__bytes_write.sum, smsp__inst_executed.sum" % (tag, ", ".join(used))
+out["source"] = "ncu --set full captures of the %s GPU pass (%s); per launch: dram__bytes_read.sum + dram__bytes_write.sum, smsp__inst_executed.sum, l1tex__data_pipe_lsu_wavefronts_mem_shared.sum" % (tag, ", ".join(used))
 json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
