@@ -724,7 +724,9 @@ k_step_random_wq(u64 *__restrict__ st, int64_t n, int64_t gid0, u32 k0, u32 k1, 
 // conflicts of the lanes' random table reads) is what the queue loop saturates first.  Measured trades of loads against ALU work
 // (profiles/r02h_env_variants.log): one-bit masks by shift instead of sO[] in the PRE stage AND in the loop 2.435 -> 2.375 ms (kept;
 // either one alone: no change); a 32-bit per-cell table with computed row / column selectors: 2.404 ms;
-// skipping the lookups of lines without another checker (predicated loads): 2.52 ms — all bit-identical, the last three dropped.
+// skipping the lookups of lines without another checker (predicated loads): 2.52 ms; BYTE answers for columns and diagonals (u8
+// tables compressed from the 64-bit ones at block start, LDS.U8 over 32 banks instead of LDS.64 over 16 bank pairs, the scatter a
+// 64-bit multiply + mask as in round 1): 2.537 ms — all bit-identical, all dropped: loads and ALU work are balanced where they are.
 
 __global__ void k_build_jump_table3(uint8_t *T3) { build_jump_table3(T3, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); }
 
