@@ -1566,9 +1566,20 @@ k_policy_dense_acc(const uint8_t *__restrict__ wb, const float *__restrict__ bia
     umma::fence_before_sync();
     __syncthreads();
     const int col_base = half * 160 + c0;
-    for (int i = t; i < 128 * NQ; i += 128) {
-        const int r = i / NQ, c = i % NQ, col = col_base + c;
-        if (row0 + r < n && col < CCX_NUM_ACTIONS) logits[(row0 + r) * CCX_NUM_ACTIONS + col] = stage[r * OUT_LD + c] + __ldg(bias + col);
+    // two logits per store: 294 and every column base are even, so a pair never straddles the end of a row and is 8-byte aligned
+    // whenever the caller's buffers are (the evaluator's own scratch always is)
+    if (((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(bias)) & 7) != 0) {
+        for (int i = t; i < 128 * NQ; i += 128) {
+            const int r = i / NQ, c = i % NQ, col = col_base + c;
+            if (row0 + r < n && col < CCX_NUM_ACTIONS) logits[(row0 + r) * CCX_NUM_ACTIONS + col] = stage[r * OUT_LD + c] + __ldg(bias + col);
+        }
+    } else
+    for (int i = t; i < 128 * (NQ / 2); i += 128) {
+        const int r = i / (NQ / 2), c = 2 * (i % (NQ / 2)), col = col_base + c;
+        if (row0 + r < n && col < CCX_NUM_ACTIONS) {
+            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(bias + col));
+            *reinterpret_cast<float2 *>(logits + (row0 + r) * CCX_NUM_ACTIONS + col) = make_float2(stage[r * OUT_LD + c] + b2.x, stage[r * OUT_LD + c + 1] + b2.y);
+        }
     }
     if (warp == 0) umma::tmem_free(tmem, 128);
 }
