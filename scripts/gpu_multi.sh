@@ -1,4 +1,4 @@
-# multi-GPU bench line: bash scripts/gpu_r02s.sh N   (run under gpurun --gpus N)
+# multi-GPU bench line: bash scripts/gpu_multi.sh N   (run under gpurun --gpus N)
 set -x
 N=${1:-8}
 mkdir -p gpurun_out
