@@ -161,6 +161,29 @@ def test_full_selfplay_with_real_net_at_size(eng):
     assert np.all((bx[..., 0] > 0).sum((1, 2)) == 6) and np.all((bx[..., 1] > 0).sum((1, 2)) == 6)
 
 
+def test_selfplay_records_do_not_depend_on_the_trunk_kernel(eng):
+    """the accurate trunk's kernel choice (one tile per CTA, or 1-3 contexts sharing the weight slots; automatic by default) is
+    invisible above the net: whole self-play runs (fused rounds, graph replay, restarts) deliver the same records bit for bit"""
+    from chinesecheckersagent_b200.model import ResidualCNN
+    from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
+    model = ResidualCNN(engine=eng).load_weights(os.path.join(GOLDEN, "good_model_weights.npz"))
+    model.set_kernel("tc_acc")
+    out = []
+    try:
+        for ctx in (0, 3, -1):
+            eng.call("ccx_net_set_acc_contexts", ctx)
+            sp = BatchedSelfPlay(eng, model.evaluate_states, n_slots=700, num_itr=10, max_iters=140, seed=99)    # 175 tiles: contexts without a tile
+            st = sp.run(iters=140)
+            traj = sp.collect()
+            out.append((st["plies"], st["records"], traj["board_x"].clone(), traj["pi_y"].clone(), traj["v_y"].clone(), sp.visits.clone()))
+    finally:
+        eng.call("ccx_net_set_acc_contexts", -1)
+    for o in out[1:]:
+        assert o[0] == out[0][0] and o[1] == out[0][1]
+        assert torch.equal(o[2], out[0][2]) and torch.equal(o[3], out[0][3]) and torch.equal(o[4], out[0][4]) and torch.equal(o[5], out[0][5])
+    assert out[0][1] > 1000
+
+
 def test_collect_consumes_its_records(eng):
     from chinesecheckersagent_b200.model import ResidualCNN
     from chinesecheckersagent_b200.selfplay import BatchedSelfPlay
