@@ -1089,33 +1089,46 @@ k_net_trunk_acc(const uint8_t *__restrict__ wb, const float *__restrict__ fb, co
 //    filling some CTAs' three contexts; contexts without a tile leave (the counts above use the round's active contexts).
 //  * the next tile's input planes are prefetched into registers while the current tile computes (k_net_trunk_acc staged them
 //    byte by byte at the tile start: 8 % of its time), the value-head dense lives in shared memory.
+//  * rows of a tile in board-row-major order (ROWMAJ, see namespace acm): the 3x3 conv reads ONE operand buffer through row-shifted
+//    descriptors instead of three copies; the conv A epilogue stores a third of the bytes (SPLIT_A then has nothing to split).
 // Arithmetic per tile is k_net_trunk_acc's, bit for bit (tests/test_gpu_net.py::test_acc_multi_context_equals_single).
 namespace acm {
 using namespace acl;
 constexpr int CTX_T = 256;
-constexpr int C_YH = 0, C_YL = 3 * Y_COPY, C_PLANES = 6 * Y_COPY, C_VALC = C_PLANES + 1376;
-constexpr int CTX_B = ((C_VALC + 512 + 127) / 128) * 128;                     // per-context shared memory: 51,840 B
+// Row order of a tile's 128 operand rows and the 3x3 conv's operand buffers, per ROWMAJ:
+//  false: position-major rows r = p*30 + y*6 + x and THREE row-shifted copies (one per kernel row dy, rows that would leak into the
+//         neighbouring position dropped) of the hi and of the lo half — k_net_trunk_acc's layout;
+//  true:  board-row-major rows r = y*24 + p*6 + x (the four positions' rows y side by side): a vertical step is +-24 rows and
+//         lands in the zero guard rows before / after the tile for y = 0 / y = 4, a horizontal step lands in the guard cell x = 5,
+//         so ONE buffer (25 guard rows + 128 + 25) serves all nine taps through the descriptor's start row: a third of the
+//         epilogue's shared-memory stores and of the buffer space.
+constexpr int G2 = 25, YROWS2 = 128 + 2 * G2, Y_LBO2 = YROWS2 * 16, Y_BUF2 = 4 * Y_LBO2;          // 11,392 B per half
+__host__ __device__ constexpr int c_yl(bool rowmaj) { return rowmaj ? Y_BUF2 : 3 * Y_COPY; }
+__host__ __device__ constexpr int c_planes(bool rowmaj) { return 2 * c_yl(rowmaj); }
+__host__ __device__ constexpr int c_valc(bool rowmaj) { return c_planes(rowmaj) + 1376; }
+__host__ __device__ constexpr int ctx_b(bool rowmaj) { return ((c_valc(rowmaj) + 512 + 127) / 128) * 128; }     // 51,840 / 24,704 B per context
 constexpr int NF = tcl::F_TOTAL - tcl::F_D1W, F_BYTES = ((NF * 4 + 15) / 16) * 16;
 constexpr int FO_D1W = 0, FO_D1B = 800, FO_VHW = 832, FO_VHB = 864;
-__host__ __device__ constexpr int s_wa(int nctx) { return nctx * CTX_B; }
-__host__ __device__ constexpr int s_wb(int nctx) { return s_wa(nctx) + B_A; }
-__host__ __device__ constexpr int s_wc(int nctx) { return s_wb(nctx) + B_B; }
-__host__ __device__ constexpr int s_ones(int nctx) { return s_wc(nctx) + B_C; }
-__host__ __device__ constexpr int s_f(int nctx) { return s_ones(nctx) + 128 * 16 * 2; }
-__host__ __device__ constexpr int s_total(int nctx) { return s_f(nctx) + F_BYTES; }
+__host__ __device__ constexpr int s_wa(int nctx, bool rowmaj) { return nctx * ctx_b(rowmaj); }
+__host__ __device__ constexpr int s_wb(int nctx, bool rowmaj) { return s_wa(nctx, rowmaj) + B_A; }
+__host__ __device__ constexpr int s_wc(int nctx, bool rowmaj) { return s_wb(nctx, rowmaj) + B_B; }
+__host__ __device__ constexpr int s_ones(int nctx, bool rowmaj) { return s_wc(nctx, rowmaj) + B_C; }
+__host__ __device__ constexpr int s_f(int nctx, bool rowmaj) { return s_ones(nctx, rowmaj) + 128 * 16 * 2; }
+__host__ __device__ constexpr int s_total(int nctx, bool rowmaj) { return s_f(nctx, rowmaj) + F_BYTES; }
 __host__ __device__ constexpr int tmem_cols(int nctx) { return nctx * 160 <= 256 ? 256 : 512; }
-static_assert(s_total(3) <= 227 * 1024, "three contexts fit in one SM's shared memory");
-static_assert(CTX_B % 128 == 0 && B_A % 128 == 0 && B_B % 128 == 0 && B_C % 128 == 0 && C_YL % 128 == 0 && C_PLANES % 16 == 0, "alignment");
+static_assert(s_total(3, false) <= 227 * 1024 && s_total(3, true) <= 227 * 1024, "three contexts fit in one SM's shared memory");
+static_assert(B_A % 128 == 0 && B_B % 128 == 0 && B_C % 128 == 0 && c_yl(false) % 128 == 0 && c_yl(true) % 128 == 0 && c_planes(false) % 16 == 0 && c_planes(true) % 16 == 0, "alignment");
 }  // namespace acm
 
-template <int NCTX, bool SPLIT_A>
+template <int NCTX, bool SPLIT_A, bool ROWMAJ>
 __global__ void __launch_bounds__(NCTX * acm::CTX_T, 1)
 k_net_trunk_accm(const uint8_t *__restrict__ wb, const float *__restrict__ fb, const uint8_t *__restrict__ planes, int64_t n,
                  uint8_t *__restrict__ polc_h, uint8_t *__restrict__ polc_l, float *__restrict__ value)
 {
     using namespace acm;
     constexpr bool FP16 = true;
-    constexpr int S_WA = s_wa(NCTX), S_WB = s_wb(NCTX), S_WC = s_wc(NCTX), S_ONES = s_ones(NCTX), S_F = s_f(NCTX);
+    constexpr int S_WA = s_wa(NCTX, ROWMAJ), S_WB = s_wb(NCTX, ROWMAJ), S_WC = s_wc(NCTX, ROWMAJ), S_ONES = s_ones(NCTX, ROWMAJ), S_F = s_f(NCTX, ROWMAJ);
+    constexpr int CTX_B = ctx_b(ROWMAJ), C_YH = 0, C_YL = c_yl(ROWMAJ), C_PLANES = c_planes(ROWMAJ), C_VALC = c_valc(ROWMAJ);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar[NCTX], barW[3];            // per context: MMAs of a phase done; weight slots A, B, C landed
     __shared__ unsigned slot_done[3];                  // contexts that have finished with a slot's current layer, cumulative
@@ -1124,7 +1137,7 @@ k_net_trunk_accm(const uint8_t *__restrict__ wb, const float *__restrict__ fb, c
     const int t = threadIdx.x & 255, warp = t >> 5, lane = t & 31;
     const int rg = warp & 3, h = warp >> 2;
     const int r = rg * 32 + lane;
-    const int p_local = r / POS_ROWS, rem = r % POS_ROWS, cy = rem / 6, cx = rem % 6;
+    const int p_local = ROWMAJ ? (r % 24) / 6 : r / POS_ROWS, cy = ROWMAJ ? r / 24 : (r % POS_ROWS) / 6, cx = r % 6;     // (30 and 24 are multiples of 6)
     const bool live = r < LIVE_ROWS && cx < 5;
     const int cell = cy * 5 + cx;
     const uint32_t sbase = umma::smem_u32(smem);
@@ -1207,7 +1220,8 @@ k_net_trunk_accm(const uint8_t *__restrict__ wb, const float *__restrict__ fb, c
     const uint32_t T_AOc = (uint32_t)(NCTX * 128 + ctx * 32), T_CHc = T_AOc, T_CLc = T_AOc + 16u;
     const uint32_t trow = tmem + ((uint32_t)(rg * 32) << 16);
     uint32_t phase = 0;
-    const umma::DescBase dYH = umma::desc_base(sbase + ctx * CTX_B + C_YH, Y_LBO, 128u), dYL = umma::desc_base(sbase + ctx * CTX_B + C_YL, Y_LBO, 128u);
+    constexpr int YLBO = ROWMAJ ? Y_LBO2 : Y_LBO;
+    const umma::DescBase dYH = umma::desc_base(sbase + ctx * CTX_B + C_YH, YLBO, 128u), dYL = umma::desc_base(sbase + ctx * CTX_B + C_YL, YLBO, 128u);
     const umma::DescBase dC1H = umma::desc_base(sbase + S_WB, 128u, 80 / 8 * 128u), dC1L = umma::desc_base(sbase + S_WB + hi_b(64, 64), 128u, 64 / 8 * 128u);
     const umma::DescBase dAH = umma::desc_base(sbase + S_WA, 128u, 80 / 8 * 128u), dAL = umma::desc_base(sbase + S_WA + hi_b(32, 64), 128u, 64 / 8 * 128u);
     const umma::DescBase dBH = umma::desc_base(sbase + S_WB, 128u, 304 / 8 * 128u);          // rows 0-31 hi, rows 32-63 lo
@@ -1328,12 +1342,12 @@ k_net_trunk_accm(const uint8_t *__restrict__ wb, const float *__restrict__ fb, c
                 // first and its three taps' MMAs are in flight while the other two copies are written (same MMA order).
                 auto store_copy = [&](int d) {
                     const int oy = cy - (d - 1);
-                    if (live && oy >= 0 && oy <= 4) {
-                        const int off = d * Y_COPY + (2 * h) * Y_LBO + (1 + r - 6 * (d - 1)) * 16;
+                    if (live && (ROWMAJ || (oy >= 0 && oy <= 4))) {
+                        const int off = ROWMAJ ? (2 * h) * YLBO + (G2 + r) * 16 : d * Y_COPY + (2 * h) * YLBO + (1 + r - 6 * (d - 1)) * 16;
                         *reinterpret_cast<uint4 *>(sctx + C_YH + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        *reinterpret_cast<uint4 *>(sctx + C_YH + off + Y_LBO) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                        *reinterpret_cast<uint4 *>(sctx + C_YH + off + YLBO) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
                         *reinterpret_cast<uint4 *>(sctx + C_YL + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                        *reinterpret_cast<uint4 *>(sctx + C_YL + off + Y_LBO) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                        *reinterpret_cast<uint4 *>(sctx + C_YL + off + YLBO) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
                     }
                 };
                 auto issue_taps = [&](int d0, int d1) {
@@ -1343,13 +1357,16 @@ k_net_trunk_accm(const uint8_t *__restrict__ wb, const float *__restrict__ fb, c
                         for (int dxi = 0; dxi < 3; dxi++)
 #pragma unroll
                             for (int ks = 0; ks < 2; ks++) {
-                                const uint32_t ao = (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * Y_LBO), wo = (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128);
+                                // input row = output row + 24 (or 6) * dy + dx, dy = d - 1, dx = dxi - 1: the start row of the A operand
+                                const uint32_t ao = ROWMAJ ? (uint32_t)((G2 + 24 * (d - 1) + (dxi - 1)) * 16 + 2 * ks * YLBO)
+                                                           : (uint32_t)(d * Y_COPY + dxi * 16 + 2 * ks * YLBO);
+                                const uint32_t wo = (uint32_t)(((d * 3 + dxi) * 32 / 8 + 2 * ks) * 128);
                                 umma::mma_bf16(tmem + T_BOc, umma::desc_at(dYH, ao), umma::desc_at(dBH, wo), ID64, true);
                                 umma::mma_bf16(tmem + T_BOc, umma::desc_at(dYL, ao), umma::desc_at(dBH, wo), ID32, true);
                             }
                 };
                 store_copy(0);
-                if (SPLIT_A) {
+                if (SPLIT_A && !ROWMAJ) {
                     smem_sync(); ACC_TS();
                     if (warp == 0) {
                         umma::fence_after_sync();
@@ -1361,13 +1378,12 @@ k_net_trunk_accm(const uint8_t *__restrict__ wb, const float *__restrict__ fb, c
                         __syncwarp();
                     }
                 }
-                store_copy(1);
-                store_copy(2);
+                if (!ROWMAJ) { store_copy(1); store_copy(2); }
                 smem_sync(); ACC_TS();
                 if (warp == 0) {
                     umma::fence_after_sync();
                     if (umma::elect_one()) {
-                        if (!SPLIT_A) {
+                        if (!SPLIT_A || ROWMAJ) {
                             umma::mbar_wait(&barW[1], phW1); phW1 ^= 1;
                             bias_mma(tmem + T_BOc, dBH, 288, ID64, false);
                             issue_taps(0, 1);
@@ -1609,12 +1625,11 @@ int ccx_net_load_acc(ccx_handle *h, const void *blob_host, int64_t blob_bytes)
     CCX_CUDA(h, cudaMemcpyAsync(a.wb, blob_host, acl::W_TOTAL, cudaMemcpyHostToDevice, h->stream));
     CCX_CUDA(h, cudaStreamSynchronize(h->stream));
     CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, acl::S_TOTAL));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(1)));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(2)));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(3)));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(1)));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(2)));
-    CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(3)));
+#define CCX_ACCM_ATTR(N, S, R) CCX_CUDA(h, cudaFuncSetAttribute(k_net_trunk_accm<N, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, acm::s_total(N, R)))
+    CCX_ACCM_ATTR(1, false, false); CCX_ACCM_ATTR(2, false, false); CCX_ACCM_ATTR(3, false, false);
+    CCX_ACCM_ATTR(1, true, false); CCX_ACCM_ATTR(2, true, false); CCX_ACCM_ATTR(3, true, false);
+    CCX_ACCM_ATTR(1, false, true); CCX_ACCM_ATTR(2, false, true); CCX_ACCM_ATTR(3, false, true);
+#undef CCX_ACCM_ATTR
     CCX_CUDA(h, cudaFuncSetAttribute(k_policy_dense_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, pda::S_TOTAL));
     return CCX_OK;
 }
@@ -1675,10 +1690,14 @@ int ccx_net_forward_acc_on(ccx_handle *h, cudaStream_t stream, int64_t cap, int6
         static const bool split_a = [] { const char *e = getenv("CCX_ACC_SPLIT"); return e ? atoi(e) != 0 : true; }();   // A/B: 0 = conv A's epilogue in one piece
         // a batch that leaves the higher contexts without a tile runs the smaller instantiation (shorter prologue, no register cap)
         const int nctx = !automatic ? acc_ctx : tiles <= h->num_sms ? 1 : tiles <= 2 * (int64_t)h->num_sms ? 2 : 3;
-#define CCX_ACCM_LAUNCH(N, S) k_net_trunk_accm<N, S><<<grid, N * acm::CTX_T, acm::s_total(N), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value)
-        if (nctx == 1) { if (split_a) CCX_ACCM_LAUNCH(1, true); else CCX_ACCM_LAUNCH(1, false); }
-        else if (nctx == 2) { if (split_a) CCX_ACCM_LAUNCH(2, true); else CCX_ACCM_LAUNCH(2, false); }
-        else { if (split_a) CCX_ACCM_LAUNCH(3, true); else CCX_ACCM_LAUNCH(3, false); }
+        // CCX_ACC_ROWS=0: position-major rows with three row-shifted copies of the 3x3 operand (k_net_trunk_acc's layout) for A/B
+        static const bool rowmaj = [] { const char *e = getenv("CCX_ACC_ROWS"); return e ? atoi(e) != 0 : true; }();
+#define CCX_ACCM_LAUNCH(N, S, R) k_net_trunk_accm<N, S, R><<<grid, N * acm::CTX_T, acm::s_total(N, R), stream>>>(a.wb, tc->fb, planes, n, polc_h, polc_l, value)
+#define CCX_ACCM_PICK(N) do { if (rowmaj) CCX_ACCM_LAUNCH(N, false, true); else if (split_a) CCX_ACCM_LAUNCH(N, true, false); else CCX_ACCM_LAUNCH(N, false, false); } while (0)
+        if (nctx == 1) CCX_ACCM_PICK(1);
+        else if (nctx == 2) CCX_ACCM_PICK(2);
+        else CCX_ACCM_PICK(3);
+#undef CCX_ACCM_PICK
 #undef CCX_ACCM_LAUNCH
     }
     CCX_LAUNCHED(h);
