@@ -67,3 +67,31 @@ def test_folded_packed_weights_equal_unfolded_graph():
     v = np.tanh(relu(relu(a @ Wv + bv).reshape(len(x), -1) @ W1 + b1) @ Wh + bh)[:, 0]
     assert off[0] == blob.size
     assert np.allclose(logits, g["logits"][:32], atol=2e-4) and np.allclose(v, g["v"][:32], atol=2e-5)
+
+
+def test_board_row_major_tile_rows_make_every_3x3_tap_a_row_shift():
+    """host model of k_net_trunk_accm's ROWMAJ operand buffer (csrc/ccx_net_tc.cu, namespace acm): rows r = y*24 + p*6 + x of a
+    four-position tile behind 25 zero guard rows, cells x = 5 and rows >= 120 never written.  For every output cell and every tap
+    (dy, dx) of the 3x3 'same' conv (model.py:128-132) the row r + 24*dy + dx must hold the input cell (y+dy, x+dx) of the SAME
+    position, or a zero when that cell is off the board — which is what lets one buffer serve all nine taps."""
+    G, ROWS = 25, 128
+    rng = np.random.default_rng(5)
+    act = rng.standard_normal((4, 5, 5))                       # one channel is enough: the layout is per row
+    buf = np.zeros(G + ROWS + G)
+    for p in range(4):
+        for y in range(5):
+            for x in range(5):
+                buf[G + y * 24 + p * 6 + x] = act[p, y, x]
+    for p in range(4):
+        for y in range(5):
+            for x in range(5):
+                r = y * 24 + p * 6 + x
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        src = G + r + 24 * dy + dx
+                        assert 0 <= src < len(buf)
+                        yy, xx = y + dy, x + dx
+                        want = act[p, yy, xx] if 0 <= yy < 5 and 0 <= xx < 5 else 0.0
+                        assert buf[src] == want, (p, y, x, dy, dx)
+    # the MMA reads 128 consecutive rows from start row G + 24*dy + dx: always inside the buffer
+    assert G - 24 - 1 >= 0 and G + 24 + 1 + ROWS <= len(buf)
