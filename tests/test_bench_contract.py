@@ -30,7 +30,7 @@ def validate_gpu_line(d, steps=None):
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    d = json.loads(open(os.path.join(ROOT, "profiles", "r02a_bench_1gpu.json")).read().strip().splitlines()[-1])
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02j_bench.json")).read().strip().splitlines()[-1])
     validate_gpu_line(d)
     assert d["clocks"]["samples"] >= 10                     # NVML sampler: tens of samples inside a 70 ms timed region
     assert d["cpu_baseline"]["kind"] == "reference"         # the unmodified Python reference ran on the GPU box's host
